@@ -1,0 +1,679 @@
+// libhc_b200: kernels + C ABI (include/hc_b200.h).
+//
+// One persistent kernel per batch: grid = #SMs x resident CTAs, one solution path per thread,
+// all lanes pull path indices from a device-side atomic queue (the `next_k` work counter of
+// threaded_solve, reference src/solve.jl:641, 660-667, moved onto the device) and write their
+// PathResult by path index (src/solve.jl:637, 670).
+//
+// With -DHC_HOST_SIM the same host logic and the same device headers are compiled by g++ into
+// tests/host_sim/libhc_sim.so, which runs the lane state machine sequentially on the CPU.  That
+// library exists only so that kernel logic can be unit-tested in a container without a GPU; it is
+// never linked into, loaded by, or reachable from libhc_b200.so.
+#include "../../include/hc_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "hc_lane.h"
+
+#ifndef HC_HOST_SIM
+#include <cuda_runtime.h>
+#endif
+
+using namespace hc;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local hc_timing g_timing;
+std::mutex g_mutex;
+
+int fail(const std::string& msg) { g_err = msg; return -1; }
+
+// ------------------------------------------------------------------ backend
+#ifndef HC_HOST_SIM
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) throw std::string(#call) + ": " + cudaGetErrorString(e_);            \
+    } while (0)
+void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
+void dev_free(void* p) { if (p) cudaFree(p); }
+void h2d(void* d, const void* h, size_t bytes) { if (bytes) CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); }
+void d2h(void* h, const void* d, size_t bytes) { if (bytes) CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); }
+void dev_zero(void* d, size_t bytes) { if (bytes) CK(cudaMemset(d, 0, bytes)); }
+#else
+void* dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 16, 1); }
+void dev_free(void* p) { free(p); }
+void h2d(void* d, const void* h, size_t bytes) { if (bytes) memcpy(d, h, bytes); }
+void d2h(void* h, const void* d, size_t bytes) { if (bytes) memcpy(h, d, bytes); }
+void dev_zero(void* d, size_t bytes) { if (bytes) memset(d, 0, bytes); }
+#endif
+
+template <class T>
+T* to_dev(const std::vector<T>& v) {
+    T* d = (T*)dev_alloc(v.size() * sizeof(T));
+    h2d(d, v.data(), v.size() * sizeof(T));
+    return d;
+}
+
+// ------------------------------------------------------------------ handles
+struct ProgramH {
+    DevProgram dev;  // pointers into device memory
+    int L = 0;
+    std::vector<void*> owned;
+    ~ProgramH() { for (void* p : owned) dev_free(p); }
+};
+struct SystemH {
+    ProgramH eval, jac;
+    int m = 0, n = 0, P = 0;
+};
+struct HomotopyH {
+    DevHomotopy dev;
+    SystemH* F = nullptr; SystemH* G = nullptr;
+    std::vector<void*> owned;
+    std::vector<double> tw_hook;  // weights set through hc_toric_set_weights (test hook)
+    ~HomotopyH() { for (void* p : owned) dev_free(p); }
+};
+
+bool supported_op(int op) {
+    switch (op) {
+        case OP_STOP: case OP_CB: case OP_INV: case OP_INV_NOT_ZERO: case OP_INVSQR: case OP_NEG: case OP_SQR:
+        case OP_IDENTITY: case OP_ADD: case OP_DIV: case OP_MUL: case OP_SUB: case OP_POW_INT: case OP_ADD3:
+        case OP_MUL3: case OP_MULADD: case OP_MULSUB: case OP_SUBMUL: case OP_ADD4: case OP_MUL4:
+        case OP_MULMULADD: case OP_MULMULSUB: return true;
+        default: return false;
+    }
+}
+
+// Repack the reference's 24-byte, 1-based Instruction stream into 16-byte, 0-based PInstr.
+void build_program(ProgramH& H, const hc_program_desc* d) {
+    if (d->tape_space >= 65536) throw std::string("tape_space >= 65536 is not supported by the packed format");
+    std::vector<PInstr> ins(d->n_instructions);
+    bool stopped = false;
+    for (int i = 0; i < d->n_instructions; ++i) {
+        const int32_t* s = d->instructions + 6 * (size_t)i;
+        int op = s[4];
+        if (!supported_op(op)) throw std::string("unsupported op in tape: ") + std::to_string(op);
+        PInstr I;
+        if (op == OP_STOP) { I.w0 = OP_STOP; I.w1 = I.w2 = 0; I.lit = 0; ins[i] = I; stopped = true; ins.resize(i + 1); break; }
+        auto slot = [&](int v) {
+            if (v < 1 || v > d->tape_space) throw std::string("tape index out of range");
+            return (uint32_t)(v - 1);
+        };
+        uint32_t a0 = slot(s[0]);
+        uint32_t a1 = (op == OP_POW_INT) ? a0 : slot(s[1]);
+        uint32_t a2 = slot(op == OP_POW_INT ? s[0] : s[2]), a3 = slot(op == OP_POW_INT ? s[0] : s[3]);
+        uint32_t out = slot(s[5]);
+        if ((int)out < d->n_constants) throw std::string("instruction writes into the constants block");
+        I.w0 = (uint32_t)op | (out << 8);
+        I.w1 = a0 | (a1 << 16);
+        I.w2 = a2 | (a3 << 16);
+        I.lit = (op == OP_POW_INT) ? s[1] : 0;
+        ins[i] = I;
+    }
+    if (!stopped) throw std::string("tape is not terminated by OP_STOP");
+    std::vector<cx> consts(d->n_constants);
+    for (int i = 0; i < d->n_constants; ++i) consts[i] = mk(d->constants[2 * i], d->constants[2 * i + 1]);
+    std::vector<int2> ua(d->n_u), Ua(d->n_U);
+    for (int i = 0; i < d->n_u; ++i) {
+        ua[i].x = d->u_assign[2 * i] - 1; ua[i].y = d->u_assign[2 * i + 1] - 1;
+        if (ua[i].x < 0 || ua[i].x >= d->out_dim || ua[i].y < 0 || ua[i].y >= d->tape_space) throw std::string("bad u assignment");
+    }
+    for (int i = 0; i < d->n_U; ++i) {
+        Ua[i].x = d->U_assign[2 * i] - 1; Ua[i].y = d->U_assign[2 * i + 1] - 1;
+        if (Ua[i].x < 0 || Ua[i].x >= d->out_dim * d->n_vars || Ua[i].y < 0 || Ua[i].y >= d->tape_space) throw std::string("bad U assignment");
+    }
+    if (d->param_offset < d->n_constants || d->var_offset < d->n_constants) throw std::string("inputs overlap the constants block");
+    DevProgram& P = H.dev;
+    P.instr = to_dev(ins); P.consts = to_dev(consts); P.u_assign = to_dev(ua); P.U_assign = to_dev(Ua);
+    H.owned = {(void*)P.instr, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign};
+    H.L = (int)ins.size();
+    P.C = d->n_constants; P.param_off = d->param_offset; P.P = d->n_params;
+    P.t_slot = d->t_index > 0 ? d->t_index - 1 : -1;
+    P.var_off = d->var_offset; P.n = d->n_vars; P.out_dim = d->out_dim; P.W = d->tape_space;
+    P.nu = d->n_u; P.nU = d->n_U;
+}
+
+cx* cvec_dev(const double* p, int n, std::vector<void*>& owned) {
+    std::vector<cx> v(n);
+    for (int i = 0; i < n; ++i) v[i] = mk(p[2 * i], p[2 * i + 1]);
+    cx* d = to_dev(v);
+    owned.push_back(d);
+    return d;
+}
+
+DevOptions to_dev_options(const hc_options* o) {
+    DevOptions D;
+    static_assert(sizeof(DevOptions) == sizeof(hc_options), "hc_options / DevOptions layout mismatch");
+    memcpy(&D, o, sizeof(D));
+    return D;
+}
+
+// ------------------------------------------------------------------ kernels
+struct KArgs {
+    DevHomotopy H;
+    DevOptions O;
+    BatchIn B;
+    DevResults R;
+    cx* cslab; double* rslab; int* islab;
+    unsigned long long* queue;
+    int stage;  // 1: copy the tapes into shared memory
+    int static_sched;  // debug: 1 = lane l tracks paths l, l + T, ... instead of pulling from the queue
+};
+
+#ifndef HC_HOST_SIM
+extern __shared__ __align__(16) unsigned char hc_smem[];
+
+template <class T>
+__device__ const T* stage_array(const T* src, int count, unsigned char*& cur) {
+    size_t bytes = ((size_t)count * sizeof(T) + 15) & ~(size_t)15;
+    T* dst = reinterpret_cast<T*>(cur);
+    const int words = (int)(bytes / 4);
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    const int valid = (int)(((size_t)count * sizeof(T)) / 4);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = i < valid ? s[i] : 0u;
+    cur += bytes;
+    return dst;
+}
+__device__ void stage_program(DevProgram& P, int L, unsigned char*& cur) {
+    P.instr = stage_array(P.instr, L, cur);
+    P.consts = stage_array(P.consts, P.C, cur);
+    P.u_assign = stage_array(P.u_assign, P.nu, cur);
+    P.U_assign = stage_array(P.U_assign, P.nU, cur);
+}
+
+struct StageLens { int LFe, LFj, LGe, LGj; };
+
+__global__ void __launch_bounds__(128) hc_track_kernel(const __grid_constant__ KArgs A, const StageLens SL) {
+    __shared__ KArgs sA;
+    if (threadIdx.x == 0) sA = A;
+    __syncthreads();
+    if (A.stage) {
+        DevHomotopy h = A.H;  // every thread computes the same pointers
+        unsigned char* cur = hc_smem;
+        stage_program(h.Fe, SL.LFe, cur);
+        stage_program(h.Fj, SL.LFj, cur);
+        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, SL.LGe, cur); stage_program(h.Gj, SL.LGj, cur); }
+        __syncthreads();
+        if (threadIdx.x == 0) sA.H = h;
+        __syncthreads();
+    }
+    Lane L;
+    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
+    const int T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, T, tid);
+    L.phase = PH_IDLE;
+    bool drained = false;
+    const long long N = sA.B.N;
+    long long next_static = tid;
+    while (true) {
+        if (L.phase == PH_IDLE && !drained) {
+            long long k;
+            if (A.static_sched) { k = next_static; next_static += T; }
+            else k = (long long)atomicAdd(A.queue, 1ULL);
+            if (k < N) L.start_path(k, sA.B, sA.R);
+            else drained = true;
+        }
+        if (__all_sync(0xffffffffu, L.phase == PH_IDLE && drained)) break;
+        if (L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
+    }
+}
+
+// single-lane operator-API hooks
+__global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, const cx* xlo, cx t, const double* tw, cx* u, cx* U) {
+    __shared__ KArgs sA;
+    sA = A;
+    Lane L;
+    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = 0; L.kind = sA.H.kind;
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, 1, 0);
+    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_taylor = 0;
+    const int n = sA.H.n;
+    if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
+    if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
+    else for (int i = 0; i < n; ++i) L.M.x[i] = x[i];
+    if (what == 0) L.eval_f64(L.M.u, nullptr, L.M.x, t);
+    else if (what == 1) { for (int i = 0; i < n; ++i) L.M.xhat[i] = xlo[i]; L.eval_dd(L.M.u, L.M.x, &L.M.xhat, t); }
+    else if (what == 2) L.eval_f64(L.M.u, &L.M.A, L.M.x, t);
+    else {
+        if (K == 1) L.taylor<1>(L.M.u, L.M.tx, t);
+        else if (K == 2) L.taylor<2>(L.M.u, L.M.tx, t);
+        else if (K == 3) L.taylor<3>(L.M.u, L.M.tx, t);
+        else L.taylor<4>(L.M.u, L.M.tx, t);
+    }
+    for (int i = 0; i < n; ++i) u[i] = L.M.u[i];
+    if (what == 2) for (int i = 0; i < n * n; ++i) U[i] = L.M.A[i];
+}
+
+__global__ void hc_dfma_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+#endif  // !HC_HOST_SIM
+
+// ------------------------------------------------------------------ launch planning
+struct Plan { int grid, block, lanes; size_t smem; int stage; MemSizes sz; };
+
+int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
+
+size_t program_stage_bytes(const ProgramH& P) {
+    auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    return r16((size_t)P.L * sizeof(PInstr)) + r16((size_t)P.dev.C * sizeof(cx)) + r16((size_t)P.dev.nu * sizeof(int2)) +
+           r16((size_t)P.dev.nU * sizeof(int2));
+}
+
+Plan make_plan(const HomotopyH& H, long long N) {
+    Plan p;
+    PathMem dummy;
+    p.sz = carve(dummy, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr, nullptr, 1, 0);
+#ifndef HC_HOST_SIM
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    p.block = env_int("HC_B200_BLOCK", 64);
+    int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 4);
+    long long want = (N + p.block - 1) / p.block;
+    // few paths: spread them over the SMs with one-warp CTAs
+    if (want < sms && p.block > 32) { p.block = 32; want = (N + 31) / 32; }
+    long long cap = (long long)sms * per_sm;
+    p.grid = (int)(want < cap ? want : cap);
+    if (p.grid < 1) p.grid = 1;
+    p.smem = program_stage_bytes(H.F->eval) + program_stage_bytes(H.F->jac);
+    if (H.dev.kind == H_STRAIGHT_LINE) p.smem += program_stage_bytes(H.G->eval) + program_stage_bytes(H.G->jac);
+    p.stage = (p.smem <= (size_t)env_int("HC_B200_STAGE_MAX", 96 * 1024)) && env_int("HC_B200_STAGE", 1);
+    if (!p.stage) p.smem = 0;
+#else
+    (void)N;
+    p.block = 1; p.grid = 1; p.smem = 0; p.stage = 0;
+#endif
+    p.lanes = p.grid * p.block;
+    return p;
+}
+
+struct DeviceBatch {  // device-resident inputs, outputs and lane slabs of one batch
+    HomotopyH* H = nullptr;
+    int mode = 0; long long N = 0; int n = 0;
+    KArgs A;
+    Plan plan;
+    std::vector<void*> owned;
+    int64_t h2d_bytes = 0;
+    ~DeviceBatch() { for (void* p : owned) dev_free(p); }
+    template <class T> T* alloc(size_t count) { T* p = (T*)dev_alloc(count * sizeof(T)); owned.push_back(p); return p; }
+    template <class T> T* upload(const T* h, size_t count) {
+        T* p = alloc<T>(count); h2d(p, h, count * sizeof(T)); h2d_bytes += (int64_t)(count * sizeof(T)); return p;
+    }
+};
+
+void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1,
+                 const double* t0, const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
+                 const double* cell_weights, int ncells) {
+    D.H = H; D.mode = mode; D.N = N; D.n = H->dev.n;
+    const int n = D.n, P = H->dev.P;
+    memset(&D.A, 0, sizeof(D.A));
+    D.A.H = H->dev;
+    D.A.H.N = N;
+    D.A.O = to_dev_options(o);
+    BatchIn& B = D.A.B;
+    B.mode = mode; B.N = N;
+    B.starts = (const cx*)D.upload<double>(starts, (size_t)2 * n * N);
+    B.t1 = t1 ? mk(t1[0], t1[1]) : mk(1.0); B.t0 = t0 ? mk(t0[0], t0[1]) : mk(0.0);
+    B.omega_mu = omega_mu ? D.upload<double>(omega_mu, (size_t)2 * N) : nullptr;
+    auto transpose_params = [&](const double* src) {  // (P x N, path-major) -> [i * N + path]
+        std::vector<double> tmp((size_t)2 * P * N);
+        for (long long k = 0; k < N; ++k)
+            for (int i = 0; i < P; ++i) {
+                tmp[2 * ((size_t)i * N + k)] = src[2 * ((size_t)k * P + i)];
+                tmp[2 * ((size_t)i * N + k) + 1] = src[2 * ((size_t)k * P + i) + 1];
+            }
+        return (const cx*)D.upload<double>(tmp.data(), tmp.size());
+    };
+    D.A.H.path_p = path_p ? transpose_params(path_p) : nullptr;
+    D.A.H.path_q = path_q ? transpose_params(path_q) : nullptr;
+    if (mode == MODE_POLYHEDRAL) {
+        B.cell_index = D.upload<int32_t>(cell_index, (size_t)N);
+        B.cell_weights = D.upload<double>(cell_weights, (size_t)ncells * P);
+    }
+    DevResults& R = D.A.R;
+    R.return_code = D.alloc<int>(N); R.solution = D.alloc<cx>((size_t)n * N); R.t = D.alloc<double>(N);
+    R.accuracy = D.alloc<double>(N); R.residual = D.alloc<double>(N); R.singular = D.alloc<unsigned char>(N);
+    R.condition_jacobian = D.alloc<double>(N); R.winding_number = D.alloc<int>(N);
+    R.extended_precision = D.alloc<unsigned char>(N); R.last_point = D.alloc<cx>((size_t)n * N); R.last_t = D.alloc<double>(N);
+    R.valuation = D.alloc<double>((size_t)n * N); R.has_valuation = D.alloc<unsigned char>(N); R.omega = D.alloc<double>(N);
+    R.mu = D.alloc<double>(N); R.accepted_steps = D.alloc<int>(N); R.rejected_steps = D.alloc<int>(N);
+    R.steps_eg = D.alloc<int>(N); R.extended_precision_used = D.alloc<unsigned char>(N);
+    R.counters = D.alloc<long long>((size_t)8 * N);
+    D.plan = make_plan(*H, N);
+    const Plan& pl = D.plan;
+    D.A.cslab = D.alloc<cx>(pl.sz.ncx * pl.lanes);
+    D.A.rslab = D.alloc<double>(pl.sz.nre * pl.lanes);
+    D.A.islab = D.alloc<int>(pl.sz.nint * pl.lanes);
+    D.A.queue = D.alloc<unsigned long long>(1);
+    D.A.stage = pl.stage;
+    D.A.static_sched = env_int("HC_B200_STATIC_SCHED", 0);
+}
+
+// runs the batch once; returns kernel milliseconds
+double run_batch(DeviceBatch& D) {
+    dev_zero(D.A.queue, sizeof(unsigned long long));
+#ifndef HC_HOST_SIM
+    StageLens SL;
+    SL.LFe = D.H->F->eval.L; SL.LFj = D.H->F->jac.L;
+    SL.LGe = D.H->G ? D.H->G->eval.L : 0; SL.LGj = D.H->G ? D.H->G->jac.L : 0;
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, 0));
+    hc_track_kernel<<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A, SL);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+#else
+    Lane L;
+    L.H = &D.A.H; L.O = &D.A.O; L.n = D.A.H.n;
+    carve(L.M, D.A.H.n, D.A.H.P, D.A.H.tape_cx, D.A.cslab, D.A.rslab, D.A.islab, 1, 0);
+    for (long long k = 0; k < D.N; ++k) {
+        L.phase = PH_IDLE;
+        L.start_path(k, D.A.B, D.A.R);
+        while (L.phase != PH_IDLE) L.iterate(D.A.B, D.A.R);
+    }
+    return 0.0;
+#endif
+}
+
+void fetch_results(DeviceBatch& D, hc_results* out) {
+    const DevResults& R = D.A.R;
+    const size_t N = (size_t)D.N, n = (size_t)D.n;
+    d2h(out->return_code, R.return_code, N * 4); d2h(out->solution, R.solution, n * N * 16); d2h(out->t, R.t, N * 8);
+    d2h(out->accuracy, R.accuracy, N * 8); d2h(out->residual, R.residual, N * 8); d2h(out->singular, R.singular, N);
+    d2h(out->condition_jacobian, R.condition_jacobian, N * 8); d2h(out->winding_number, R.winding_number, N * 4);
+    d2h(out->extended_precision, R.extended_precision, N); d2h(out->last_point, R.last_point, n * N * 16);
+    d2h(out->last_t, R.last_t, N * 8); d2h(out->valuation, R.valuation, n * N * 8); d2h(out->has_valuation, R.has_valuation, N);
+    d2h(out->omega, R.omega, N * 8); d2h(out->mu, R.mu, N * 8); d2h(out->accepted_steps, R.accepted_steps, N * 4);
+    d2h(out->rejected_steps, R.rejected_steps, N * 4); d2h(out->steps_eg, R.steps_eg, N * 4);
+    d2h(out->extended_precision_used, R.extended_precision_used, N);
+    if (out->counters) d2h(out->counters, R.counters, N * 64);
+}
+int64_t result_bytes(long long N, int n, bool counters) {
+    return (int64_t)N * (4 + 16 * n + 8 + 8 + 8 + 1 + 8 + 4 + 1 + 16 * n + 8 + 8 * n + 1 + 8 + 8 + 4 + 4 + 4 + 1 + (counters ? 64 : 0));
+}
+
+double now_ms() {
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// A polyhedral batch runs on a merged homotopy: the toric stage and the coefficient stage share F;
+// p = start coefficients (toric system coefficients), q = target coefficients.
+HomotopyH* merged_polyhedral(HomotopyH* toric, HomotopyH* coeff) {
+    if (toric->F != coeff->F) throw std::string("toric and coefficient homotopy must share the system handle");
+    if (toric->dev.kind != H_TORIC || coeff->dev.kind != H_COEFFICIENT) throw std::string("expected (toric, coefficient) homotopies");
+    return coeff;  // coeff.p are the start coefficients == toric system coefficients (src/polyhedral.jl:397-406)
+}
+
+int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1, const double* t0,
+               const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
+               const double* cell_weights, int ncells, hc_results* out) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try {
+        if (N <= 0) return 0;
+        double tA = now_ms();
+        DeviceBatch D;
+        setup_batch(D, H, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, cell_index, cell_weights, ncells);
+#ifndef HC_HOST_SIM
+        CK(cudaDeviceSynchronize());
+#endif
+        double tB = now_ms();
+        double kms = run_batch(D);
+        double tC = now_ms();
+        fetch_results(D, out);
+        double tD = now_ms();
+        g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
+        g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
+        g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.lanes;
+        g_timing.slab_bytes = (int64_t)D.plan.lanes * (int64_t)(D.plan.sz.ncx * 16 + D.plan.sz.nre * 8 + D.plan.sz.nint * 4);
+    } catch (const std::string& e) { return fail(e); }
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* hc_last_error(void) { return g_err.c_str(); }
+
+int32_t hc_init(int32_t device) {
+#ifndef HC_HOST_SIM
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail("no CUDA device available (libhc_b200 has no CPU fallback)");
+    if (device < 0 || device >= count) return fail("invalid device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceSetLimit(cudaLimitStackSize, (size_t)env_int("HC_B200_STACK", 8192));
+#else
+    (void)device;
+#endif
+    return 0;
+}
+
+void hc_options_default(hc_options* o) {
+    // TrackerOptions / TrackerParameters (src/tracker.jl:45-62, 105-115)
+    o->max_steps = 10000; o->max_step_size = HC_INF; o->max_initial_step_size = HC_INF; o->extended_precision = 1;
+    o->min_step_size = 1e-48; o->min_rel_step_size = 0.0;
+    o->a = 0.125; o->beta_a = 1.0; o->beta_omega_p = 3.0; o->beta_tau = 0.4; o->strict_beta_tau = 0.3; o->min_newton_iters = 2;
+    // EndgameOptions (src/endgame_tracker.jl:47-72)
+    o->endgame_start = 0.1; o->max_endgame_steps = 2000; o->max_endgame_extended_steps = 400;
+    o->min_cond = 1e6; o->min_cond_growth = 1e4; o->min_coord_growth = 100.0;
+    o->zero_is_at_infinity = 0; o->at_infinity_check = 1; o->only_nonsingular = 0;
+    o->singular_min_accuracy = 1e-6; o->max_winding_number = 6;
+    o->val_finite_tol = 0.05; o->val_at_infinity_tol = 0.01; o->sing_cond = 1e14; o->sing_accuracy = 1e-12;
+    o->scaling_threshold = -30.0; o->refine_steps = 3;
+    // WeightedNormOptions (src/norm.jl:36-40)
+    o->scale_min = 1e-4; o->scale_abs_min = 1e-6; o->scale_max = 6.703903964971299e153;
+}
+
+void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac) {
+    SystemH* S = nullptr;
+    try {
+        if (eval->n_vars != jac->n_vars || eval->out_dim != jac->out_dim || eval->n_params != jac->n_params)
+            throw std::string("eval and Jacobian tapes disagree on dimensions");
+        if (eval->out_dim != eval->n_vars) throw std::string("only square systems are supported");
+        S = new SystemH();
+        build_program(S->eval, eval);
+        build_program(S->jac, jac);
+        S->m = eval->out_dim; S->n = eval->n_vars; S->P = eval->n_params;
+    } catch (const std::string& e) { delete S; fail(e); return nullptr; }
+    return S;
+}
+void hc_system_destroy(void* s) { delete (SystemH*)s; }
+
+void* hc_homotopy_create(const hc_homotopy_desc* d) {
+    HomotopyH* H = nullptr;
+    try {
+        if (!d->F) throw std::string("homotopy needs a system F");
+        H = new HomotopyH();
+        H->F = (SystemH*)d->F; H->G = (SystemH*)d->G;
+        DevHomotopy& D = H->dev;
+        memset(&D, 0, sizeof(D));
+        D.kind = d->kind; D.n = H->F->n; D.P = H->F->P;
+        D.Fe = H->F->eval.dev; D.Fj = H->F->jac.dev;
+        D.gamma = mk(d->gamma[0], d->gamma[1]);
+        int W = H->F->jac.dev.W, We = H->F->eval.dev.W;
+        if (d->kind == HC_STRAIGHT_LINE) {
+            if (!H->G) throw std::string("straight-line homotopy needs a start system G");
+            if (H->G->n != H->F->n) throw std::string("G and F have different sizes");
+            if (d->n_G_params != H->G->P || d->n_F_params != H->F->P) throw std::string("wrong number of fixed parameters");
+            D.Ge = H->G->eval.dev; D.Gj = H->G->jac.dev;
+            static const double dummy[2] = {0, 0};
+            D.G_params = cvec_dev(d->n_G_params ? d->G_params : dummy, d->n_G_params ? d->n_G_params : 1, H->owned);
+            D.F_params = cvec_dev(d->n_F_params ? d->F_params : dummy, d->n_F_params ? d->n_F_params : 1, H->owned);
+            if (H->G->jac.dev.W > W) W = H->G->jac.dev.W;
+            if (H->G->eval.dev.W > We) We = H->G->eval.dev.W;
+        } else {
+            if (d->n_pq != H->F->P) throw std::string("wrong number of parameters");
+            static const double dummy[2] = {0, 0};
+            D.p = cvec_dev(d->n_pq ? d->p : dummy, d->n_pq ? d->n_pq : 1, H->owned);
+            if (d->kind != HC_TORIC) D.q = cvec_dev(d->n_pq ? d->q : dummy, d->n_pq ? d->n_pq : 1, H->owned);
+        }
+        // tape region (cx units): Jacobian tape, DD eval tape (2x), order-3 Taylor eval tape (4x; hooks may ask order 4)
+        int need = W;
+        if (2 * We > need) need = 2 * We;
+        if (5 * We > need) need = 5 * We;
+        D.tape_cx = need + 2;
+    } catch (const std::string& e) { delete H; fail(e); return nullptr; }
+    return H;
+}
+void hc_homotopy_destroy(void* h) { delete (HomotopyH*)h; }
+
+int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, const double* starts, const double* t1,
+                       const double* t0, const double* path_p, const double* path_q, const double* omega_mu, hc_results* out,
+                       int32_t) {
+    if (mode != MODE_ENDGAME && mode != MODE_TRACKER) return fail("mode must be 0 (endgame tracker) or 1 (tracker)");
+    HomotopyH* h = (HomotopyH*)H;
+    if (h->dev.kind == H_TORIC) return fail("toric homotopies are tracked through hc_polyhedral_track_batch");
+    return track_impl(h, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, nullptr, nullptr, 0, out);
+}
+
+int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* o, int64_t N, const double* starts,
+                                  const int32_t* cell_index, const double* cell_weights, int32_t ncells, hc_results* out, int32_t) {
+    try {
+        HomotopyH* h = merged_polyhedral((HomotopyH*)Htoric, (HomotopyH*)Hcoeff);
+        return track_impl(h, o, MODE_POLYHEDRAL, N, starts, nullptr, nullptr, nullptr, nullptr, nullptr, cell_index, cell_weights, ncells, out);
+    } catch (const std::string& e) { return fail(e); }
+}
+
+void hc_get_timing(hc_timing* t) { *t = g_timing; }
+
+void* hc_resident_create(void* H, void* Hcoeff, const hc_options* o, int32_t mode, int64_t N, const double* starts, const double* t1,
+                         const double* t0, const double* path_p, const double* path_q, const int32_t* cell_index,
+                         const double* cell_weights, int32_t ncells) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceBatch* D = nullptr;
+    try {
+        HomotopyH* h = (HomotopyH*)H;
+        if (mode == MODE_POLYHEDRAL) h = merged_polyhedral((HomotopyH*)H, (HomotopyH*)Hcoeff);
+        D = new DeviceBatch();
+        setup_batch(*D, h, o, mode, N, starts, t1, t0, path_p, path_q, nullptr, cell_index, cell_weights, ncells);
+    } catch (const std::string& e) { delete D; fail(e); return nullptr; }
+    return D;
+}
+int32_t hc_resident_run(void* r, double* kernel_ms) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try { double ms = run_batch(*(DeviceBatch*)r); if (kernel_ms) *kernel_ms = ms; }
+    catch (const std::string& e) { return fail(e); }
+    return 0;
+}
+int32_t hc_resident_fetch(void* r, hc_results* out) {
+    try { fetch_results(*(DeviceBatch*)r, out); } catch (const std::string& e) { return fail(e); }
+    return 0;
+}
+void hc_resident_destroy(void* r) { delete (DeviceBatch*)r; }
+
+// ------------------------------------------------------------------ operator API hooks
+static int hook(void* Hv, int what, int K, const double* x, const double* xlo, const double* t, double* u, double* U) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try {
+        HomotopyH* H = (HomotopyH*)Hv;
+        const int n = H->dev.n, P = H->dev.P;
+        hc_options o; hc_options_default(&o);
+        KArgs A; memset(&A, 0, sizeof(A));
+        A.H = H->dev; A.H.N = 1; A.O = to_dev_options(&o);
+        PathMem dummy;
+        MemSizes sz = carve(dummy, n, P, A.H.tape_cx, nullptr, nullptr, nullptr, 1, 0);
+        std::vector<void*> owned;
+        auto A_ = [&](size_t b) { void* p = dev_alloc(b); owned.push_back(p); return p; };
+        A.cslab = (cx*)A_(sz.ncx * 16); A.rslab = (double*)A_(sz.nre * 8); A.islab = (int*)A_(sz.nint * 4);
+        const int nx = what == 3 ? K * n : n;
+        cx* dx = (cx*)A_((size_t)nx * 16); h2d(dx, x, (size_t)nx * 16);
+        cx* dlo = nullptr;
+        if (xlo) { dlo = (cx*)A_((size_t)n * 16); h2d(dlo, xlo, (size_t)n * 16); }
+        double* dtw = nullptr;
+        if (!H->tw_hook.empty()) { dtw = (double*)A_((size_t)P * 8); h2d(dtw, H->tw_hook.data(), (size_t)P * 8); }
+        cx* du = (cx*)A_((size_t)n * 16);
+        cx* dU = (cx*)A_((size_t)n * n * 16);
+        cx tt = mk(t[0], t[1]);
+#ifndef HC_HOST_SIM
+        hc_hook_kernel<<<1, 1>>>(A, what, K, dx, dlo, tt, dtw, du, dU);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+#else
+        Lane L;
+        L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = 0; L.kind = A.H.kind;
+        carve(L.M, n, P, A.H.tape_cx, A.cslab, A.rslab, A.islab, 1, 0);
+        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_taylor = 0;
+        if (dtw) for (int i = 0; i < P; ++i) L.M.tw[i] = dtw[i];
+        if (what == 3) for (int i = 0; i < K * n; ++i) L.M.tx[i] = dx[i]; else for (int i = 0; i < n; ++i) L.M.x[i] = dx[i];
+        if (what == 0) L.eval_f64(L.M.u, nullptr, L.M.x, tt);
+        else if (what == 1) { for (int i = 0; i < n; ++i) L.M.xhat[i] = dlo[i]; L.eval_dd(L.M.u, L.M.x, &L.M.xhat, tt); }
+        else if (what == 2) L.eval_f64(L.M.u, &L.M.A, L.M.x, tt);
+        else if (K == 1) L.taylor<1>(L.M.u, L.M.tx, tt);
+        else if (K == 2) L.taylor<2>(L.M.u, L.M.tx, tt);
+        else if (K == 3) L.taylor<3>(L.M.u, L.M.tx, tt);
+        else L.taylor<4>(L.M.u, L.M.tx, tt);
+        for (int i = 0; i < n; ++i) du[i] = L.M.u[i];
+        if (what == 2) for (int i = 0; i < n * n; ++i) dU[i] = L.M.A[i];
+#endif
+        d2h(u, du, (size_t)n * 16);
+        if (U) d2h(U, dU, (size_t)n * n * 16);
+        for (void* p : owned) dev_free(p);
+    } catch (const std::string& e) { return fail(e); }
+    return 0;
+}
+int32_t hc_evaluate(void* H, const double* x, const double* t, double* u) { return hook(H, 0, 0, x, nullptr, t, u, nullptr); }
+int32_t hc_evaluate_dd(void* H, const double* x_hi, const double* x_lo, const double* t, double* u) { return hook(H, 1, 0, x_hi, x_lo, t, u, nullptr); }
+int32_t hc_evaluate_and_jacobian(void* H, const double* x, const double* t, double* u, double* U) { return hook(H, 2, 0, x, nullptr, t, u, U); }
+int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double* u) {
+    if (K < 1 || K > 4) return fail("taylor order must be 1..4");
+    return hook(H, 3, K, tx, nullptr, t, u, nullptr);
+}
+int32_t hc_toric_set_weights(void* Hv, const double* w) {
+    HomotopyH* H = (HomotopyH*)Hv;
+    H->tw_hook.assign(w, w + H->dev.P);
+    return 0;
+}
+
+double hc_dfma_peak(int32_t iters) {
+#ifndef HC_HOST_SIM
+    try {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int block = 256, grid = sms * 8;
+        double* out = (double*)dev_alloc((size_t)grid * block * 8);
+        hc_dfma_kernel<<<grid, block>>>(out, 1000);
+        CK(cudaDeviceSynchronize());
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, 0));
+        hc_dfma_kernel<<<grid, block>>>(out, iters);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        dev_free(out);
+        return 2.0 * 8.0 * (double)iters * grid * block / (ms * 1e-3) / 1e9;
+    } catch (const std::string& e) { fail(e); return -1.0; }
+#else
+    (void)iters;
+    return -1.0;
+#endif
+}
+
+}  // extern "C"

@@ -1,0 +1,503 @@
+// The lane state machine: one flat loop iteration = (at most) one tracker step for every active
+// lane of the warp, so all lanes stay converged on the expensive primitive (predict + Newton +
+// predictor update) while the cheap phase logic around it diverges.  A lane whose path ends
+// writes its PathResult and refills itself from the device-side path queue.
+//
+// The phases flatten the reference's nested loops (file:line):
+//   PH_PLAIN    Tracker.track!                              src/tracker.jl:937-968
+//   PH_EG       EndgameTracker.step! (regular)              src/endgame_tracker.jl:329-399
+//   PH_SING     singular_endgame_step! inner tracking loop  src/endgame_tracker.jl:533-628
+//   PH_TORIC_A/B  PolyhedralTracker stage 1 (toric 0 -> 1, optional re-weighted restart)
+//                                                           src/polyhedral.jl:414-530
+// plus Valuation (src/valuation.jl:39-228), check_finite!/check_at_infinity!/switch_to_*!
+// (src/endgame_tracker.jl:402-530), add_sample!/predict_endpoint!/tracking_stopped!
+// (:630-721) and the PathResult assembly (:847-888).
+#pragma once
+#include "hc_path.h"
+
+namespace hc {
+
+enum EGCode : int {  // src/endgame_tracker.jl:100-117
+    EG_tracking = 0, EG_success, EG_at_infinity, EG_at_zero, EG_terminated_accuracy_limit,
+    EG_terminated_invalid_startvalue, EG_terminated_invalid_startvalue_singular_jacobian,
+    EG_terminated_ill_conditioned, EG_terminated_max_steps, EG_terminated_max_extended_steps,
+    EG_terminated_max_winding_number, EG_terminated_step_size_too_small, EG_terminated_unknown,
+    EG_post_check_failed, EG_excess_solution, EG_polyhedral_failed
+};
+HC_HD int convert_code(int c) {  // :119-139
+    switch (c) {
+        case TC_success: return EG_success;
+        case TC_terminated_max_steps: return EG_terminated_max_steps;
+        case TC_terminated_accuracy_limit: return EG_terminated_accuracy_limit;
+        case TC_terminated_ill_conditioned: return EG_terminated_ill_conditioned;
+        case TC_terminated_invalid_startvalue: return EG_terminated_invalid_startvalue;
+        case TC_terminated_invalid_startvalue_singular_jacobian: return EG_terminated_invalid_startvalue_singular_jacobian;
+        case TC_terminated_step_size_too_small: return EG_terminated_step_size_too_small;
+        case TC_terminated_unknown: return EG_terminated_unknown;
+        default: return EG_tracking;
+    }
+}
+
+enum Phase : int { PH_IDLE = 0, PH_PLAIN, PH_EG, PH_SING, PH_TORIC_A, PH_TORIC_B };
+enum Mode : int { MODE_ENDGAME = 0, MODE_TRACKER = 1, MODE_POLYHEDRAL = 2 };
+
+struct DevResults {  // caller's SoA, path-major (fields of src/path_result.jl:76-98)
+    int* return_code; cx* solution; double* t; double* accuracy; double* residual; unsigned char* singular;
+    double* condition_jacobian; int* winding_number; unsigned char* extended_precision; cx* last_point;
+    double* last_t; double* valuation; unsigned char* has_valuation; double* omega; double* mu;
+    int* accepted_steps; int* rejected_steps; int* steps_eg; unsigned char* extended_precision_used;
+    long long* counters;  // 8 per path: factorizations, ldivs, evaljac, eval, eval_dd, taylor, 0, 0
+};
+
+struct BatchIn {
+    int mode;
+    long long N;
+    const cx* starts;          // path-major: starts[path * n + i]
+    cx t1, t0;
+    const double* omega_mu;    // optional 2 x N
+    const int* cell_index;     // polyhedral: N
+    const double* cell_weights;// polyhedral: ncells x P (unscaled s_ij, 0 on the cell's vertices)
+};
+
+struct Lane : Path {
+    int phase, mode;
+    // ---- endgame state (src/endgame_tracker.jl:177-215)
+    int eg_code; bool singular_endgame; int eg_winding;  // 0 = nothing
+    double eg_accuracy, eg_cond; bool eg_singular;
+    int steps_eg, ext_steps_eg_start;
+    bool jtz_prev, jtz_cur, is_jump_to_zero;
+    double last_t;
+    int sidx0, sidx1, sidx2; double stime[3], scond[3];
+    int singular_steps; double sing_t;
+    double logt2, logt1;
+    // ---- polyhedral
+    int toric_acc, toric_rej; double poly_mu, poly_omega, poly_maxw, saved_min_step;
+    // ---- flop accounting totals of finished stages
+    int c_fact, c_ldiv;
+
+    HC_HD RV val_x() { return M.val; }
+    HC_HD RV val_tx() { return M.val.at(n); }
+    HC_HD RV dval_x() { return M.val.at(2 * n); }
+    HC_HD RV dval_tx() { return M.val.at(3 * n); }
+
+    // ================================================================ valuation
+    HC_HD void val_init() { for (int i = 0; i < 12 * n; ++i) M.val[i] = 0.0; logt2 = logt1 = HC_NAN; }
+    HC_HD static double fdiff(double v, double s, double v2, double s2, double v1, double s1) {
+        double D1 = s - s1, D2 = s - s2, D12 = s1 - s2;
+        return (D2 * v1) / (D12 * D1) - ((D12 + D2) * v2) / (D12 * D2) - (D12 * v) / (D1 * D2);
+    }
+    HC_HD static void nu_nu1(cx x, cx xd, cx x2, double t, double& nu, double& nu1) {
+        double xx = abs2(x), mu_ = x.re * xd.re + x.im * xd.im, l = mu_ / xx;
+        double mu1 = x.re * x2.re + xd.re * xd.re + x.im * x2.im + xd.im * xd.im;
+        double l1 = mu1 / xx - 2 * (l * l);
+        nu = t * l; nu1 = t * l1 + l;
+    }
+    HC_HDN void val_update(double t) {  // valuation.jl:82-124
+        const int nn = n;
+        const double logt = log(t);
+        const bool diff = winding > 1 && logt2 == logt2;
+        RV V = M.val;  // [val_x, val_tx, dval_x, dval_tx, vx2, vx1, vd2, vd1, lx2, lx1, ld2, ld1] x n
+        for (int i = 0; i < nn; ++i) {
+            cx x = M.tx[i], xd = M.tx[nn + i], x2 = M.tx[2 * nn + i], x3 = M.tx[3 * nn + i];
+            double logx = log(cabs(x)), logxd = log(cabs(xd));
+            if (diff) {
+                double nu = t * ((x.re * xd.re + x.im * xd.im) / abs2(x));
+                double dnu = fdiff(nu, logt, V[4 * nn + i], logt2, V[5 * nn + i], logt1);
+                V[i] = nu; V[2 * nn + i] = dnu;
+                double vxd = fdiff(logxd, logt, V[10 * nn + i], logt2, V[11 * nn + i], logt1);
+                double dvxd = fdiff(vxd, logt, V[6 * nn + i], logt2, V[7 * nn + i], logt1);
+                V[nn + i] = vxd + 1; V[3 * nn + i] = dvxd;
+            } else {
+                double nu, nu1;
+                nu_nu1(x, xd, 2.0 * x2, t, nu, nu1);
+                V[i] = nu; V[2 * nn + i] = t * nu1;
+                double o = V[4 * nn + i]; V[4 * nn + i] = nu; V[5 * nn + i] = o;
+                double vxd;
+                nu_nu1(xd, 2.0 * x2, 6.0 * x3, t, vxd, nu1);
+                V[nn + i] = vxd + 1; V[3 * nn + i] = t * nu1;
+            }
+            double o = V[8 * nn + i]; V[8 * nn + i] = logx; V[9 * nn + i] = o;
+            o = V[10 * nn + i]; V[10 * nn + i] = logxd; V[11 * nn + i] = o;
+        }
+        logt1 = logt2; logt2 = logt;
+    }
+    HC_HD double eps_inf(int i) {
+        double vx = M.val[i], vt = M.val[n + i];
+        return jmax(jmax(fabs(1.0 - vt / vx), fabs(M.val[2 * n + i] / vx)), fabs(M.val[3 * n + i] / vt));
+    }
+    HC_HD bool val_is_finite() {  // valuation.jl:175-205
+        const double ftol = O->val_finite_tol, delta = 1.0 / O->max_winding_number;
+        const bool zero_is_finite = !O->zero_is_at_infinity;
+        for (int i = 0; i < n; ++i) {
+            double vx = M.val[i];
+            if (fabs(vx) < ftol) {
+                if (!(fabs(M.val[2 * n + i]) < ftol) || M.val[n + i] < 0.5 * delta) return false;
+            } else if (zero_is_finite && vx > (delta - ftol)) {
+                if (!(eps_inf(i) < ftol)) return false;
+            } else return false;
+        }
+        return true;
+    }
+    HC_HD void estimate_winding(int& m, double& min_err) {  // valuation.jl:207-228
+        m = 1; min_err = HC_INF;
+        for (int k = 1; k <= O->max_winding_number; ++k) {
+            double err = 0.0;
+            for (int i = 0; i < n; ++i) { double mv = k * M.val[n + i]; double e = fabs(rint(mv) - mv); err = e > err ? e : err; }
+            if (err < min_err) { m = k; min_err = err; }
+        }
+    }
+
+    // ================================================================ endgame
+    HC_HD double eg_jac_cond() { return jac_cond(&M.egrs, &M.egcs); }
+    HC_HD void eg_scaling_update() {  // col_scaling .= weights(norm); row_scaling!(...)
+        for (int i = 0; i < n; ++i) M.egcs[i] = M.w[i];
+        skeel(M.egrs, M.egcs, O->scaling_threshold);
+    }
+    // init!(endgame_tracker, x, t1; omega, mu, extended_precision)  endgame_tracker.jl:260-294
+    HC_HDN void eg_init(double t1, double omega_, double mu_, bool ext) {
+        min_rel_step_size = 0.0;
+        tracker_init(mk(t1), mk(0.0), omega_, mu_, HC_INF, HC_INF, false, ext);
+        eg_code = convert_code(code);
+        singular_endgame = false; jtz_prev = jtz_cur = false;
+        val_init(); eg_winding = 0;
+        for (int i = 0; i < n; ++i) M.sol[i] = mk(HC_NAN, HC_NAN);
+        eg_accuracy = HC_NAN; eg_cond = HC_NAN; eg_singular = false; steps_eg = 0; ext_steps_eg_start = 0x3fffffff;
+        for (int i = 0; i < n; ++i) { M.egrs[i] = 1.0; M.egcs[i] = 1.0; M.ais[i] = HC_NAN; }
+        singular_steps = 0; sidx0 = 0; sidx1 = 1; sidx2 = 2;
+        last_t = HC_NAN;
+        for (int i = 0; i < n; ++i) M.lastp[i] = M.x[i];
+    }
+    HC_HDN void tracking_stopped() {  // :695-721
+        eg_accuracy = accuracy;
+        if (eg_code == EG_success && eg_accuracy > 1e-14) refine_current_solution(1e-14, O->refine_steps);
+        for (int i = 0; i < n; ++i) M.sol[i] = M.x[i];
+        eg_winding = 0;
+        if (eg_code == EG_success) {
+            eg_scaling_update();
+            eg_cond = cond_at(M.sol, mk(0.0), &M.egrs, &M.egcs);
+            eg_singular = eg_cond > O->sing_cond || eg_accuracy > O->sing_accuracy;
+        }
+    }
+    HC_HD bool check_finite() {  // :402-422
+        if (!val_is_finite()) return false;
+        int mw; double merr;
+        estimate_winding(mw, merr);
+        if (merr < O->val_finite_tol) {
+            if (mw == 1 && !jtz_prev) return false;
+            eg_winding = mw;
+            return true;
+        }
+        return false;
+    }
+    HC_HDN bool check_at_infinity() {  // :424-499
+        if (!O->at_infinity_check) return false;
+        const double ftol = O->val_finite_tol;
+        const bool zero_is_finite = !O->zero_is_at_infinity;
+        double kappa = HC_NAN;
+        const double t = st_t().re;
+        for (int i = 0; i < n; ++i) {
+            // at_infinity_tol!  valuation.jl:143-173
+            double vx = M.val[i], e = eps_inf(i), tol;
+            if (e != e) tol = HC_INF;
+            else if (vx + e < -ftol) tol = e;
+            else if (!zero_is_finite && vx - e > -ftol) tol = e;
+            else tol = HC_INF;
+            M.ait[i] = tol;
+        }
+        for (int i = 0; i < n; ++i) {
+            if (M.ait[i] < O->val_at_infinity_tol) {
+                if (M.ais[i] != M.ais[i]) {
+                    bool allnan = true;
+                    for (int k = 0; k < n; ++k) allnan = allnan && (M.ais[k] != M.ais[k]);
+                    if (allnan) eg_scaling_update();
+                    kappa = eg_jac_cond();
+                    M.aic[i] = kappa; M.aia[i] = cabs(M.x[i]); M.ais[i] = t;
+                } else {
+                    if (kappa != kappa) kappa = eg_jac_cond();
+                    double v = M.val[i];
+                    bool at_zero = v > 0;
+                    double cond_growth = kappa / M.aic[i];
+                    double coord_growth = at_zero ? M.aia[i] / cabs(M.x[i]) : cabs(M.x[i]) / M.aia[i];
+                    if (coord_growth > clampd(pow(0.25, 4 * v), 20.0, O->min_coord_growth) &&
+                        (cond_growth > O->min_cond_growth || kappa > jmax(1e8, O->min_cond))) {
+                        eg_code = at_zero ? EG_at_zero : EG_at_infinity;
+                        return true;
+                    }
+                }
+            } else if (M.ais[i] == M.ais[i]) M.ais[i] = HC_NAN;
+        }
+        return false;
+    }
+    HC_HDN void add_sample(double t) {  // :630-662
+        const int nn = n;
+        const int mw = eg_winding;
+        double s = nthroot(t, mw), mu_ = mw;
+        for (int k = 0; k < mw - 1; ++k) mu_ *= s;
+        double kappa = eg_jac_cond();
+        int slot;
+        if (singular_steps <= 2) slot = singular_steps;
+        else {
+            int first = sidx0;
+            sidx0 = sidx1; stime[0] = stime[1]; scond[0] = scond[1];
+            sidx1 = sidx2; stime[1] = stime[2]; scond[1] = scond[2];
+            sidx2 = first; slot = 2;
+        }
+        int sid = slot == 0 ? sidx0 : (slot == 1 ? sidx1 : sidx2);
+        CV ty = M.samp.at(sid * 2 * nn);
+        for (int i = 0; i < nn; ++i) { ty[i] = M.tx[i]; ty[nn + i] = mu_ * M.tx[nn + i]; }
+        if (slot == 0) { stime[0] = s; scond[0] = kappa; } else if (slot == 1) { stime[1] = s; scond[1] = kappa; } else { stime[2] = s; scond[2] = kappa; }
+    }
+    HC_HDN double predict_endpoint() {  // :664-693
+        const int nn = n;
+        if (singular_steps < 2) return HC_INF;
+        CV S0 = M.samp.at(sidx0 * 2 * nn), S1 = M.samp.at(sidx1 * 2 * nn), S2 = M.samp.at(sidx2 * 2 * nn);
+        if (singular_steps == 2) cubic_hermite(M.pred, S0, S0.at(nn), mk(stime[0]), S1, S1.at(nn), mk(stime[1]), mk(0.0));
+        for (int i = 0; i < nn; ++i) M.ppred[i] = M.pred[i];
+        cubic_hermite(M.pred, S1, S1.at(nn), mk(stime[1]), S2, S2.at(nn), mk(stime[2]), mk(0.0));
+        double p = stime[2] / stime[1], p2 = p * p;
+        double err = inf_dist(M.pred, M.ppred, nn) / fabs(p2 * p2 - 1);
+        double ns = inf_norm(M.pred, nn);
+        if (ns > 1e-8) err /= ns;
+        return err;
+    }
+    HC_HDN void switch_to_singular() {  // :501-524
+        singular_endgame = true;
+        double t = st_t().re;
+        bool allone = true;
+        for (int i = 0; i < n; ++i) allone = allone && (M.egrs[i] == 1.0);
+        if (allone) eg_scaling_update();
+        add_sample(t);
+        singular_steps = 0;
+        winding = eg_winding;
+        M.aic[0] = scond[0];
+        keep_extended_prec = true;
+    }
+    HC_HD void switch_to_regular() {  // :525-530
+        singular_endgame = false;
+        winding = 1;
+        tracker_init_continue(mk(0.0));
+        phase = PH_EG;
+    }
+    // First half of step!(::EndgameTracker): returns false when the path ended without a tracker step.
+    HC_HDN bool eg_pre() {  // :329-358
+        if (steps_eg >= O->max_endgame_steps) { eg_code = EG_terminated_max_steps; return false; }
+        if (ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) {
+            bool nonan = true;
+            for (int i = 0; i < n; ++i) nonan = nonan && !cisnan(M.sol[i]);
+            if (nonan && eg_winding != 0 && eg_accuracy < O->singular_min_accuracy) {
+                eg_cond = cond_at(M.sol, mk(0.0), &M.egrs, &M.egcs);
+                eg_singular = true; eg_code = EG_success;
+            } else eg_code = EG_terminated_max_extended_steps;
+            return false;
+        }
+        for (int i = 0; i < n; ++i) M.lastp[i] = M.x[i];
+        last_t = st_t().re;
+        if (singular_endgame) {  // begin singular_endgame_step!  :533-540
+            sing_t = st_t().re;
+            tracker_init_continue(mk(0.25 * sing_t));
+            phase = PH_SING;
+            return true;
+        }
+        is_jump_to_zero = ciszero(st_tp());
+        return true;
+    }
+    // Second half of step!(::EndgameTracker) after a regular tracker step  :362-398
+    HC_HDN void eg_post(bool step_success) {
+        eg_code = convert_code(code);
+        if (eg_code != EG_tracking) { tracking_stopped(); return; }
+        jtz_prev = jtz_cur; jtz_cur = is_jump_to_zero;
+        double t = st_t().re;
+        if (!(t <= O->endgame_start)) return;
+        if (steps_eg == 0) ext_steps_eg_start = ext_steps();
+        steps_eg += 1;
+        if (!step_success) return;
+        val_update(t);
+        if (check_finite()) { switch_to_singular(); return; }
+        check_at_infinity();
+    }
+    // After each tracker step of the singular endgame's inner loop  :541-628
+    HC_HDN void sing_post() {
+        bool max_steps = false;
+        if ((steps_eg += 1) >= O->max_endgame_steps) { eg_code = EG_terminated_max_steps; max_steps = true; }
+        else if (ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) { eg_code = EG_terminated_max_extended_steps; max_steps = true; }
+        if (!max_steps && code == TC_tracking) return;  // inner loop continues
+        phase = PH_EG;
+        singular_steps += 1;
+        const double lt = 0.25 * sing_t;
+        if (!max_steps) {
+            if (code != TC_success) { eg_code = convert_code(code); tracking_stopped(); return; }
+            val_update(lt);
+            int mh; double mh_err;
+            estimate_winding(mh, mh_err);
+            if (mh != eg_winding || mh_err > 0.1) { switch_to_regular(); return; }
+            add_sample(lt);
+            if (singular_steps < 2) return;
+            double acc = predict_endpoint();
+            if (singular_steps == 2 || (acc < eg_accuracy && eg_accuracy > 1e-12)) {
+                eg_accuracy = acc;
+                for (int i = 0; i < n; ++i) M.sol[i] = M.pred[i];
+                return;
+            }
+        }
+        const int mw = eg_winding;
+        const double kappa = scond[2], zero_cond = 1.0 / (mw + 1);
+        for (int i = 0; i < n; ++i) M.sol[i] = (M.val[i] < zero_cond ? 1.0 : 0.0) * M.pred[i];
+        double kappa0 = cond_at(M.sol, mk(0.0), &M.egrs, &M.egcs);
+        double J0 = a_inf_norm(&M.egrs, nullptr);
+        if (eg_accuracy < O->singular_min_accuracy &&
+            (((mw > 1 && kappa > O->min_cond && nanmax(kappa0, 1.0 / J0) > kappa) || (mw == 1 && kappa0 > 1e12)) || max_steps ||
+             (n == 1 && 1.0 / J0 < O->min_cond))) {
+            eg_cond = jmax(kappa0, 1.0 / J0);
+            eg_singular = true;
+            eg_code = EG_success;
+        } else if (!max_steps) switch_to_regular();
+    }
+
+    // ================================================================ polyhedral stage 1
+    // update_weights!(H, support, lifting, cell; min_weight | max_weight)  toric_homotopy.jl:66-112
+    HC_HD void set_weights(const double* raw, bool use_min, double target, double& smin, double& smax) {
+        const int P = H->P;
+        smax = 0.0; smin = HC_INF;
+        for (int l = 0; l < P; ++l) { double r = ld_real(raw + l); if (r != 0.0) { smax = jmax(smax, r); smin = jmin(smin, r); } }
+        double lam = use_min ? smin / target : smax / target;
+        for (int l = 0; l < P; ++l) M.tw[l] = ld_real(raw + l) / lam;
+        if (use_min) { smax = smax / lam; smin = target; } else { smin = smin / lam; smax = target; }
+    }
+
+    // ================================================================ results
+    HC_HDN void write_result(const DevResults& R, int rc, bool success_at_zero, bool valuation_ok) {
+        const long long k = pidx;
+        const int nn = n;
+        double tt;
+        CV sol = success_at_zero ? M.sol : M.x;
+        if (success_at_zero) tt = 0.0; else tt = st_t().re;
+        R.return_code[k] = rc;
+        for (int i = 0; i < nn; ++i) { R.solution[k * nn + i] = sol[i]; R.last_point[k * nn + i] = M.lastp[i]; }
+        R.t[k] = tt;
+        R.last_t[k] = last_t;
+        R.omega[k] = omega; R.mu[k] = mu;
+        R.extended_precision[k] = extended_prec; R.extended_precision_used[k] = used_extended_prec;
+        R.accepted_steps[k] = accepted_steps; R.rejected_steps[k] = rejected_steps;
+        if (R.counters) {
+            long long* c = R.counters + 8 * k;
+            c[0] = c_fact + n_fact; c[1] = c_ldiv + n_ldiv; c[2] = n_evaljac; c[3] = n_eval; c[4] = n_evaldd; c[5] = n_taylor; c[6] = 0; c[7] = 0;
+        }
+        (void)valuation_ok;
+    }
+    HC_HDN void finish_eg(const DevResults& R) {  // PathResult(::EndgameTracker)  :847-888
+        const long long k = pidx;
+        const int nn = n;
+        const bool ok = eg_code == EG_success;
+        const double tt = ok ? 0.0 : st_t().re;
+        eval_f64(M.r, nullptr, ok ? M.sol : M.x, mk(tt));
+        R.residual[k] = inf_norm(M.r, nn);
+        write_result(R, eg_code, ok, true);
+        R.singular[k] = eg_singular; R.accuracy[k] = eg_accuracy; R.condition_jacobian[k] = eg_cond;
+        R.winding_number[k] = eg_winding; R.steps_eg[k] = steps_eg;
+        R.has_valuation[k] = !(tt > O->endgame_start);
+        for (int i = 0; i < nn; ++i) R.valuation[k * nn + i] = M.val[i];
+        if (mode == MODE_POLYHEDRAL) { R.accepted_steps[k] += toric_acc; R.rejected_steps[k] += toric_rej; }
+        phase = PH_IDLE;
+    }
+    HC_HDN void finish_plain(const DevResults& R) {  // TrackerResult  tracker.jl:998-1012
+        const long long k = pidx;
+        const int nn = n;
+        for (int i = 0; i < nn; ++i) M.lastp[i] = M.x[i];
+        last_t = st_t().im;
+        write_result(R, code, false, false);
+        R.accuracy[k] = accuracy; R.residual[k] = HC_NAN; R.singular[k] = 0; R.condition_jacobian[k] = tau;
+        R.winding_number[k] = 0; R.steps_eg[k] = 0; R.has_valuation[k] = 0;
+        R.extended_precision[k] = extended_prec || refined_extended_prec;
+        R.extended_precision_used[k] = used_extended_prec || refined_extended_prec;
+        for (int i = 0; i < nn; ++i) R.valuation[k * nn + i] = HC_NAN;
+        phase = PH_IDLE;
+    }
+    HC_HDN void finish_poly_failed(const DevResults& R) {  // polyhedral.jl:491-513
+        const long long k = pidx;
+        const int nn = n;
+        for (int i = 0; i < nn; ++i) M.lastp[i] = M.x[i];
+        last_t = st_t().re;
+        write_result(R, EG_polyhedral_failed, false, false);
+        R.accuracy[k] = accuracy; R.residual[k] = HC_NAN; R.singular[k] = 0; R.condition_jacobian[k] = HC_NAN;
+        R.winding_number[k] = 0; R.steps_eg[k] = 0; R.has_valuation[k] = 0;
+        for (int i = 0; i < nn; ++i) R.valuation[k * nn + i] = 0.0;
+        phase = PH_IDLE;
+    }
+
+    // ================================================================ driver
+    HC_HDN void start_path(long long k, const BatchIn& B, const DevResults& R) {
+        pidx = k; mode = B.mode;
+        const int nn = n;
+        for (int i = 0; i < nn; ++i) M.x[i] = B.starts[k * nn + i];
+        refined_extended_prec = false; factorized = scaled = false;
+        min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
+        n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_taylor = 0; c_fact = c_ldiv = 0;
+        toric_acc = toric_rej = 0;
+        double om = HC_NAN, mu_ = HC_NAN;
+        if (B.omega_mu) { om = B.omega_mu[2 * k]; mu_ = B.omega_mu[2 * k + 1]; }
+        if (mode == MODE_TRACKER) {
+            kind = H->kind;
+            tracker_init(B.t1, B.t0, om, mu_, HC_INF, HC_INF, false, false);
+            phase = PH_PLAIN;
+            if (code != TC_tracking) finish_plain(R);
+        } else if (mode == MODE_ENDGAME) {
+            kind = H->kind;
+            eg_init(B.t1.re, om, mu_, false);
+            phase = PH_EG;
+            if (eg_code != EG_tracking) finish_eg(R);
+        } else {  // polyhedral.jl:414-465
+            kind = H_TORIC;
+            double smin, smax;
+            const double* raw = B.cell_weights + (size_t)B.cell_index[k] * H->P;
+            set_weights(raw, true, 1.0, smin, smax);
+            poly_maxw = smax;
+            double tend = smax < 10 ? 1.0 : clampd(pow(0.1, 10 / smax), 0.9, 1 - 1e-6);
+            tracker_init(mk(0.0), mk(tend), 20.0, 1e-12, HC_INF, 0.2, false, false);
+            phase = PH_TORIC_A;
+            if (code != TC_tracking) toric_transition(B, R);
+        }
+    }
+    HC_HDN void toric_done(const DevResults& R) {  // polyhedral.jl:491-529
+        if (code != TC_success) { finish_poly_failed(R); return; }
+        toric_acc = accepted_steps; toric_rej = rejected_steps;
+        c_fact += n_fact; c_ldiv += n_ldiv;
+        kind = H_COEFFICIENT;
+        // omega deliberately not passed (:515-521)
+        eg_init(1.0, HC_NAN, mu, false);
+        phase = PH_EG;
+        if (eg_code != EG_tracking) finish_eg(R);
+    }
+    HC_HDN void toric_transition(const BatchIn& B, const DevResults& R) {
+        if (phase == PH_TORIC_A && poly_maxw >= 10 && code == TC_success) {  // :466-489
+            double smin, smax;
+            const double* raw = B.cell_weights + (size_t)B.cell_index[pidx] * H->P;
+            double t0 = st_target.re;
+            set_weights(raw, false, 10.0, smin, smax);
+            double t_restart = pow(t0, 1 / smin);
+            saved_min_step = min_step_size; min_step_size = 0.0;
+            c_fact += n_fact; c_ldiv += n_ldiv;
+            tracker_init(mk(t_restart), mk(1.0), omega, mu, 0.1 * t_restart, HC_INF, true, false);
+            phase = PH_TORIC_B;
+            if (code != TC_tracking) { min_step_size = saved_min_step; toric_done(R); }
+            return;
+        }
+        if (phase == PH_TORIC_B) min_step_size = saved_min_step;
+        toric_done(R);
+    }
+    // One flat iteration of an active lane.
+    HC_HD void iterate(const BatchIn& B, const DevResults& R) {
+        bool do_step = true;
+        if (phase == PH_EG) do_step = eg_pre();
+        bool ok = false;
+        if (do_step) ok = tracker_step();
+        switch (phase) {
+            case PH_PLAIN: if (code != TC_tracking) finish_plain(R); break;
+            case PH_TORIC_A: case PH_TORIC_B: if (code != TC_tracking) toric_transition(B, R); break;
+            case PH_SING: sing_post(); if (eg_code != EG_tracking) finish_eg(R); break;
+            case PH_EG: if (do_step) eg_post(ok); if (eg_code != EG_tracking) finish_eg(R); break;
+            default: break;
+        }
+    }
+};
+
+}  // namespace hc

@@ -1,0 +1,964 @@
+// One solution path per thread: per-lane memory views, homotopy evaluation, small dense linear
+// algebra, norms, predictor, Newton corrector and the core tracker step.
+//
+// Replaces (reference file:line):
+//   src/homotopies/straight_line_homotopy.jl:81-154, parameter_homotopy.jl:66-101,
+//   coefficient_homotopy.jl:89-141, toric_homotopy.jl:114-278         homotopy operator API
+//   src/linear_algebra.jl:88-98, 130-184, 268-354, 389-408, 432-567, 585-774, 833-885
+//   src/norm.jl:101-136, 150-234;  src/utils.jl:300-394 (SegmentStepper)
+//   src/predictor.jl:158-371;  src/newton_corrector.jl:55-286
+//   src/tracker.jl:509-619, 639-844, 851-926
+#pragma once
+#include "hc_program.h"
+
+namespace hc {
+
+enum HKind : int { H_STRAIGHT_LINE = 0, H_PARAMETER = 1, H_COEFFICIENT = 2, H_TORIC = 3 };
+
+struct DevOptions {  // same field order as hc_options (include/hc_b200.h)
+    int max_steps; double max_step_size, max_initial_step_size; int extended_precision;
+    double min_step_size, min_rel_step_size;
+    double a, beta_a, beta_omega_p, beta_tau, strict_beta_tau; int min_newton_iters;
+    double endgame_start; int max_endgame_steps, max_endgame_extended_steps;
+    double min_cond, min_cond_growth, min_coord_growth;
+    int zero_is_at_infinity, at_infinity_check, only_nonsingular;
+    double singular_min_accuracy; int max_winding_number;
+    double val_finite_tol, val_at_infinity_tol, sing_cond, sing_accuracy, scaling_threshold;
+    int refine_steps;
+    double scale_min, scale_abs_min, scale_max;
+};
+
+struct DevHomotopy {
+    int kind, n, P;            // square systems: m == n; P = #parameters of F
+    DevProgram Fe, Fj, Ge, Gj; // eval / Jacobian tapes of F (and of G for straight-line)
+    cx gamma;
+    const cx* G_params;        // straight-line: fixed parameters of G (scaling), length Ge.P
+    const cx* F_params;        // straight-line: fixed parameters of F
+    const cx* p;               // parameter/coefficient: start (t = 1); toric: system coefficients
+    const cx* q;               // parameter/coefficient: target (t = 0)
+    const cx* path_p;          // optional per-path start parameters, [i * N + path]
+    const cx* path_q;          // optional per-path target parameters, [i * N + path]
+    long long N;
+    int tape_cx;               // per-lane tape region, in cx units
+};
+
+// ---------------------------------------------------------------- per-lane memory
+struct PathMem {
+    CV x, xhat, xbar, tx, ptx1, ty1, pty1, xtemp, u, dx, r, A, LU, wr, wdx, work;
+    CV sol, lastp, pred, ppred, samp, tape;
+    DV xbd, rbd, tape_dd;
+    RV w, rs, rwork, egrs, egcs, ais, ait, aia, aic, val, tw;
+    IV ipiv;
+};
+struct MemSizes { size_t ncx, nre, nint; };
+
+// Carves the per-lane vectors out of three lane-interleaved slabs (element i of lane l at
+// base[i * stride + l]).  With null bases it only counts; the host sizes the allocation so.
+HC_HD MemSizes carve(PathMem& M, int n, int P, int tape_cx, cx* cb, double* rb, int* ib, int stride, int lane) {
+    size_t oc = 0, orr = 0, oi = 0;
+    auto C = [&](size_t k) { CV v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += k; return v; };
+    auto D = [&](size_t k) { DV v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += 2 * k; return v; };
+    auto R = [&](size_t k) { RV v; v.p = rb ? rb + orr * (size_t)stride + lane : nullptr; v.s = stride; orr += k; return v; };
+    M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n); M.ptx1 = C(2 * n); M.ty1 = C(2 * n); M.pty1 = C(2 * n);
+    M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
+    M.wr = C(n); M.wdx = C(n); M.work = C(n);
+    M.sol = C(n); M.lastp = C(n); M.pred = C(n); M.ppred = C(n); M.samp = C(6 * n);
+    M.xbd = D(n); M.rbd = D(n);
+    {   // tape region: viewed as cx (F64 / Taylor) or as cdd (DD)
+        size_t tc = (size_t)((tape_cx + 1) & ~1);
+        M.tape.p = cb ? cb + oc * (size_t)stride + lane : nullptr; M.tape.s = stride;
+        M.tape_dd.p = M.tape.p; M.tape_dd.s = stride;
+        oc += tc;
+    }
+    M.w = R(n); M.rs = R(n); M.rwork = R(n); M.egrs = R(n); M.egcs = R(n);
+    M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n); M.tw = R(P > 0 ? P : 1);
+    M.ipiv.p = ib ? ib + oi * (size_t)stride + lane : nullptr; M.ipiv.s = stride; oi += n;
+    MemSizes s; s.ncx = oc; s.nre = orr; s.nint = oi;
+    return s;
+}
+
+// ---------------------------------------------------------------- norms (src/norm.jl)
+HC_HD double inf_norm(CV x, int n) {
+    double d = abs2(x[0]);
+    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2(x[i]));
+    double r = sqrt(d);
+    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) r = jmax(r, hypot(x[i].re, x[i].im)); }
+    return r;
+}
+HC_HD double inf_dist(CV x, CV y, int n) {
+    double d = abs2(x[0] - y[0]);
+    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2(x[i] - y[i]));
+    double r = sqrt(d);
+    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) { cx z = x[i] - y[i]; r = jmax(r, hypot(z.re, z.im)); } }
+    return r;
+}
+HC_HD double wnorm(CV x, RV w, int n) {
+    double d = abs2(x[0] / w[0]);
+    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2(x[i] / w[i]));
+    double r = sqrt(d);
+    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) { cx z = x[i] / w[i]; r = jmax(r, hypot(z.re, z.im)); } }
+    return r;
+}
+HC_HD double wdist(CV x, CV y, RV w, int n) {
+    double d = abs2((x[0] - y[0]) / w[0]);
+    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2((x[i] - y[i]) / w[i]));
+    double r = sqrt(d);
+    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) { cx z = (x[i] - y[i]) / w[i]; r = jmax(r, hypot(z.re, z.im)); } }
+    return r;
+}
+
+// ---------------------------------------------------------------- the path
+enum TrackerCode : int {  // src/tracker.jl:166-176
+    TC_tracking = 0, TC_success, TC_terminated_max_steps, TC_terminated_accuracy_limit,
+    TC_terminated_ill_conditioned, TC_terminated_invalid_startvalue,
+    TC_terminated_invalid_startvalue_singular_jacobian, TC_terminated_step_size_too_small,
+    TC_terminated_unknown
+};
+enum NewtonCode : int { NEWT_CONVERGED = 0, NEWT_TERMINATED, NEWT_MAX_ITERS, NEWT_SINGULARITY };
+struct NewtonResult { int code; double accuracy; int iters; double omega, theta, mu_low, norm_dx0; };
+
+HC_HD double hfun(double a) { return 2 * a * (sqrt(4 * a * a + 1) - 2 * a); }  // tracker.jl:517
+
+HC_HD cx t_to_s_plane(cx t, int m) {  // predictor.jl:338-351
+    double r = cabs(t);
+    if (t.im == 0.0 && t.re > 0) return mk(nthroot(r, m));
+    double th = atan2(t.im, t.re);
+    th = fmod(th, 6.283185307179586); if (th < 0) th += 6.283185307179586;
+    double rr = nthroot(r, m);
+    return mk(rr * cos(th / m), rr * sin(th / m));
+}
+HC_HD cx cpow_pos(cx z, int p) { return cpowi(z, p); }
+
+struct Path {
+    // ---- immutable context
+    const DevHomotopy* H;
+    const DevOptions* O;
+    PathMem M;
+    int n;
+    long long pidx;
+    int kind;  // current homotopy kind (polyhedral paths switch TORIC -> COEFFICIENT)
+    // ---- tracker state (src/tracker.jl:307-338)
+    cx st_start, st_target; double st_absd; bool st_forward; double st_s, st_sp;  // SegmentStepper
+    double ds_prev, accuracy, omega, omega_prev, mu, tau;
+    bool extended_prec, used_extended_prec, refined_extended_prec, keep_extended_prec, use_strict_beta_tau;
+    bool factorized, scaled;  // MatrixWorkspace flags
+    int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
+    double min_step_size, min_rel_step_size;  // mutable copies (polyhedral.jl:474-488, endgame_tracker.jl:270)
+    // ---- predictor (src/predictor.jl:72-103)
+    int pm_hermite; double trust_region, local_error, cond_H;
+    cx pt, pprev_t, ps, pprev_s; int winding;
+    // ---- counters (src/linear_algebra.jl:809-826 + flop accounting of SURVEY.md 8(d))
+    int n_fact, n_ldiv, n_evaljac, n_eval, n_evaldd, n_taylor;
+
+    // ================================================================ homotopy
+    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)i * H->N + pidx] : ld_const(H->p + i); }
+    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)i * H->N + pidx] : ld_const(H->q + i); }
+
+    // Taylor coefficients c[0..4] of parameter i at t (only the first `np` are meaningful)
+    HC_HD void param_series(int i, cx t, cx* c) const {
+        c[1] = c[2] = c[3] = c[4] = mk(0.0);
+        if (kind == H_TORIC) {  // toric_homotopy.jl:145-177, 220-264 (real t >= 0)
+            cx u = ld_const(H->p + i);
+            double w = M.tw[i], tr = t.re;
+            if (tr == 0.0) {
+                c[0] = mk(0.0);
+                if (w < 1e-12) c[0] = u;
+                else if (fabs(w - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(w), 1.0)) c[1] = u;
+            } else {
+                double tw = exp(w * log(tr)), ti = 1.0 / tr;
+                c[0] = u * tw;
+                double tw1 = w * tw * ti; c[1] = u * tw1;
+                double tw2 = 0.5 * (w - 1) * tw1 * ti; c[2] = u * tw2;
+                double tw3 = (w - 2) * tw2 * ti / 3; c[3] = u * tw3;
+                double tw4 = 0.25 * (w - 3) * tw3 * ti; c[4] = u * tw4;
+            }
+        } else {  // parameter_homotopy.jl:66-87, coefficient_homotopy.jl:89-107
+            cx p = param_p(i), q = param_q(i);
+            if (t.im == 0.0) c[0] = t.re * p + (1.0 - t.re) * q;
+            else c[0] = t * p + (mk(1.0) - t) * q;
+            c[1] = p - q;
+        }
+    }
+    // value of parameter i at t (toric t == 0: weights that are exactly 0 survive, toric_homotopy.jl:160-165)
+    HC_HD cx param_value(int i, cx t) const {
+        if (kind == H_TORIC) {
+            cx u = ld_const(H->p + i);
+            double w = M.tw[i];
+            if (t.re == 0.0) return w == 0.0 ? u : mk(0.0);
+            return u * exp(w * log(t.re));
+        }
+        cx c[5]; param_series(i, t, c); return c[0];
+    }
+
+    template <class T, class TapeT>
+    HC_HD void load_inputs(const DevProgram& P, TapeT tape, CV x, const CV* xlo, cx t, const cx* fixed) {
+        for (int i = 0; i < P.P; ++i) {
+            cx v = fixed ? ld_const(fixed + i) : param_value(i, t);
+            store_in(tape, P.param_off + i - P.C, v, mk(0.0));
+        }
+        if (P.t_slot >= 0) store_in(tape, P.t_slot - P.C, t, mk(0.0));
+        for (int i = 0; i < P.n; ++i) store_in(tape, P.var_off + i - P.C, x[i], xlo ? (*xlo)[i] : mk(0.0));
+    }
+    HC_HD static void store_in(CV tape, int s, cx hi, cx) { tape[s] = hi; }
+    HC_HD static void store_in(DV tape, int s, cx hi, cx lo) { tape.set(s, mkcdd(mkdd(hi.re, lo.re), mkdd(hi.im, lo.im))); }
+
+    // u (and optionally the column-major Jacobian U) of H(x, t)
+    HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
+        const int nn = n;
+        const bool jac = U != nullptr;
+        if (jac) n_evaljac++; else n_eval++;
+        if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:96-124
+            const cx ts = H->gamma * t, tt = mk(1.0) - t;
+            const DevProgram& PG = jac ? H->Gj : H->Ge;
+            const DevProgram& PF = jac ? H->Fj : H->Fe;
+            for (int i = 0; i < nn; ++i) u[i] = mk(0.0);
+            if (jac) for (int i = 0; i < nn * nn; ++i) (*U)[i] = mk(0.0);
+            load_inputs<cx>(PG, M.tape, x, nullptr, t, H->G_params);
+            run_tape<cx>(PG, M.tape);
+            for (int k = 0; k < PG.nu; ++k) { int2 a = ld_i2(PG.u_assign + k); u[a.x] = ts * fetch(PG, M.tape, a.y); }
+            if (jac) for (int k = 0; k < PG.nU; ++k) { int2 a = ld_i2(PG.U_assign + k); (*U)[a.x] = ts * fetch(PG, M.tape, a.y); }
+            load_inputs<cx>(PF, M.tape, x, nullptr, t, H->F_params);
+            run_tape<cx>(PF, M.tape);
+            for (int k = 0; k < PF.nu; ++k) { int2 a = ld_i2(PF.u_assign + k); u[a.x] = cfma(tt, fetch(PF, M.tape, a.y), u[a.x]); }
+            if (jac) for (int k = 0; k < PF.nU; ++k) { int2 a = ld_i2(PF.U_assign + k); (*U)[a.x] = cfma(tt, fetch(PF, M.tape, a.y), (*U)[a.x]); }
+        } else {
+            const DevProgram& PF = jac ? H->Fj : H->Fe;
+            load_inputs<cx>(PF, M.tape, x, nullptr, t, nullptr);
+            run_tape<cx>(PF, M.tape);
+            if (PF.nu != nn) for (int i = 0; i < nn; ++i) u[i] = mk(0.0);
+            for (int k = 0; k < PF.nu; ++k) { int2 a = ld_i2(PF.u_assign + k); u[a.x] = fetch(PF, M.tape, a.y); }
+            if (jac) {
+                if (PF.nU != nn * nn) for (int i = 0; i < nn * nn; ++i) (*U)[i] = mk(0.0);
+                for (int k = 0; k < PF.nU; ++k) { int2 a = ld_i2(PF.U_assign + k); (*U)[a.x] = fetch(PF, M.tape, a.y); }
+            }
+        }
+    }
+    // DoubleDouble re-evaluation of the residual, rounded to fp64 on store
+    // (newton_corrector.jl:104-105; straight_line_homotopy.jl:81-94: combine in DD)
+    HC_HDN void eval_dd(CV u, CV x, const CV* xlo, cx t) {
+        const int nn = n;
+        n_evaldd++;
+        if (kind == H_STRAIGHT_LINE) {
+            const cdd ts = tocdd(H->gamma * t), tt = tocdd(mk(1.0) - t);
+            for (int i = 0; i < nn; ++i) M.rbd.set(i, tocdd(mk(0.0)));
+            load_inputs<cdd>(H->Ge, M.tape_dd, x, xlo, t, H->G_params);
+            run_tape<cdd>(H->Ge, M.tape_dd);
+            for (int k = 0; k < H->Ge.nu; ++k) { int2 a = ld_i2(H->Ge.u_assign + k); M.rbd.set(a.x, ts * fetch(H->Ge, M.tape_dd, a.y)); }
+            load_inputs<cdd>(H->Fe, M.tape_dd, x, xlo, t, H->F_params);
+            run_tape<cdd>(H->Fe, M.tape_dd);
+            for (int k = 0; k < H->Fe.nu; ++k) { int2 a = ld_i2(H->Fe.u_assign + k); M.rbd.set(a.x, M.rbd.get(a.x) + tt * fetch(H->Fe, M.tape_dd, a.y)); }
+            for (int i = 0; i < nn; ++i) u[i] = tocx(M.rbd.get(i));
+        } else {
+            const DevProgram& PF = H->Fe;
+            load_inputs<cdd>(PF, M.tape_dd, x, xlo, t, nullptr);
+            run_tape<cdd>(PF, M.tape_dd);
+            if (PF.nu != nn) for (int i = 0; i < nn; ++i) u[i] = mk(0.0);
+            for (int k = 0; k < PF.nu; ++k) { int2 a = ld_i2(PF.u_assign + k); u[a.x] = tocx(fetch(PF, M.tape_dd, a.y)); }
+        }
+    }
+
+    template <int K>
+    HC_HD void taylor_inputs(const DevProgram& P, CV tx, cx t, const cx* fixed) {
+        for (int i = 0; i < P.P; ++i) {
+            cx c[5];
+            if (fixed) { c[0] = ld_const(fixed + i); c[1] = c[2] = c[3] = c[4] = mk(0.0); }
+            else param_series(i, t, c);
+            const int b = (P.param_off + i - P.C) * (K + 1);
+#pragma unroll
+            for (int k = 0; k <= K; ++k) M.tape[b + k] = c[k];
+        }
+        if (P.t_slot >= 0) {
+            const int b = (P.t_slot - P.C) * (K + 1);
+            M.tape[b] = t; M.tape[b + 1] = mk(1.0);
+#pragma unroll
+            for (int k = 2; k <= K; ++k) M.tape[b + k] = mk(0.0);
+        }
+        for (int i = 0; i < P.n; ++i) {  // x series: rows 0..K-1 of tx, coefficient K zero padded
+            const int b = (P.var_off + i - P.C) * (K + 1);
+#pragma unroll
+            for (int k = 0; k < K; ++k) M.tape[b + k] = tx[k * n + i];
+            M.tape[b + K] = mk(0.0);
+        }
+    }
+    template <int K>
+    HC_HD cx ser_coeff(const DevProgram& P, int slot, int k) {
+        if (slot < P.C) return k == 0 ? ld_const(P.consts + slot) : mk(0.0);
+        return M.tape[(slot - P.C) * (K + 1) + k];
+    }
+    // u = K-th Taylor coefficient of lambda -> H(x(lambda), t + lambda); tx rows x^0..x^{K-1}
+    template <int K>
+    HC_HDN void taylor(CV u, CV tx, cx t) {
+        n_taylor++;
+        for (int i = 0; i < n; ++i) u[i] = mk(0.0);
+        if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:130-154
+            taylor_inputs<K>(H->Ge, tx, t, H->G_params);
+            run_taylor_tape<K>(H->Ge, M.tape);
+            for (int k = 0; k < H->Ge.nu; ++k) {
+                int2 a = ld_i2(H->Ge.u_assign + k);
+                u[a.x] = H->gamma * (ser_coeff<K>(H->Ge, a.y, K - 1) + t * ser_coeff<K>(H->Ge, a.y, K));
+            }
+            taylor_inputs<K>(H->Fe, tx, t, H->F_params);
+            run_taylor_tape<K>(H->Fe, M.tape);
+            for (int k = 0; k < H->Fe.nu; ++k) {
+                int2 a = ld_i2(H->Fe.u_assign + k);
+                u[a.x] = u[a.x] + ((mk(1.0) - t) * ser_coeff<K>(H->Fe, a.y, K) - ser_coeff<K>(H->Fe, a.y, K - 1));
+            }
+        } else {  // parameter / coefficient / toric: parameters are series in lambda
+            taylor_inputs<K>(H->Fe, tx, t, nullptr);
+            run_taylor_tape<K>(H->Fe, M.tape);
+            for (int k = 0; k < H->Fe.nu; ++k) { int2 a = ld_i2(H->Fe.u_assign + k); u[a.x] = ser_coeff<K>(H->Fe, a.y, K); }
+        }
+    }
+
+    // ================================================================ linear algebra
+    HC_HD void updated() {  // linear_algebra.jl:88-98
+        factorized = false; scaled = false;
+        const int nn = n * n;
+        for (int i = 0; i < nn; ++i) M.LU[i] = M.A[i];
+    }
+    HC_HDN void lu_factor() {  // :130-184
+        const int nn = n;
+        CV A = M.LU;
+        for (int k = 0; k < nn; ++k) {
+            int kp = k;
+            double amax = abs2(A[k * nn + k]);
+            for (int i = k + 1; i < nn; ++i) { double v = abs2(A[k * nn + i]); if (v > amax) { kp = i; amax = v; } }
+            M.ipiv[k] = kp;
+            if (amax != 0.0) {
+                if (kp != k) for (int j = 0; j < nn; ++j) { cx tmp = A[j * nn + k]; A[j * nn + k] = A[j * nn + kp]; A[j * nn + kp] = tmp; }
+                cx pinv = cinv(A[k * nn + k]);
+                for (int i = k + 1; i < nn; ++i) A[k * nn + i] = A[k * nn + i] * pinv;
+            }
+            for (int j = k + 1; j < nn; ++j) {
+                cx akj = A[j * nn + k];
+                for (int i = k + 1; i < nn; ++i) A[j * nn + i] = cfnma(A[k * nn + i], akj, A[j * nn + i]);
+            }
+        }
+        factorized = true;
+        n_fact++;
+    }
+    HC_HDN void lu_solve(CV x) {  // :310-316 (in place)
+        const int nn = n;
+        CV A = M.LU;
+        for (int i = 0; i < nn; ++i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
+        for (int j = 0; j < nn; ++j) { cx xj = x[j]; for (int i = j + 1; i < nn; ++i) x[i] = cfnma(A[j * nn + i], xj, x[i]); }
+        for (int j = nn - 1; j >= 0; --j) {
+            cx xj = cdiv(x[j], A[j * nn + j]); x[j] = xj;
+            for (int i = 0; i < j; ++i) x[i] = cfnma(A[j * nn + i], xj, x[i]);
+        }
+    }
+    HC_HDN void lu_solve_adj(CV x) {  // :318-354 (in place)
+        const int nn = n;
+        CV A = M.LU;
+        for (int j = 0; j < nn; ++j) {
+            cx z = x[j];
+            for (int i = 0; i < j; ++i) z = cfnma(conj(A[j * nn + i]), x[i], z);
+            x[j] = cdiv(z, conj(A[j * nn + j]));
+        }
+        for (int j = nn - 1; j >= 0; --j) {
+            cx z = x[j];
+            for (int i = nn - 1; i > j; --i) z = cfnma(conj(A[j * nn + i]), x[i], z);
+            x[j] = z;
+        }
+        for (int i = nn - 1; i >= 0; --i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
+    }
+    // skeel_row_scaling!(d, A, c; threshold)  :432-459
+    HC_HDN void skeel(RV d, RV c, double threshold) {
+        const int nn = n;
+        for (int i = 0; i < nn; ++i) d[i] = 0.0;
+        for (int j = 0; j < nn; ++j) { double cj = c[j]; for (int i = 0; i < nn; ++i) d[i] += cabs(M.A[j * nn + i]) * cj; }
+        double m = d[0];
+        for (int i = 1; i < nn; ++i) m = jmax(m, d[i]);
+        double s = threshold + m;
+        for (int i = 0; i < nn; ++i) {
+            int e = 0; double di = d[i];
+            if (di != 0.0 && di == di && di < HC_INF) frexp(di, &e);
+            d[i] = (e < s) ? 1.0 : ldexp(1.0, -e);
+        }
+    }
+    // ldiv!(x, J, b[, norm])  :389-408, 833-862;  x may alias b
+    HC_HDN void ldiv(CV x, CV b, bool with_norm) {
+        const int nn = n;
+        n_ldiv++;
+        if (with_norm && !factorized) {
+            skeel(M.rs, M.w, -30.0);
+            for (int j = 0; j < nn; ++j) for (int i = 0; i < nn; ++i) M.LU[j * nn + i] = M.LU[j * nn + i] * M.rs[i];
+            scaled = true;
+        }
+        if (nn == 1) { x[0] = cdiv(b[0], M.A[0]); return; }
+        if (!factorized) lu_factor();
+        if (scaled) for (int i = 0; i < nn; ++i) x[i] = M.rs[i] * b[i];
+        else if (x.p != b.p) for (int i = 0; i < nn; ++i) x[i] = b[i];
+        lu_solve(x);
+    }
+    // one sweep of fixed precision refinement (:553-567); returns |dx| / |x| in the given norm
+    HC_HDN double refine_fixed(CV x, CV b, bool weighted) {
+        const int nn = n;
+        for (int i = 0; i < nn; ++i) M.wr[i] = -b[i];
+        for (int j = 0; j < nn; ++j) { cx xj = x[j]; for (int i = 0; i < nn; ++i) M.wr[i] = cfma(M.A[j * nn + i], xj, M.wr[i]); }
+        n_ldiv--;  // workspace-level ldiv! is not counted by Jacobian.ldivs
+        ldiv(M.wdx, M.wr, false);
+        for (int i = 0; i < nn; ++i) x[i] = x[i] - M.wdx[i];
+        return weighted ? wnorm(M.wdx, M.w, nn) / wnorm(x, M.w, nn) : inf_norm(M.wdx, nn) / inf_norm(x, nn);
+    }
+    // one sweep of mixed precision refinement (:528-544): residual A x - b accumulated in DD
+    HC_HDN double refine_mixed(CV x, CV b, bool weighted) {
+        const int nn = n;
+        for (int i = 0; i < nn; ++i) M.rbd.set(i, tocdd(-b[i]));
+        for (int j = 0; j < nn; ++j) {
+            cx xj = x[j];  // x converted exactly to DD, A stays fp64: products are exact two_prods
+            for (int i = 0; i < nn; ++i) {
+                cx a = M.A[j * nn + i];
+                dd rr = two_prod(a.re, xj.re) - two_prod(a.im, xj.im);
+                dd ri = two_prod(a.re, xj.im) + two_prod(a.im, xj.re);
+                cdd acc = M.rbd.get(i);
+                M.rbd.set(i, mkcdd(acc.re + rr, acc.im + ri));
+            }
+        }
+        for (int i = 0; i < nn; ++i) M.wr[i] = tocx(M.rbd.get(i));
+        n_ldiv--;
+        ldiv(M.wdx, M.wr, false);
+        for (int i = 0; i < nn; ++i) x[i] = x[i] - M.wdx[i];
+        return weighted ? wnorm(M.wdx, M.w, nn) / wnorm(x, M.w, nn) : inf_norm(M.wdx, nn) / inf_norm(x, nn);
+    }
+    // iterative_refinement!(x, J, b, norm; max_iters, tol)  :864-885
+    HC_HDN void iterative_refinement(CV x, CV b, bool weighted, int max_iters, double tol) {
+        n_ldiv++;
+        double d = refine_mixed(x, b, weighted);
+        for (int i = 2; i <= max_iters; ++i) {
+            n_ldiv++;
+            double d2 = refine_mixed(x, b, weighted);
+            if (d2 < tol) return;
+            if (d2 > 0.5 * d) return;
+            d = d2;
+        }
+    }
+    // Hager/Higham estimator of |diag(d_r)^-1 A^-1 diag(d_l)^-1|_inf  :585-682
+    HC_HDN double inverse_inf_norm_est(const RV* dl, const RV* dr) {
+        const int nn = n;
+        if (!factorized) lu_factor();
+        CV y = M.work; RV x = M.rwork;
+        for (int i = 0; i < nn; ++i) { double v = 1.0 / nn; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
+        lu_solve_adj(y);
+        double gamma = 0;
+        for (int i = 0; i < nn; ++i) {
+            cx v = y[i]; if (dl) v = v / (*dl)[i]; if (scaled) v = v * M.rs[i];
+            double a = cabs(v); gamma += a;
+            v = v / a; if (dl) v = v / (*dl)[i]; if (scaled) v = v / M.rs[i];
+            y[i] = v;
+        }
+        lu_solve(y);
+        for (int i = 0; i < nn; ++i) x[i] = dr ? y[i].re / (*dr)[i] : y[i].re;
+        int k = 2;
+        while (true) {
+            int j = 0; double mx = fabs(x[0]);
+            for (int i = 1; i < nn; ++i) { double a = fabs(x[i]); if (a > mx) { j = i; mx = a; } }
+            for (int i = 0; i < nn; ++i) { double v = (i == j) ? 1.0 : 0.0; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
+            lu_solve_adj(y);
+            double gbar = gamma; gamma = 0;
+            for (int i = 0; i < nn; ++i) {
+                cx v = y[i]; if (dl) v = v / (*dl)[i]; if (scaled) v = v * M.rs[i];
+                y[i] = v; gamma += cabs(v);
+            }
+            if (gamma <= gbar) { gamma = gbar; break; }
+            for (int i = 0; i < nn; ++i) {
+                cx v = y[i]; v = v / cabs(v); if (dl) v = v / (*dl)[i]; if (scaled) v = v / M.rs[i];
+                y[i] = v;
+            }
+            lu_solve(y);
+            double ninf = 0;
+            for (int i = 0; i < nn; ++i) { double v = dr ? y[i].re / (*dr)[i] : y[i].re; x[i] = v; ninf = jmax(ninf, fabs(v)); }
+            k += 1;
+            if (x[j] == ninf || k > 2) break;
+        }
+        return nanmin(gamma, HC_INF);
+    }
+    HC_HD double a_inf_norm(const RV* dl, const RV* dr) {  // :684-707
+        const int nn = n;
+        double nrm = -HC_INF;
+        for (int i = 0; i < nn; ++i) {
+            double ni = 0.0;
+            for (int j = 0; j < nn; ++j) ni += dr ? cabs(M.A[j * nn + i]) * (*dr)[j] : cabs(M.A[j * nn + i]);
+            if (dl) ni *= (*dl)[i];
+            nrm = fmaxq(nrm, ni);
+        }
+        return nrm;
+    }
+    HC_HDN double jac_cond(const RV* dl, const RV* dr) {  // :745-774
+        if (n == 1) {
+            double a = hypot(M.A[0].re, M.A[0].im);
+            if (dl) a *= (*dl)[0];
+            if (dr) a *= (*dr)[0];
+            return 1.0 / a;
+        }
+        return inverse_inf_norm_est(dl, dr) * a_inf_norm(dl, dr);
+    }
+    // LA.cond(tracker, x, t, d_l, d_r)  tracker.jl:509-514
+    HC_HDN double cond_at(CV x, cx t, const RV* dl, const RV* dr) {
+        eval_f64(M.r, &M.A, x, t);
+        updated();
+        return jac_cond(dl, dr);
+    }
+
+    // ================================================================ norm weights (norm.jl:101-136)
+    HC_HD void norm_init(CV x) {
+        const double pn = inf_norm(x, n);
+        for (int i = 0; i < n; ++i) {
+            double wi = cabs(x[i]);
+            if (wi < O->scale_min * pn) wi = O->scale_min * pn;
+            else if (wi > O->scale_max * pn) wi = O->scale_max * pn;
+            M.w[i] = jmax(wi, O->scale_abs_min);
+        }
+    }
+    HC_HD void norm_update(CV x) {
+        const double nx = wnorm(x, M.w, n);
+        for (int i = 0; i < n; ++i) {
+            double wi = (cabs(x[i]) + M.w[i]) / 2;
+            if (wi < O->scale_min * nx) wi = O->scale_min * nx;
+            else if (wi > O->scale_max * nx) wi = O->scale_max * nx;
+            if (wi == wi && wi < HC_INF && wi > -HC_INF) M.w[i] = jmax(wi, O->scale_abs_min);
+        }
+    }
+
+    // ================================================================ stepper (utils.jl:300-394)
+    HC_HD void st_init(cx a, cx b) {
+        st_start = a; st_target = b;
+        st_absd = hypot(b.re - a.re, b.im - a.im);
+        st_forward = hypot(a.re, a.im) < hypot(b.re, b.im);
+        st_s = st_sp = st_forward ? 0.0 : st_absd;
+    }
+    HC_HD bool st_done() const { return st_forward ? st_s == st_absd : st_s == 0.0; }
+    HC_HD void st_propose(double ds) { st_sp = st_forward ? jmin(st_s + ds, st_absd) : jmax(st_s - ds, 0.0); }
+    HC_HD double st_dist() const { return st_forward ? st_absd - st_s : st_s; }
+    HC_HD double st_ds() const { return st_forward ? st_sp - st_s : st_s - st_sp; }
+    HC_HD cx st_at(double s) const {
+        if (st_forward) {
+            if (s == 0.0) return st_start;
+            if (s == st_absd) return st_target;
+            return st_start + (s / st_absd) * (st_target - st_start);
+        }
+        if (s == st_absd) return st_start;
+        if (s == 0.0) return st_target;
+        return st_target + (s / st_absd) * (st_start - st_target);
+    }
+    HC_HD cx st_t() const { return st_at(st_s); }
+    HC_HD cx st_tp() const { return st_at(st_sp); }
+    HC_HD cx st_dt() const {
+        double f = st_forward ? (st_sp - st_s) / st_absd : (st_s - st_sp) / st_absd;
+        return f * (st_target - st_start);
+    }
+
+    // ================================================================ predictor
+    HC_HD void pred_init() {  // predictor.jl:124-133
+        cond_H = 1.0; winding = 1;
+        pt = pprev_t = ps = pprev_s = mk(HC_NAN, 0.0);
+        trust_region = local_error = HC_NAN;
+        pm_hermite = 0;
+    }
+    // update!(predictor, H, x, t, J, norm, xhat)  predictor.jl:158-284
+    HC_HDN void pred_update(cx t, bool have_xhat) {
+        const int nn = n;
+        CV x0 = M.tx, x1 = M.tx.at(nn), x2 = M.tx.at(2 * nn), x3 = M.tx.at(3 * nn);
+        for (int i = 0; i < 2 * nn; ++i) M.ptx1[i] = M.tx[i];
+        pprev_t = pt; pt = t;
+        if (winding > 1) { pprev_s = ps; ps = t_to_s_plane(t, winding); }
+        if (!have_xhat) local_error = HC_NAN;
+        else {
+            double ds = cabs(t - pprev_t), d2 = ds * ds;
+            local_error = wdist(M.xhat, M.x, M.w, nn) / (d2 * d2);
+        }
+        for (int i = 0; i < nn; ++i) x0[i] = M.x[i];
+        double nrm0 = wnorm(M.x, M.w, nn);
+        if (winding > 1) for (int i = 0; i < nn; ++i) M.ty1[i] = M.x[i];
+
+        taylor<1>(M.u, M.tx, t);
+        for (int i = 0; i < nn; ++i) M.u[i] = -M.u[i];
+        ldiv(M.xtemp, M.u, false);
+        double delta = refine_fixed(M.xtemp, M.u, true);
+        cond_H = delta / HC_EPS;
+        if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, false, 5, 1e-10);
+        double nrm1 = wnorm(M.xtemp, M.w, nn);
+        for (int i = 0; i < nn; ++i) x1[i] = M.xtemp[i];
+        if (winding > 1) {
+            cx mu = winding == 2 ? 2.0 * ps : (double)winding * cpow_pos(ps, winding - 1);
+            for (int i = 0; i < nn; ++i) M.ty1[nn + i] = mu * M.xtemp[i];
+            pm_hermite = 1;
+            trust_region = nrm0 / nrm1;
+            if (local_error != local_error) { double q = nrm1 / nrm0; local_error = q * q * q; }
+            return;
+        }
+        taylor<2>(M.u, M.tx, t);
+        for (int i = 0; i < nn; ++i) M.u[i] = -M.u[i];
+        ldiv(M.xtemp, M.u, false);
+        if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, true, 4, 1e-10);
+        double nrm2 = wnorm(M.xtemp, M.w, nn);
+        for (int i = 0; i < nn; ++i) x2[i] = M.xtemp[i];
+
+        taylor<3>(M.u, M.tx, t);
+        for (int i = 0; i < nn; ++i) M.u[i] = -M.u[i];
+        ldiv(M.xtemp, M.u, false);
+        if (delta > 1e-4) iterative_refinement(M.xtemp, M.u, true, 3, 1e-4);
+        double nrm3 = wnorm(M.xtemp, M.w, nn);
+        for (int i = 0; i < nn; ++i) x3[i] = M.xtemp[i];
+
+        double tau_ = HC_INF;
+        for (int i = 0; i < nn; ++i) {
+            double c1 = cabs(x1[i]), c2 = cabs(x2[i]), c3 = cabs(x3[i]);
+            double lam = jmax(1e-6, c1);
+            c1 /= lam; c2 /= lam * lam; c3 /= lam * lam * lam;
+            double tol = 1e-14 * jmax(jmax(c1, c2), c3);
+            if (!((c1 <= tol && c2 <= tol && c3 <= tol) || c2 <= tol)) {
+                double ti = (c2 / c3) / lam;
+                if (ti < tau_) tau_ = ti;
+            }
+        }
+        if (!(tau_ < HC_INF && tau_ > -HC_INF)) tau_ = nrm2 / nrm3;
+        if (!(tau_ < HC_INF && tau_ > -HC_INF)) tau_ = nrm0 / jmax(jmax(nrm0, nrm1), jmax(nrm2, nrm3));
+        pm_hermite = 0;
+        trust_region = tau_;
+        if (local_error != local_error) { double q = 1.0 / tau_; local_error = (q * q) * (q * q); }
+    }
+    HC_HD void cubic_hermite(CV xh, CV v0, CV d0, cx t0, CV v1, CV d1, cx t1, cx t) {  // predictor.jl:354-371
+        const int nn = n;
+        if (t0.im == 0 && t1.im == 0 && t.im == 0) {
+            double T = t.re, T0 = t0.re, T1 = t1.re;
+            double s = (T - T0) / (T1 - T0), oms2 = (1 - s) * (1 - s);
+            double h00 = (1 + 2 * s) * oms2, h10 = (T - T0) * oms2, h01 = (s * s) * (3 - 2 * s), h11 = (T - T0) * s * (s - 1);
+            for (int i = 0; i < nn; ++i) xh[i] = h00 * v0[i] + h10 * d0[i] + h01 * v1[i] + h11 * d1[i];
+        } else {
+            cx one = mk(1.0), s = cdiv(t - t0, t1 - t0), oms2 = (one - s) * (one - s);
+            cx h00 = (one + 2.0 * s) * oms2, h10 = (t - t0) * oms2, h01 = (s * s) * (mk(3.0) - 2.0 * s), h11 = (t - t0) * s * (s - one);
+            for (int i = 0; i < nn; ++i) xh[i] = h00 * v0[i] + h10 * d0[i] + h01 * v1[i] + h11 * d1[i];
+        }
+    }
+    HC_HDN void predict(cx t, cx dt) {  // predictor.jl:286-329
+        const int nn = n;
+        if (!pm_hermite) {
+            double lam = trust_region, lam2 = lam * lam, lam3 = lam2 * lam;
+            for (int i = 0; i < nn; ++i) {
+                cx X = M.tx[i], X1 = M.tx[nn + i], X2 = M.tx[2 * nn + i], X3 = M.tx[3 * nn + i];
+                double c = cabs(X), a1 = cabs(X1) * lam, a2 = cabs(X2) * lam2, a3 = cabs(X3) * lam3;
+                double tau_ = 1e-12 * sqrt(c * c + a1 * a1 + a2 * a2 + a3 * a3);
+                if (a3 <= tau_ || a2 <= tau_) M.xhat[i] = X + dt * (X1 + dt * X2);
+                else {
+                    cx d = mk(1.0) - cdiv(dt * X3, X2);
+                    M.xhat[i] = X + dt * (X1 + cdiv(dt * X2, d));
+                }
+            }
+        } else {
+            int mw = winding;
+            cx s0 = t_to_s_plane(pprev_t, mw), s1 = t_to_s_plane(t, mw), sp = t_to_s_plane(t + dt, mw);
+            cx psm, sm;
+            if (mw == 2) { psm = 2.0 * s0; sm = 2.0 * s1; }
+            else { psm = (double)mw * cpow_pos(s0, mw - 1); sm = (double)mw * cpow_pos(s1, mw - 1); }
+            for (int i = 0; i < nn; ++i) { M.pty1[i] = M.ptx1[i]; M.pty1[nn + i] = psm * M.ptx1[nn + i]; }
+            for (int i = 0; i < nn; ++i) { M.ty1[i] = M.tx[i]; M.ty1[nn + i] = sm * M.tx[nn + i]; }
+            cubic_hermite(M.xhat, M.pty1, M.pty1.at(nn), s0, M.ty1, M.ty1.at(nn), s1, sp);
+        }
+    }
+
+    // ================================================================ Newton corrector
+    // extended_prec_refinement_step!  newton_corrector.jl:55-78 (xout may alias xin)
+    HC_HDN double ext_refinement_step(CV xout, CV xin, cx t, bool simple_newton_step) {
+        const int nn = n;
+        eval_f64(M.r, &M.A, xin, t);
+        eval_dd(M.r, xin, nullptr, t);
+        updated();
+        ldiv(M.dx, M.r, true);
+        iterative_refinement(M.dx, M.r, true, 3, 1e-8);
+        for (int i = 0; i < nn; ++i) xout[i] = xin[i] - M.dx[i];
+        if (simple_newton_step) {
+            eval_dd(M.r, xout, nullptr, t);
+            ldiv(M.dx, M.r, true);
+        }
+        return wnorm(M.dx, M.w, nn);
+    }
+    // newton!  newton_corrector.jl:80-205; iterates live in xbar (x0 may alias xbar)
+    HC_HDN NewtonResult newton(CV x0, cx t, double mu_, double omega_, bool ext, bool accurate_mu, bool first_correction) {
+        const int nn = n;
+        const double a = O->a, h_a = hfun(a);
+        CV xi = M.xbar;
+        if (xi.p != x0.p) for (int i = 0; i < nn; ++i) xi[i] = x0[i];
+        NewtonResult R; R.mu_low = R.theta = R.norm_dx0 = HC_NAN; R.omega = omega_;
+        double ndxi = HC_NAN, ndxim1 = HC_NAN, abar = a;
+        for (int i = 0; i <= 10; ++i) {
+            eval_f64(M.r, &M.A, xi, t);
+            if (ext) eval_dd(M.r, xi, nullptr, t);
+            updated();
+            ldiv(M.dx, M.r, true);
+            if (ext) iterative_refinement(M.dx, M.r, true, 3, abar * abar);
+            ndxi = wnorm(M.dx, M.w, nn);
+            if (ndxi != ndxi) { R.code = NEWT_SINGULARITY; R.accuracy = ndxi; R.iters = i + 1; return R; }
+            for (int k = 0; k < nn; ++k) xi[k] = xi[k] - M.dx[k];
+            if (i == 0) R.norm_dx0 = ndxi;
+            if (i == 1) R.omega = 2 * ndxi / (ndxim1 * ndxim1);
+            if (i >= 1) R.theta = ndxi / ndxim1;
+            if ((i >= 1 && R.theta > abar) || (i == 0 && !first_correction && 0.125 * R.norm_dx0 * R.omega > h_a)) {
+                R.code = NEWT_TERMINATED; R.accuracy = ndxi; R.iters = i + 1; return R;
+            } else if (R.omega * ndxi * ndxi < 2 * mu_ * sqrt(1 - 2 * h_a)) {
+                eval_f64(M.r, &M.A, xi, t);
+                updated();
+                if (ext) {
+                    ldiv(M.dx, M.r, false);
+                    R.mu_low = wnorm(M.dx, M.w, nn);
+                    eval_dd(M.r, xi, nullptr, t);
+                }
+                ldiv(M.dx, M.r, false);
+                if (ext) iterative_refinement(M.dx, M.r, true, 3, abar * abar);
+                for (int k = 0; k < nn; ++k) xi[k] = xi[k] - M.dx[k];
+                double ndxip1 = wnorm(M.dx, M.w, nn);
+                if (ndxip1 != ndxip1) { R.code = NEWT_SINGULARITY; R.accuracy = ndxip1; R.iters = i + 1; return R; }
+                if (ndxip1 > sqrt(ndxi)) {
+                    R.theta = ndxip1 / ndxi; R.code = NEWT_TERMINATED; R.accuracy = ndxip1; R.iters = i + 2; return R;
+                }
+                if (ndxip1 > 2 * mu_ && ext) {
+                    eval_dd(M.r, xi, nullptr, t);
+                    ldiv(M.dx, M.r, false);
+                    ndxi = ndxip1;
+                    mu_ = ndxip1 = wnorm(M.dx, M.w, nn);
+                } else if (ndxip1 > 2 * mu_ || accurate_mu) {
+                    eval_f64(M.r, nullptr, xi, t);
+                    ldiv(M.dx, M.r, false);
+                    mu_ = wnorm(M.dx, M.w, nn);
+                } else mu_ = ndxip1;
+                if (i == 0) {
+                    double ob = 2 * ndxi / (ndxip1 * ndxip1);
+                    if (ob < R.omega) R.omega = ob; else R.omega *= 0.25;
+                }
+                R.code = NEWT_CONVERGED; R.accuracy = mu_; R.iters = i + 2; return R;
+            }
+            ndxim1 = ndxi;
+            if (i >= 1) abar *= abar;
+        }
+        R.code = NEWT_MAX_ITERS; R.accuracy = mu_; R.iters = 11; return R;
+    }
+    // init_newton!  newton_corrector.jl:207-286
+    HC_HDN bool init_newton(cx t, bool ext, double& omega_out, double& mu_out) {
+        const int nn = n;
+        const double a = O->a, a7 = a * a * a * a * a * a * a;
+        eval_f64(M.r, &M.A, M.x, t);
+        if (ext) eval_dd(M.r, M.x, nullptr, t);
+        updated();
+        ldiv(M.dx, M.r, true);
+        double v = wnorm(M.dx, M.w, nn) + HC_EPS;
+        bool valid = false;
+        omega_out = mu_out = HC_NAN;
+        double e = sqrt(v);
+        for (int k = 1; k <= 3; ++k) {
+            for (int i = 0; i < nn; ++i) M.xbar[i] = M.x[i] + mk(e * M.w[i]);
+            eval_f64(M.r, &M.A, M.xbar, t);
+            if (ext) eval_dd(M.r, M.xbar, nullptr, t);
+            updated();
+            ldiv(M.dx, M.r, true);
+            for (int i = 0; i < nn; ++i) M.xbar[i] = M.xbar[i] - M.dx[i];
+            double nd0 = wnorm(M.dx, M.w, nn);
+            if (ext) eval_dd(M.r, M.xbar, nullptr, t); else eval_f64(M.r, nullptr, M.xbar, t);
+            ldiv(M.dx, M.r, true);
+            for (int i = 0; i < nn; ++i) M.xbar[i] = M.xbar[i] - M.dx[i];
+            double nd1 = wnorm(M.dx, M.w, nn) + HC_EPS;
+            if (nd1 < a * nd0) {
+                omega_out = 2 * nd1 / (nd0 * nd0);
+                mu_out = nd1;
+                if (omega_out * mu_out > a7) {
+                    NewtonResult res = newton(M.xbar, t, a7 / omega_out, omega_out, ext, true, false);
+                    if (res.code == NEWT_CONVERGED) { valid = true; omega_out = res.omega; mu_out = res.accuracy; }
+                    else valid = false;
+                } else { valid = true; break; }
+            } else e *= sqrt(e);
+        }
+        return valid;
+    }
+
+    // ================================================================ tracker
+    HC_HD int steps() const { return accepted_steps + rejected_steps; }
+    HC_HD int ext_steps() const { return ext_accepted_steps + ext_rejected_steps; }
+
+    HC_HD double initial_step_size() {  // tracker.jl:520-539
+        double a = O->beta_a * O->a;
+        double e = local_error;
+        if (e == HC_INF || e == -HC_INF) e = 1e5;
+        double ds1 = nthroot((sqrt(1 + 2 * hfun(a)) - 1) / (omega * e), 4) / O->beta_omega_p;
+        double ds2 = O->beta_tau * trust_region;
+        double ds = nanmin(ds1, ds2);
+        return jmin(jmin(ds, O->max_step_size), O->max_initial_step_size);
+    }
+    HC_HD void update_stepsize(const NewtonResult& R) {  // tracker.jl:541-588
+        double a = O->beta_a * O->a;
+        double om = clampd(omega + 2 * (omega - omega_prev), omega, 8 * omega);
+        double ds;
+        if (R.code == NEWT_CONVERGED) {
+            double e = local_error;
+            double ds1 = nthroot((sqrt(1 + 2 * hfun(a)) - 1) / (om * e), 4) / O->beta_omega_p;
+            double ds2 = O->beta_tau * tau;
+            if (use_strict_beta_tau || st_dist() < ds2) ds2 = O->strict_beta_tau * tau;
+            ds = jmin(nanmin(ds1, ds2), O->max_step_size);
+            if (use_strict_beta_tau && st_dist() < ds) ds *= O->strict_beta_tau;
+            ds = jmin(ds, 10 * ds_prev);
+            if (last_steps_failed > 0) ds = jmin(ds, ds_prev);
+        } else {
+            int j = R.iters - 2;
+            int rootn = j >= 0 ? (1 << j) : 0;
+            double Th = rootn == 8 ? sqrt(sqrt(sqrt(R.theta))) : nthroot(R.theta, rootn);
+            double hT = hfun(Th), ha = hfun(0.5 * a);
+            if (Th != Th || R.code == NEWT_SINGULARITY || R.accuracy != R.accuracy || R.iters == 1 || hT < ha)
+                ds = 0.25 * st_ds();
+            else
+                ds = nthroot((sqrt(1 + 2 * ha) - 1) / (sqrt(1 + 2 * hT) - 1), 4) * st_ds();
+        }
+        st_propose(ds);
+    }
+    HC_HD void check_terminated() {  // tracker.jl:591-619
+        double tol_acc = HC_INF;
+        if (extended_prec || !O->extended_precision) {
+            double a = O->a;
+            tol_acc = pow(a, (double)((1 << O->min_newton_iters) - 1)) * hfun(a);
+        }
+        cx tp = st_tp(), t = st_t();
+        if (st_done()) code = TC_success;
+        else if (steps() >= O->max_steps) code = TC_terminated_max_steps;
+        else if (omega * mu > tol_acc) code = TC_terminated_accuracy_limit;
+        else if (st_ds() < min_step_size) code = TC_terminated_step_size_too_small;
+        else if (cabs(tp - t) <= 2 * eps_of(cabs(t))) code = TC_terminated_step_size_too_small;
+        else if (min_rel_step_size > 0 && !(tp.re == st_target.re && tp.im == st_target.im) && cabs(tp - t) < cabs(t) * min_rel_step_size)
+            code = TC_terminated_step_size_too_small;
+    }
+    // rank(J; rtol = 1e-14) < n ?  (tracker.jl:711-737).  One-sided Jacobi on the columns of LU (scratch).
+    HC_HDN bool jacobian_rank_deficient() {
+        const int nn = n;
+        CV V = M.LU;
+        for (int i = 0; i < nn * nn; ++i) { V[i] = M.A[i]; if (cisnan(M.A[i])) return false; }
+        for (int sweep = 0; sweep < 60; ++sweep) {
+            double off = 0;
+            for (int p = 0; p < nn; ++p)
+                for (int q = p + 1; q < nn; ++q) {
+                    double app = 0, aqq = 0; cx apq = mk(0.0);
+                    for (int i = 0; i < nn; ++i) { cx vp = V[p * nn + i], vq = V[q * nn + i]; app += abs2(vp); aqq += abs2(vq); apq = cfma(conj(vp), vq, apq); }
+                    double g = hypot(apq.re, apq.im);
+                    if (g <= 1e-300 || g <= 1e-17 * sqrt(app * aqq)) continue;
+                    off = fmax(off, g / sqrt(app * aqq));
+                    cx ph = apq / g;
+                    double zeta = (aqq - app) / (2 * g);
+                    double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+                    double c = 1 / sqrt(1 + tt * tt), s = c * tt;
+                    for (int i = 0; i < nn; ++i) {
+                        cx vp = V[p * nn + i], vq = V[q * nn + i] * conj(ph);
+                        V[p * nn + i] = c * vp - s * vq;
+                        V[q * nn + i] = (s * vp + c * vq) * ph;
+                    }
+                }
+            if (off < 1e-15) break;
+        }
+        double smax = 0;
+        for (int p = 0; p < nn; ++p) { double s2 = 0; for (int i = 0; i < nn; ++i) s2 += abs2(V[p * nn + i]); smax = fmax(smax, sqrt(s2)); }
+        int r = 0;
+        for (int p = 0; p < nn; ++p) { double s2 = 0; for (int i = 0; i < nn; ++i) s2 += abs2(V[p * nn + i]); if (sqrt(s2) > 1e-14 * smax) ++r; }
+        return r < nn;
+    }
+
+    // init!(tracker, x1, t1, t0; omega, mu, tau, max_initial_step_size, keep_steps, extended_precision)
+    // tracker.jl:639-754; M.x must already hold x1.
+    HC_HDN bool tracker_init(cx t1, cx t0, double omega_, double mu_, double tau_, double max_init_step, bool keep_steps, bool ext) {
+        st_init(t1, t0);
+        ds_prev = 0.0; accuracy = HC_EPS; omega = 1.0;
+        keep_extended_prec = false; use_strict_beta_tau = false;
+        norm_init(M.x);
+        n_fact = n_ldiv = 0;
+        code = TC_tracking;
+        if (!keep_steps) accepted_steps = rejected_steps = ext_accepted_steps = ext_rejected_steps = 0;
+        last_steps_failed = 0;
+        cx t = st_t();
+        bool valid = true;
+        if (omega_ != omega_ || mu_ != mu_) {
+            valid = init_newton(t, ext, omega_, mu_);
+            if (!valid && !ext) { ext = true; valid = init_newton(t, true, omega_, mu_); }
+        }
+        used_extended_prec = extended_prec = ext;
+        if (omega_ == omega_) omega = omega_;
+        if (valid) { accuracy = mu_; mu = jmax(mu_, HC_EPS); }
+        else {
+            eval_f64(M.r, &M.A, M.x, t);
+            code = jacobian_rank_deficient() ? TC_terminated_invalid_startvalue_singular_jacobian : TC_terminated_invalid_startvalue;
+            return false;
+        }
+        tau = tau_;
+        eval_f64(M.r, &M.A, M.x, t);
+        updated();
+        pred_init();
+        pred_update(t, false);
+        tau = trust_region;
+        double ds = initial_step_size();
+        ds = jmax(jmin(ds, max_init_step), min_step_size);
+        st_propose(ds);
+        omega_prev = omega;
+        return code == TC_tracking;
+    }
+    HC_HD void tracker_init_continue(cx t0) {  // init!(tracker, t0)  tracker.jl:756-766
+        code = TC_tracking;
+        st_init(st_t(), t0);
+        st_propose(initial_step_size());
+        ds_prev = 0.0;
+    }
+    HC_HDN void use_extended_precision() {  // tracker.jl:788-813
+        if (!O->extended_precision || extended_prec) return;
+        extended_prec = true; used_extended_prec = true;
+        double m_ = mu;
+        for (int i = 0; i < 2; ++i) m_ = ext_refinement_step(M.x, M.x, st_t(), false);
+        mu = jmax(m_, HC_EPS);
+    }
+    HC_HD void update_precision(double mu_low) {  // tracker.jl:768-786
+        if (!O->extended_precision) return;
+        const double a = O->a, a5 = a * a * a * a * a, a7 = a5 * a * a;
+        if (extended_prec && !keep_extended_prec && mu_low == mu_low && mu_low > mu) {
+            if (mu_low * omega < a7 * hfun(a)) { extended_prec = false; mu = mu_low; }
+        } else if (mu * omega > a5 * hfun(a)) use_extended_precision();
+    }
+    HC_HDN double refine_current_solution(double min_tol, int nsteps) {  // tracker.jl:815-844
+        const int nn = n;
+        double m_ = accuracy;
+        double mb = ext_refinement_step(M.xbar, M.x, st_t(), false);
+        if (mb < m_) { for (int i = 0; i < nn; ++i) M.x[i] = M.xbar[i]; m_ = mb; }
+        int k = 1;
+        while (m_ > min_tol && k <= nsteps) {
+            mb = ext_refinement_step(M.xbar, M.x, st_t(), true);
+            if (mb < m_) { for (int i = 0; i < nn; ++i) M.x[i] = M.xbar[i]; m_ = mb; }
+            k += 1;
+        }
+        return m_;
+    }
+    // step!(tracker)  tracker.jl:851-926; returns true iff the step was accepted
+    HC_HDN bool tracker_step() {
+        const int nn = n;
+        cx t = st_t(), dt = st_dt(), tp = st_tp();
+        predict(t, dt);
+        norm_update(M.xhat);
+        NewtonResult R = newton(M.xhat, tp, mu, omega, extended_prec, false, accepted_steps == 0);
+        if (R.code == NEWT_CONVERGED) {
+            for (int i = 0; i < nn; ++i) M.x[i] = M.xbar[i];
+            ds_prev = st_ds();
+            st_s = st_sp;
+            accuracy = R.accuracy;
+            mu = jmax(R.accuracy, HC_EPS);
+            omega_prev = omega;
+            omega = jmax(jmax(R.omega, 0.5 * omega), 0.1);
+            update_precision(R.mu_low);
+            if (st_done() && O->extended_precision && accuracy > 1e-14) {
+                accuracy = refine_current_solution(1e-14, 3);
+                refined_extended_prec = true;
+            }
+            pred_update(st_t(), true);
+            tau = trust_region;
+            accepted_steps += 1;
+            ext_accepted_steps += extended_prec ? 1 : 0;
+            last_steps_failed = 0;
+        } else {
+            rejected_steps += 1;
+            ext_rejected_steps += extended_prec ? 1 : 0;
+            last_steps_failed += 1;
+        }
+        update_stepsize(R);
+        check_terminated();
+        return last_steps_failed == 0;
+    }
+};
+
+}  // namespace hc

@@ -1,0 +1,148 @@
+/* hc_b200 -- C ABI of the B200-native batched path tracker for HomotopyContinuation.jl.
+ *
+ * This is the drop-in boundary: the Julia host (`ccall`) builds systems, start
+ * solutions and ModelKit instruction tapes and calls these entry points; the library implements
+ * the `track -> PathResult` contract of the reference's trackers on the GPU.
+ *
+ * What each entry point replaces in the reference (file:line under /root/reference):
+ *   hc_system_create            InterpretedSystem(F): src/model_kit/interpreted_system.jl:23-51; takes
+ *                               ModelKit.instruction_sequence(F) / jacobian_instruction_sequence(F)
+ *                               (src/model_kit/instruction_sequence.jl:133-143, 256-272) verbatim
+ *   hc_homotopy_create          StraightLineHomotopy / ParameterHomotopy / CoefficientHomotopy /
+ *                               ToricHomotopy constructors (src/homotopies/*.jl) incl. FixedParameterSystem
+ *   hc_track_batch   mode 0     track(::EndgameTracker, x, t1) for every start  (src/endgame_tracker.jl:902-914)
+ *                               driven like threaded_solve (src/solve.jl:628-709); with path_q it is
+ *                               many_solve (src/solve.jl:815-881) inverted to (parameter point x start)
+ *                    mode 1     track(::Tracker, x, t1, t0)                     (src/tracker.jl:1023-1026)
+ *   hc_polyhedral_track_batch   track(::PolyhedralTracker, (cell, x))           (src/polyhedral.jl:414-530)
+ *   hc_evaluate, hc_evaluate_dd, hc_evaluate_and_jacobian, hc_taylor
+ *                               the operator API evaluate!/evaluate_and_jacobian!/taylor!
+ *                               (src/model_kit/abstract_system_homotopy.jl:96-120), single point test hooks
+ *   hc_options                  TrackerOptions + TrackerParameters (src/tracker.jl:45-62, 94-140),
+ *                               EndgameOptions (src/endgame_tracker.jl:47-72), WeightedNormOptions (src/norm.jl:36-40)
+ *   hc_results                  struct-of-arrays of PathResult (src/path_result.jl:76-98)
+ *
+ * Conventions: every array is caller-owned and must stay alive for the duration of the (blocking)
+ * call; complex numbers are (re, im) pairs of doubles (Julia ComplexF64); matrices and batches are
+ * column-major as in Julia (starts: n x N, i.e. path k at starts[2*n*k ...]).  Functions returning
+ * int32 give 0 on success and a negative code on library errors (hc_last_error() describes it);
+ * per-path numerical failures are not errors but return codes in hc_results, as in the reference.
+ * There is no CPU fallback: without a usable CUDA device every compute entry point fails. */
+#ifndef HC_B200_H
+#define HC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    const int32_t* instructions; /* 6 int32 per Instruction: input[4], op, output (1-based); last = OP_STOP */
+    int32_t n_instructions;
+    const double* constants;     /* tape[1..C] */
+    int32_t n_constants;
+    int32_t param_offset, n_params; /* parameters_range = param_offset+1 : param_offset+n_params */
+    int32_t t_index;                /* continuation_parameter_index, 0 = nothing */
+    int32_t var_offset, n_vars;     /* variables_range */
+    const int32_t* u_assign;        /* u_assignments (i, k) */
+    int32_t n_u;
+    const int32_t* U_assign;        /* U_assignments (j, k) */
+    int32_t n_U;
+    int32_t out_dim, tape_space;    /* output_dim, tape_space_needed */
+} hc_program_desc;
+
+enum { HC_STRAIGHT_LINE = 0, HC_PARAMETER = 1, HC_COEFFICIENT = 2, HC_TORIC = 3 };
+
+typedef struct {
+    int32_t kind;
+    void* F;            /* hc_system: target system / the parametrised system */
+    void* G;            /* hc_system: start system (straight line only) */
+    double gamma[2];    /* straight line */
+    const double* G_params; int32_t n_G_params; /* fixed parameters of G (total degree `scaling`) */
+    const double* F_params; int32_t n_F_params; /* fixed parameters of F */
+    const double* p;    /* start parameters (t = 1); toric: start coefficients */
+    const double* q;    /* target parameters (t = 0) */
+    int32_t n_pq;
+} hc_homotopy_desc;
+
+typedef struct {
+    int32_t max_steps; double max_step_size, max_initial_step_size; int32_t extended_precision;
+    double min_step_size, min_rel_step_size;
+    double a, beta_a, beta_omega_p, beta_tau, strict_beta_tau; int32_t min_newton_iters;
+    double endgame_start; int32_t max_endgame_steps, max_endgame_extended_steps;
+    double min_cond, min_cond_growth, min_coord_growth;
+    int32_t zero_is_at_infinity, at_infinity_check, only_nonsingular;
+    double singular_min_accuracy; int32_t max_winding_number;
+    double val_finite_tol, val_at_infinity_tol, sing_cond, sing_accuracy, scaling_threshold;
+    int32_t refine_steps;
+    double scale_min, scale_abs_min, scale_max;
+} hc_options;
+
+typedef struct {
+    int32_t* return_code;        /* EndgameTrackerCode order (mode 0 / polyhedral), TrackerCode order (mode 1) */
+    double* solution;            /* 2n x N */
+    double* t;
+    double* accuracy;
+    double* residual;
+    uint8_t* singular;
+    double* condition_jacobian;  /* mode 1: TrackerResult.tau */
+    int32_t* winding_number;     /* 0 = nothing */
+    uint8_t* extended_precision;
+    double* last_point;          /* 2n x N */
+    double* last_t;
+    double* valuation;           /* n x N */
+    uint8_t* has_valuation;
+    double* omega;
+    double* mu;
+    int32_t* accepted_steps;
+    int32_t* rejected_steps;
+    int32_t* steps_eg;
+    uint8_t* extended_precision_used;
+    int64_t* counters;           /* optional 8 x N: factorizations, ldivs, evaljac, eval, eval_dd, taylor, 0, 0 */
+} hc_results;
+
+typedef struct {                 /* device timing of the last batch call on this thread */
+    double h2d_ms, kernel_ms, d2h_ms;
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t grid, block, lanes;
+    int64_t slab_bytes;
+} hc_timing;
+
+int32_t hc_init(int32_t device);            /* selects the CUDA device of this process */
+const char* hc_last_error(void);
+void hc_options_default(hc_options* o);
+void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac);
+void hc_system_destroy(void* s);
+void* hc_homotopy_create(const hc_homotopy_desc* d);
+void hc_homotopy_destroy(void* h);
+
+int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, const double* starts,
+                       const double* t1, const double* t0, const double* path_p, const double* path_q,
+                       const double* omega_mu, hc_results* out, int32_t reserved);
+int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* o, int64_t N, const double* starts,
+                                  const int32_t* cell_index, const double* cell_weights, int32_t ncells,
+                                  hc_results* out, int32_t reserved);
+void hc_get_timing(hc_timing* t);
+
+/* Device-resident variant for throughput measurement: inputs are uploaded once, results stay on
+ * the device; hc_resident_run may be called repeatedly (kernel only). */
+void* hc_resident_create(void* H, void* Hcoeff_or_null, const hc_options* o, int32_t mode, int64_t N, const double* starts,
+                         const double* t1, const double* t0, const double* path_p, const double* path_q,
+                         const int32_t* cell_index, const double* cell_weights, int32_t ncells);
+int32_t hc_resident_run(void* r, double* kernel_ms);
+int32_t hc_resident_fetch(void* r, hc_results* out);
+void hc_resident_destroy(void* r);
+
+/* single point test hooks of the operator API */
+int32_t hc_evaluate(void* H, const double* x, const double* t, double* u);
+int32_t hc_evaluate_dd(void* H, const double* x_hi, const double* x_lo, const double* t, double* u);
+int32_t hc_evaluate_and_jacobian(void* H, const double* x, const double* t, double* u, double* U);
+int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double* u);
+int32_t hc_toric_set_weights(void* H, const double* w);
+
+/* fp64 FMA pipe microbenchmark (roofline denominator): returns achieved GFLOP/s */
+double hc_dfma_peak(int32_t iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
