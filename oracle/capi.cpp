@@ -6,6 +6,8 @@
 #include "hc_oracle.h"
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 
@@ -93,6 +95,8 @@ void parallel_for(int64_t N, int nthreads, Fn make_worker) {
     for (auto& t : th) t.join();
 }
 
+static std::mutex g_hook_mutex;
+static std::map<const void*, std::vector<double>> g_hook_weights;
 }  // namespace
 
 extern "C" {
@@ -135,7 +139,10 @@ void* orc_homotopy_create(const orc_homotopy_desc* d) {
     else if (d->kind != H_STRAIGHT_LINE) { H->p = cvec(d->p, d->n_pq); H->q = cvec(d->q, d->n_pq); }
     return H;
 }
-void orc_homotopy_destroy(void* h) { delete (HomotopyDef*)h; }
+void orc_homotopy_destroy(void* h) {
+    { std::lock_guard<std::mutex> lock(g_hook_mutex); g_hook_weights.erase(h); }
+    delete (HomotopyDef*)h;
+}
 
 int32_t orc_track_batch(void* Hv, const orc_options* o, int32_t mode, int64_t N, const double* starts, const double* t1,
                         const double* t0, const double* path_p, const double* path_q, const double* omega_mu,
@@ -203,40 +210,45 @@ int32_t orc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const orc_options
 }
 
 // ------------------------------------------------------------------ test hooks
-static thread_local Homotopy* g_H = nullptr;
-static thread_local const HomotopyDef* g_D = nullptr;
-static Homotopy& hook_H(void* Hv) {
-    if (g_D != Hv) { delete g_H; g_H = new Homotopy(); g_H->init((const HomotopyDef*)Hv); g_D = (const HomotopyDef*)Hv; }
-    return *g_H;
-}
+// A fresh Homotopy per hook call (no caching by handle address: handles get recycled).
+struct HookH {
+    Homotopy H;
+    explicit HookH(void* Hv) {
+        H.init((const HomotopyDef*)Hv);
+        std::lock_guard<std::mutex> lock(g_hook_mutex);
+        auto it = g_hook_weights.find(Hv);
+        if (it != g_hook_weights.end()) for (int i = 0; i < H.P; ++i) H.weights[i] = it->second[i];
+    }
+};
 static void put(double* dst, const std::vector<cplx>& v) { for (size_t i = 0; i < v.size(); ++i) { dst[2 * i] = v[i].re; dst[2 * i + 1] = v[i].im; } }
 
 int32_t orc_toric_set_weights(void* Hv, const double* w) {
-    Homotopy& H = hook_H(Hv);
-    for (int i = 0; i < H.P; ++i) H.weights[i] = w[i];
+    const HomotopyDef* D = (const HomotopyDef*)Hv;
+    std::lock_guard<std::mutex> lock(g_hook_mutex);
+    g_hook_weights[Hv].assign(w, w + D->F->eval.P);
     return 0;
 }
 int32_t orc_evaluate(void* Hv, const double* x, const double* t, double* u) {
-    Homotopy& H = hook_H(Hv);
+    HookH hh(Hv); Homotopy& H = hh.H;
     std::vector<cplx> xv = cvec(x, H.n), uv(H.m);
     H.evaluate(uv.data(), xv.data(), cplx(t[0], t[1]));
     put(u, uv); return 0;
 }
 int32_t orc_evaluate_dd(void* Hv, const double* x_hi, const double* x_lo, const double* t, double* u) {
-    Homotopy& H = hook_H(Hv);
+    HookH hh(Hv); Homotopy& H = hh.H;
     std::vector<cdd> xv(H.n); std::vector<cplx> uv(H.m);
     for (int i = 0; i < H.n; ++i) xv[i] = cdd(dd(x_hi[2 * i], x_lo[2 * i]), dd(x_hi[2 * i + 1], x_lo[2 * i + 1]));
     H.evaluate_dd(uv.data(), xv.data(), cplx(t[0], t[1]));
     put(u, uv); return 0;
 }
 int32_t orc_evaluate_and_jacobian(void* Hv, const double* x, const double* t, double* u, double* U) {
-    Homotopy& H = hook_H(Hv);
+    HookH hh(Hv); Homotopy& H = hh.H;
     std::vector<cplx> xv = cvec(x, H.n), uv(H.m), Uv((size_t)H.m * H.n);
     H.evaluate_and_jacobian(uv.data(), Uv.data(), xv.data(), cplx(t[0], t[1]));
     put(u, uv); put(U, Uv); return 0;
 }
 int32_t orc_taylor(void* Hv, int32_t K, const double* tx, const double* t, double* u) {
-    Homotopy& H = hook_H(Hv);
+    HookH hh(Hv); Homotopy& H = hh.H;
     std::vector<cplx> xv = cvec(tx, K * H.n), uv(H.m);
     H.taylor(K, uv.data(), xv.data(), cplx(t[0], t[1]));
     put(u, uv); return 0;

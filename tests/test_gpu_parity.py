@@ -1,0 +1,127 @@
+"""Parity of the CUDA path (through the C ABI of libhc_b200.so) with the CPU oracle.
+
+Bar (BASELINE.json north_star): identical return codes / solution classes, every endpoint within
+1e-8 relative; operator-API values within 1e-12 relative (reference test/model_kit/e2e_test.jl:42-52)."""
+import numpy as np
+import pytest
+
+import ref_systems
+from helpers import assert_batches_match, rel_endpoint_error, straight_line, system_2x2
+from hcb200 import capi, lib, systems
+from hcb200.modelkit import make_system
+
+pytestmark = pytest.mark.gpu
+
+
+def track_td(api, F, gamma, tp=None, **kw):
+    td, H = straight_line(api, F, gamma, tp)
+    return H.track_batch(td.start_solutions(), **kw)
+
+
+@pytest.mark.parametrize("name", ["katsura", "tritangents", "cyclooctane", "biochem1", "steiner"])
+def test_operator_api(oracle, gpu, name):
+    rng = np.random.default_rng(11)
+    F, P = {"katsura": (systems.katsura(8), 0), "tritangents": (systems.tritangents(), 20), "cyclooctane": (systems.cyclooctane(), 36),
+            "biochem1": (systems.biochem1(), 10), "steiner": (ref_systems.steiner_higher_prec()[0], 30)}[name]
+    n = F.n_vars
+    p = rng.normal(size=P) + 1j * rng.normal(size=P); q = rng.normal(size=P) + 1j * rng.normal(size=P)
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    tx = np.stack([x, rng.normal(size=n) + 1j * rng.normal(size=n), rng.normal(size=n) + 1j * rng.normal(size=n)])
+    out = []
+    for api in (oracle, gpu):
+        H = api.homotopy(capi.H_PARAMETER, api.system(F), p=p, q=q)
+        u, U = H.evaluate_and_jacobian(x, 0.41)
+        out.append([u, U, H.evaluate(x, 0.41), H.evaluate_dd(x, x * 2.0 ** -54, 0.41)] + [H.taylor(K, tx[:K], 0.41) for K in (1, 2, 3)])
+    for a, b in zip(*out):
+        assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(a).max())
+
+
+def test_straight_line_operator_api(oracle, gpu):
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=9) + 1j * rng.normal(size=9)
+    tx = np.stack([x, 0.3 * x + 0.1j, 0.01 * x * x])
+    out = []
+    for api in (oracle, gpu):
+        td, H = straight_line(api, systems.katsura(8), 0.4 + 1.3j)
+        u, U = H.evaluate_and_jacobian(x, 0.37)
+        out.append([u, U, H.evaluate_dd(x, 0 * x, 0.37)] + [H.taylor(K, tx[:K], 0.37) for K in (1, 2, 3)])
+    for a, b in zip(*out):
+        assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(a).max())
+
+
+def test_endgame_golden_cases(oracle, gpu):  # reference test/endgame_tracker_test.jl:4-45
+    ro, rg = (track_td(api, system_2x2(), 0.4 + 1.3j) for api in (oracle, gpu))
+    assert_batches_match(ro, rg)
+    assert [capi.ENDGAME_CODES[c] for c in rg.return_code] == ["success", "success", "at_infinity", "at_infinity"]
+    assert np.allclose(rg.valuation[2], [-1, -1], rtol=1e-3) and rg.accuracy[0] < 1e-12 and rg.residual[0] < 1e-12
+    for d in (2, 3, 5):
+        F = make_system(lambda v, p: [(v[0] - 10) ** d], 1)
+        ro, rg = (track_td(api, F, np.exp(2j * np.pi * 0.123)) for api in (oracle, gpu))
+        assert_batches_match(ro, rg)
+        assert (rg.winding_number == d).all() and rg.singular.all() and (0 < rg.last_t).all() and (rg.last_t < 0.1).all()
+
+
+def test_katsura8_config1(oracle, gpu):  # BASELINE.json configs[0]: 256 paths
+    ro, rg = (track_td(api, systems.katsura(8), 0.4 + 1.3j, nthreads=8) for api in (oracle, gpu))
+    assert_batches_match(ro, rg)
+    assert (rg.return_code == 1).sum() == 256 and rg.singular.sum() == 0
+    assert rg.residual.max() < 1e-12
+    assert abs(int(ro.accepted_steps.sum()) - int(rg.accepted_steps.sum())) <= 0.02 * ro.accepted_steps.sum()
+
+
+def test_cyclic7_total_degree(oracle, gpu):  # reference test/endgame_test.jl:2-5: 924 of 5040 paths finite
+    ro, rg = (track_td(api, systems.cyclic(7), np.exp(2j * np.pi * 0.7133), nthreads=8) for api in (oracle, gpu))
+    assert int((rg.return_code == 1).sum()) == 924
+    assert_batches_match(ro, rg)
+
+
+def test_steiner_and_four_bar(oracle, gpu):  # golden endpoint vectors, needs DoubleDouble
+    F, g = ref_systems.steiner_higher_prec()
+    H = gpu.homotopy(capi.H_PARAMETER, gpu.system(F), p=g["p"], q=g["q"])
+    r = H.track_batch([g["s_p"]], mode=1)
+    assert capi.TRACKER_CODES[r.return_code[0]] == "success" and r.extended_precision_used[0]
+    assert np.allclose(r.solution[0], g["s_q"], rtol=1.5e-8, atol=0)
+    back = H.track_batch([r.solution[0]], mode=1, t1=0.0, t0=1.0, omega_mu=[r.omega[0], r.mu[0]])
+    assert np.allclose(back.solution[0], g["s_p"], rtol=1.5e-8, atol=0)
+    F, g = ref_systems.four_bar()
+    r = gpu.homotopy(capi.H_PARAMETER, gpu.system(F), p=g["p"], q=g["q"]).track_batch([g["s"]], mode=1)
+    assert capi.TRACKER_CODES[r.return_code[0]] == "success"
+
+
+def test_invalid_start_value(oracle, gpu):  # reference test/tracker_test.jl:93-105
+    F = make_system(lambda v, p: [v[0] ** 2 + v[1] ** 2 - 3, 2 * v[0] ** 2 + 0.5 * v[0] * v[1] + 3 * v[1] ** 2 - 2], 2)
+    td, H = straight_line(gpu, F, 1j)
+    r = H.track_batch([[100, -100], [1, 1]], mode=1)
+    assert capi.TRACKER_CODES[r.return_code[0]] == "terminated_invalid_startvalue"
+    assert capi.TRACKER_CODES[r.return_code[1]] == "success"
+
+
+def test_lane_refill_is_deterministic(gpu):
+    """Size-independent property: replicas of the same start must give bit-identical results whatever
+    lane / queue position they get (catches cross-lane aliasing and state leaking between paths)."""
+    td, H = straight_line(gpu, systems.katsura(8), 0.4 + 1.3j)
+    S = td.start_solutions()
+    R = 40
+    r = H.track_batch(np.tile(S, (R, 1)))
+    assert (r.return_code == 1).all()
+    sol = r.solution.reshape(R, 256, -1)
+    assert (sol == sol[0][None]).all()
+    assert (r.accepted_steps.reshape(R, 256) == r.accepted_steps[:256][None]).all()
+
+
+def test_parameter_sweep(oracle, gpu):  # BASELINE.json configs[4] at test size
+    F = systems.biochem1()
+    rng = np.random.default_rng(5)
+    p1 = rng.normal(size=10) + 1j * rng.normal(size=10)
+    td, H0 = straight_line(gpu, F, 0.4 + 1.3j, p1)
+    r0 = H0.track_batch(td.start_solutions())
+    starts = r0.solution[r0.return_code == 1]
+    K = 500
+    q = systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * rng.normal(size=(K, 10)))
+    S = np.repeat(starts[None], K, axis=0).reshape(-1, 3)
+    Q = np.repeat(q[:, None, :], len(starts), axis=1).reshape(-1, 10).astype(np.complex128)
+    ro, rg = (api.homotopy(capi.H_PARAMETER, api.system(F), p=p1, q=q[0]).track_batch(S, path_q=Q, nthreads=8) for api in (oracle, gpu))
+    assert_batches_match(ro, rg)
+    # residual check at the target parameters (property that holds at any size)
+    ok = rg.return_code == 1
+    assert rg.residual[ok].max() < 1e-9

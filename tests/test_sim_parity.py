@@ -1,0 +1,73 @@
+"""Kernel logic without a GPU: the device headers compiled for the host (tests/host_sim) must agree
+with the oracle.  This is a unit test of the code that runs on the B200, not a product path."""
+import numpy as np
+import pytest
+
+import ref_systems
+from helpers import assert_batches_match, straight_line, system_2x2
+from hcb200 import capi, systems
+from hcb200.modelkit import make_system
+
+
+def both(oracle, sim, build):
+    return [build(api) for api in (oracle, sim)]
+
+
+def test_operator_api(oracle, sim):
+    rng = np.random.default_rng(1)
+    F = systems.katsura(4)
+    x = rng.normal(size=5) + 1j * rng.normal(size=5)
+    tx = np.stack([x, 0.3 * x + 0.1j, 0.01 * x * x])
+    out = []
+    for api in (oracle, sim):
+        td, H = straight_line(api, F, 0.4 + 1.3j)
+        u, U = H.evaluate_and_jacobian(x, 0.37)
+        out.append([u, U, H.evaluate(x, 0.37), H.evaluate_dd(x, x * 2.0 ** -54, 0.37)] + [H.taylor(K, tx[:K], 0.37) for K in (1, 2, 3)])
+    for a, b in zip(*out):
+        assert np.abs(a - b).max() <= 1e-13 * max(1.0, np.abs(a).max())
+
+
+def test_endgame_paths(oracle, sim):
+    ro, rs = both(oracle, sim, lambda api: (lambda td_H: td_H[1].track_batch(td_H[0].start_solutions()))(straight_line(api, system_2x2(), 0.4 + 1.3j)))
+    assert_batches_match(ro, rs)
+    assert np.allclose(ro.valuation[2:], rs.valuation[2:], atol=1e-6)
+    F1 = make_system(lambda v, p: [(v[0] - 10) ** 3], 1)
+    ro, rs = both(oracle, sim, lambda api: (lambda td_H: td_H[1].track_batch(td_H[0].start_solutions()))(straight_line(api, F1, np.exp(0.77j))))
+    assert_batches_match(ro, rs)
+    assert (rs.winding_number == 3).all() and rs.singular.all()
+
+
+def test_katsura6(oracle, sim):
+    ro, rs = both(oracle, sim, lambda api: (lambda td_H: td_H[1].track_batch(td_H[0].start_solutions()))(straight_line(api, systems.katsura(6), 0.4 + 1.3j)))
+    assert_batches_match(ro, rs)
+    assert (rs.return_code == 1).sum() == 64
+    assert abs(int(ro.accepted_steps.sum()) - int(rs.accepted_steps.sum())) <= 0.02 * ro.accepted_steps.sum()
+
+
+def test_steiner_double_double(oracle, sim):
+    F, g = ref_systems.steiner_higher_prec()
+    rs = sim.homotopy(capi.H_PARAMETER, sim.system(F), p=g["p"], q=g["q"]).track_batch([g["s_p"]], mode=1)
+    assert capi.TRACKER_CODES[rs.return_code[0]] == "success" and rs.extended_precision_used[0]
+    assert np.allclose(rs.solution[0], g["s_q"], rtol=1.5e-8, atol=0)
+
+
+def test_parameter_sweep_per_path_targets(oracle, sim):
+    F = systems.biochem1()
+    rng = np.random.default_rng(5)
+    p1 = rng.normal(size=10) + 1j * rng.normal(size=10)
+    # start solutions of the generic instance via total degree
+    td, H0 = straight_line(oracle, F, 0.4 + 1.3j, p1)
+    r0 = H0.track_batch(td.start_solutions())
+    starts = r0.solution[(r0.return_code == 1)]
+    assert len(starts) >= 1
+    K = 6
+    q = systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * rng.normal(size=(K, 10)))
+    S = np.repeat(starts[None], K, axis=0).reshape(-1, 3)
+    Q = np.repeat(q[:, None, :], len(starts), axis=1).reshape(-1, 10).astype(np.complex128)
+    res = [api.homotopy(capi.H_PARAMETER, api.system(F), p=p1, q=q[0]).track_batch(S, path_q=Q) for api in (oracle, sim)]
+    assert_batches_match(*res)
+    # per-path targets really are used: path block k equals a homogeneous run with q[k]
+    one = sim.homotopy(capi.H_PARAMETER, sim.system(F), p=p1, q=q[3]).track_batch(starts)
+    blk = slice(3 * len(starts), 4 * len(starts))
+    assert (one.return_code == res[1].return_code[blk]).all()
+    assert np.allclose(one.solution, res[1].solution[blk], rtol=1e-12, atol=1e-14)
