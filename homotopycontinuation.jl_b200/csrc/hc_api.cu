@@ -233,7 +233,7 @@ __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, cons
     Lane L;
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = 0; L.kind = sA.H.kind;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, 1, 0);
-    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_taylor = 0;
+    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0;
     const int n = sA.H.n;
     if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
@@ -617,7 +617,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         Lane L;
         L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = 0; L.kind = A.H.kind;
         carve(L.M, n, P, A.H.tape_cx, A.cslab, A.rslab, A.islab, 1, 0);
-        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_taylor = 0;
+        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0;
         if (dtw) for (int i = 0; i < P; ++i) L.M.tw[i] = dtw[i];
         if (what == 3) for (int i = 0; i < K * n; ++i) L.M.tx[i] = dx[i]; else for (int i = 0; i < n; ++i) L.M.x[i] = dx[i];
         if (what == 0) L.eval_f64(L.M.u, nullptr, L.M.x, tt);

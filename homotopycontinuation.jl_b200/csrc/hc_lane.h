@@ -46,7 +46,7 @@ struct DevResults {  // caller's SoA, path-major (fields of src/path_result.jl:7
     double* condition_jacobian; int* winding_number; unsigned char* extended_precision; cx* last_point;
     double* last_t; double* valuation; unsigned char* has_valuation; double* omega; double* mu;
     int* accepted_steps; int* rejected_steps; int* steps_eg; unsigned char* extended_precision_used;
-    long long* counters;  // 8 per path: factorizations, ldivs, evaljac, eval, eval_dd, taylor, 0, 0
+    long long* counters;  // 8 per path: factorizations, ldivs, evaljac, eval, eval_dd, taylor K=1, K=2, K=3
 };
 
 struct BatchIn {
@@ -380,7 +380,7 @@ struct Lane : Path {
         R.accepted_steps[k] = accepted_steps; R.rejected_steps[k] = rejected_steps;
         if (R.counters) {
             long long* c = R.counters + 8 * k;
-            c[0] = c_fact + n_fact; c[1] = c_ldiv + n_ldiv; c[2] = n_evaljac; c[3] = n_eval; c[4] = n_evaldd; c[5] = n_taylor; c[6] = 0; c[7] = 0;
+            c[0] = c_fact + n_fact; c[1] = c_ldiv + n_ldiv; c[2] = n_evaljac; c[3] = n_eval; c[4] = n_evaldd; c[5] = n_tay1; c[6] = n_tay2; c[7] = n_tay3;
         }
         (void)valuation_ok;
     }
@@ -431,7 +431,7 @@ struct Lane : Path {
         for (int i = 0; i < nn; ++i) M.x[i] = B.starts[k * nn + i];
         refined_extended_prec = false; factorized = scaled = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
-        n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_taylor = 0; c_fact = c_ldiv = 0;
+        n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_tay1 = n_tay2 = n_tay3 = 0; c_fact = c_ldiv = 0;
         toric_acc = toric_rej = 0;
         double om = HC_NAN, mu_ = HC_NAN;
         if (B.omega_mu) { om = B.omega_mu[2 * k]; mu_ = B.omega_mu[2 * k + 1]; }

@@ -148,7 +148,7 @@ struct Path {
     int pm_hermite; double trust_region, local_error, cond_H;
     cx pt, pprev_t, ps, pprev_s; int winding;
     // ---- counters (src/linear_algebra.jl:809-826 + flop accounting of SURVEY.md 8(d))
-    int n_fact, n_ldiv, n_evaljac, n_eval, n_evaldd, n_taylor;
+    int n_fact, n_ldiv, n_evaljac, n_eval, n_evaldd, n_tay1, n_tay2, n_tay3;
 
     // ================================================================ homotopy
     HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)i * H->N + pidx] : ld_const(H->p + i); }
@@ -288,7 +288,7 @@ struct Path {
     // u = K-th Taylor coefficient of lambda -> H(x(lambda), t + lambda); tx rows x^0..x^{K-1}
     template <int K>
     HC_HDN void taylor(CV u, CV tx, cx t) {
-        n_taylor++;
+        if (K == 1) n_tay1++; else if (K == 2) n_tay2++; else n_tay3++;
         for (int i = 0; i < n; ++i) u[i] = mk(0.0);
         if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:130-154
             taylor_inputs<K>(H->Ge, tx, t, H->G_params);

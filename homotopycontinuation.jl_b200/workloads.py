@@ -1,0 +1,87 @@
+"""The benchmark workloads of BASELINE.json, built for any C-ABI backend (GPU library or, in the
+tests / CPU baseline, the oracle)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi, flops, start_systems, systems
+
+
+@dataclass
+class Workload:
+    name: str
+    description: str
+    n: int
+    starts: np.ndarray                    # (N, n) complex
+    mode: int = 0                         # 0 endgame tracker, 1 tracker, 2 polyhedral
+    build: callable = None                # api -> dict(H=..., [Hcoeff=...])
+    path_q: np.ndarray | None = None
+    cell_index: np.ndarray | None = None
+    cell_weights: np.ndarray | None = None
+    costs: dict = field(default_factory=dict)
+    expected: dict = field(default_factory=dict)
+
+    @property
+    def N(self):
+        return int(self.starts.shape[0])
+
+    def subset(self, count: int) -> "Workload":
+        count = min(count, self.N)
+        w = Workload(self.name, self.description, self.n, self.starts[:count], self.mode, self.build,
+                     None if self.path_q is None else self.path_q[:count],
+                     None if self.cell_index is None else self.cell_index[:count], self.cell_weights, self.costs, {})
+        return w
+
+    def track(self, api, handles, options=None, nthreads=1):
+        if self.mode == 2:
+            return capi.polyhedral_track_batch(api, handles["H"], handles["Hcoeff"], self.starts, self.cell_index,
+                                               self.cell_weights, options, nthreads)
+        return handles["H"].track_batch(self.starts, options=options, mode=self.mode, path_q=self.path_q, nthreads=nthreads)
+
+
+def katsura8(replicas: int = 1) -> Workload:
+    """BASELINE.json configs[0]: katsura(8) total-degree homotopy, 256 paths (x replicas for throughput)."""
+    F = systems.katsura(8)
+    td = start_systems.total_degree(F, 0.4 + 1.3j)   # gamma of reference test/endgame_tracker_test.jl:5
+
+    def build(api):
+        hF, hG = api.system(td.F), api.system(td.G)
+        return {"H": api.homotopy(capi.H_STRAIGHT_LINE, hF, hG, gamma=td.gamma, G_params=td.scaling, F_params=[])}
+    S = np.tile(td.start_solutions(), (replicas, 1))
+    return Workload("katsura8", f"katsura(8) total-degree homotopy, 256 paths x {replicas} replicas", 9, S, 0, build,
+                    costs=flops.homotopy_costs(td.F, td.G), expected={"success": 256 * replicas, "singular": 0})
+
+
+def cyclic7_total_degree(replicas: int = 1) -> Workload:
+    F = systems.cyclic(7)
+    td = start_systems.total_degree(F, np.exp(2j * np.pi * 0.7133))
+
+    def build(api):
+        hF, hG = api.system(td.F), api.system(td.G)
+        return {"H": api.homotopy(capi.H_STRAIGHT_LINE, hF, hG, gamma=td.gamma, G_params=td.scaling, F_params=[])}
+    S = np.tile(td.start_solutions(), (replicas, 1))
+    return Workload("cyclic7_td", f"cyclic-7 total-degree homotopy, 5040 paths x {replicas} replicas", 7, S, 0, build,
+                    costs=flops.homotopy_costs(td.F, td.G), expected={"success": 924 * replicas})
+
+
+def biochem_sweep(points: int, seed: int = 6) -> Workload:
+    """BASELINE.json configs[4]: parameter homotopy sweep of bio-chemical network 1
+    (benchmarks/bio-chemical-rection-networks.jl:19-26); the generic start solutions come from one
+    total-degree solve at p1 and are replicated for every parameter point."""
+    raise NotImplementedError("needs start solutions: use biochem_sweep_from_starts")
+
+
+def biochem_sweep_from_starts(starts: np.ndarray, p1: np.ndarray, points: int, seed: int = 6) -> Workload:
+    F = systems.biochem1()
+    rng = np.random.default_rng(seed)
+    q = systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * rng.normal(size=(points, 10)))
+    k = len(starts)
+    S = np.repeat(starts[None], points, axis=0).reshape(-1, 3)
+    Q = np.repeat(q[:, None, :], k, axis=1).reshape(-1, 10).astype(np.complex128)
+
+    def build(api):
+        return {"H": api.homotopy(capi.H_PARAMETER, api.system(F), p=p1, q=q[0])}
+    return Workload("biochem_sweep", f"bio-chemical network 1 parameter sweep, {points} parameter points x {k} start solutions",
+                    3, S, 0, build, path_q=Q, costs=flops.homotopy_costs(F))

@@ -97,7 +97,7 @@ typedef struct {
     int32_t* rejected_steps;
     int32_t* steps_eg;
     uint8_t* extended_precision_used;
-    int64_t* counters;           /* optional 8 x N: factorizations, ldivs, evaljac, eval, eval_dd, taylor, 0, 0 */
+    int64_t* counters;           /* optional 8 x N: factorizations, ldivs, evaljac, eval, eval_dd, taylor K=1, K=2, K=3 */
 } hc_results;
 
 typedef struct {                 /* device timing of the last batch call on this thread */
