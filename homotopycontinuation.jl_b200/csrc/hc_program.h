@@ -29,8 +29,15 @@ template <class T>
 struct SV {
     T* p;
     int s;
-    HC_HD T& operator[](int i) const { return p[(size_t)i * (size_t)s]; }
-    HC_HD SV<T> at(int off) const { SV<T> r; r.p = p + (size_t)off * (size_t)s; r.s = s; return r; }
+    // 32-bit index arithmetic (rows * lanes < 2^31) and a global-address-space hint: without them
+    // every access costs a 64-bit multiply and a generic LD/ST (ncu r01: IMAD+LEA+R2UR = 47 % of issue)
+    HC_HD T& operator[](int i) const {
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isGlobal(p));
+#endif
+        return p[(unsigned)i * (unsigned)s];
+    }
+    HC_HD SV<T> at(int off) const { SV<T> r; r.p = p + (unsigned)off * (unsigned)s; r.s = s; return r; }
 };
 using CV = SV<cx>;
 using RV = SV<double>;
@@ -43,12 +50,18 @@ struct DV {
     cx* p;
     int s;
     HC_HD cdd get(int i) const {
-        cx a = p[(size_t)(2 * i) * (size_t)s], b = p[(size_t)(2 * i + 1) * (size_t)s];
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isGlobal(p));
+#endif
+        cx a = p[(unsigned)(2 * i) * (unsigned)s], b = p[(unsigned)(2 * i + 1) * (unsigned)s];
         return mkcdd(mkdd(a.re, a.im), mkdd(b.re, b.im));
     }
     HC_HD void set(int i, cdd v) const {
-        p[(size_t)(2 * i) * (size_t)s] = mk(v.re.hi, v.re.lo);
-        p[(size_t)(2 * i + 1) * (size_t)s] = mk(v.im.hi, v.im.lo);
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isGlobal(p));
+#endif
+        p[(unsigned)(2 * i) * (unsigned)s] = mk(v.re.hi, v.re.lo);
+        p[(unsigned)(2 * i + 1) * (unsigned)s] = mk(v.im.hi, v.im.lo);
     }
 };
 HC_HD cx tget(CV t, int i) { return t[i]; }
