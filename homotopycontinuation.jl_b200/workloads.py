@@ -6,7 +6,11 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import capi, flops, start_systems, systems
+import os
+
+from . import capi, flops, polyhedral, start_systems, systems
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
 @dataclass
@@ -64,6 +68,23 @@ def cyclic7_total_degree(replicas: int = 1) -> Workload:
     S = np.tile(td.start_solutions(), (replicas, 1))
     return Workload("cyclic7_td", f"cyclic-7 total-degree homotopy, 5040 paths x {replicas} replicas", 7, S, 0, build,
                     costs=flops.homotopy_costs(td.F, td.G), expected={"success": 924 * replicas})
+
+
+def cyclic_polyhedral(n: int = 7, replicas: int = 1) -> Workload:
+    """BASELINE.json configs[1]: cyclic-7 polyhedral start system, 924 mixed-volume paths (x replicas).
+    Lifting and mixed cells are cached in tests/golden (deterministic in the seeds; the enumeration
+    takes about a minute for n = 7)."""
+    ps = polyhedral.polyhedral(systems.cyclic(n), cache=os.path.join(_GOLDEN, f"cyclic{n}_cells.json"))
+    S, ci = ps.start_solutions()
+    cw = ps.cell_weights()
+
+    def build(api):
+        h = api.system(ps.F)
+        return {"H": api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs),
+                "Hcoeff": api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)}
+    return Workload(f"cyclic{n}_polyhedral", f"cyclic-{n} polyhedral homotopy, {len(S)} mixed-volume paths x {replicas} replicas", n,
+                    np.tile(S, (replicas, 1)), 2, build, cell_index=np.tile(ci, replicas), cell_weights=cw,
+                    costs=flops.homotopy_costs(ps.F), expected={"success": len(S) * replicas})
 
 
 def biochem_sweep(points: int, seed: int = 6) -> Workload:

@@ -125,3 +125,13 @@ def test_parameter_sweep(oracle, gpu):  # BASELINE.json configs[4] at test size
     # residual check at the target parameters (property that holds at any size)
     ok = rg.return_code == 1
     assert rg.residual[ok].max() < 1e-9
+
+
+def test_cyclic7_polyhedral_config2(oracle, gpu):  # BASELINE.json configs[1]: 924 mixed-volume paths
+    from hcb200 import workloads
+    w = workloads.cyclic_polyhedral(7)
+    ro, rg = (w.track(api, w.build(api), nthreads=8) for api in (oracle, gpu))
+    assert_batches_match(ro, rg)
+    assert (rg.return_code == 1).sum() == 924 and rg.singular.sum() == 0
+    assert len(np.unique(np.round(rg.solution, 6), axis=0)) == 924
+    assert rg.residual.max() < 1e-10

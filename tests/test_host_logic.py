@@ -42,3 +42,50 @@ def test_support_coefficients_and_degrees():
     td = start_systems.total_degree(F, 0.4 + 1.3j, c)
     assert list(td.degrees) == [2, 2, 3, 4] * 3 and td.n_paths() == 110592   # benchmarks/tritangents.jl
     assert systems.cyclooctane().n_eqs == 17 and systems.cyclic(7).n_eqs == 7
+
+
+def test_hermite_normal_form_and_binomial_systems():
+    """x^A = b has |det A| solutions, all valid (reference test/binomial_system_test.jl:107-120 checks residuals)."""
+    from hcb200 import polyhedral as ph
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 5):
+        for _ in range(5):
+            A = rng.integers(-4, 5, size=(n, n))
+            d = abs(ph._int_det(A))
+            if d == 0:
+                continue
+            H, U = ph.hnf(A)
+            assert (np.array(A, dtype=object).dot(U) == H).all()
+            assert all(H[i][j] == 0 for i in range(n) for j in range(i + 1, n))
+            assert all(0 <= H[i][j] < H[i][i] for i in range(n) for j in range(i))
+            b = rng.normal(size=n) + 1j * rng.normal(size=n)
+            X = ph.solve_binomial_system(A, b)
+            assert X.shape == (n, d)
+            for k in range(d):
+                for j in range(n):
+                    assert abs(np.prod(X[:, k] ** A[:, j].astype(float)) - b[j]) < 1e-9 * max(1, abs(b[j]))
+            assert len(np.unique(np.round(X.T, 9), axis=0)) == d
+
+
+def test_mixed_cells_give_the_mixed_volume():
+    """Sum of the cell volumes == mixed volume: 6 (cyclic-3), 70 (cyclic-5, reference test/polyhedral_test.jl:38-46),
+    and 924 for the cached cyclic-7 subdivision whose cells are re-verified here against the definition."""
+    from hcb200 import polyhedral as ph
+    assert ph.polyhedral(systems.cyclic(3)).n_paths() == 6
+    ps = ph.polyhedral(systems.cyclic(5))
+    assert ps.n_paths() == 70
+    import os
+    cache = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cyclic7_cells.json")
+    ps = ph.polyhedral(systems.cyclic(7), cache=cache)
+    assert ps.n_paths() == 924
+    for cell in ps.cells:   # every cached cell satisfies the mixed-cell inequalities for the cached lifting
+        E = np.array([ps.support[i][:, a] - ps.support[i][:, b] for i, (a, b) in enumerate(cell.indices)])
+        assert abs(ph._int_det(E)) == cell.volume
+        for i, A in enumerate(ps.support):
+            v = A.T @ cell.normal + ps.lifting[i]
+            a, b = cell.indices[i]
+            assert abs(v[a] - cell.beta[i]) < 1e-7 and abs(v[b] - cell.beta[i]) < 1e-7
+            rest = np.delete(v, [a, b])
+            assert rest.size == 0 or rest.min() > cell.beta[i] + 1e-9
+    w = ps.cell_weights()
+    assert w.shape == (len(ps.cells), len(ps.start_coeffs)) and (w >= 0).all()

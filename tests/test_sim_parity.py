@@ -71,3 +71,21 @@ def test_parameter_sweep_per_path_targets(oracle, sim):
     blk = slice(3 * len(starts), 4 * len(starts))
     assert (one.return_code == res[1].return_code[blk]).all()
     assert np.allclose(one.solution, res[1].solution[blk], rtol=1e-12, atol=1e-14)
+
+
+def test_polyhedral_cyclic5(oracle, sim):
+    """PolyhedralTracker two-stage track (reference src/polyhedral.jl:414-530): 70 mixed-volume paths, 70 solutions
+    (reference test/polyhedral_test.jl:38-46)."""
+    from hcb200 import polyhedral as ph
+    ps = ph.polyhedral(systems.cyclic(5))
+    S, ci = ps.start_solutions()
+    cw = ps.cell_weights()
+    res = []
+    for api in (oracle, sim):
+        h = api.system(ps.F)
+        Ht = api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs)
+        Hc = api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)
+        res.append(capi.polyhedral_track_batch(api, Ht, Hc, S, ci, cw))
+    assert_batches_match(*res)
+    assert (res[1].return_code == 1).sum() == 70
+    assert len(np.unique(np.round(res[1].solution, 6), axis=0)) == 70
