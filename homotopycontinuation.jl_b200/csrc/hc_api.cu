@@ -1,7 +1,7 @@
 // libhc_b200: kernels + C ABI (include/hc_b200.h).
 //
-// One persistent kernel per batch: grid = #SMs x resident CTAs, one solution path per thread,
-// all lanes pull path indices from a device-side atomic queue (the `next_k` work counter of
+// One persistent kernel per batch: grid = #SMs x resident CTAs, one solution path per group of
+// G lanes (state in shared memory), all groups pull path indices from a device-side atomic queue (the `next_k` work counter of
 // threaded_solve, reference src/solve.jl:641, 660-667, moved onto the device) and write their
 // PathResult by path index (src/solve.jl:637, 670).
 //
@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "hc_lane.h"
+#include "hc_lower.h"
 
 #ifndef HC_HOST_SIM
 #include <cuda_runtime.h>
@@ -65,7 +66,7 @@ T* to_dev(const std::vector<T>& v) {
 // ------------------------------------------------------------------ handles
 struct ProgramH {
     DevProgram dev;  // pointers into device memory
-    int L = 0;
+    LoweredProgram low;
     std::vector<void*> owned;
     ~ProgramH() { for (void* p : owned) dev_free(p); }
 };
@@ -81,63 +82,38 @@ struct HomotopyH {
     ~HomotopyH() { for (void* p : owned) dev_free(p); }
 };
 
-bool supported_op(int op) {
-    switch (op) {
-        case OP_STOP: case OP_CB: case OP_INV: case OP_INV_NOT_ZERO: case OP_INVSQR: case OP_NEG: case OP_SQR:
-        case OP_IDENTITY: case OP_ADD: case OP_DIV: case OP_MUL: case OP_SUB: case OP_POW_INT: case OP_ADD3:
-        case OP_MUL3: case OP_MULADD: case OP_MULSUB: case OP_SUBMUL: case OP_ADD4: case OP_MUL4:
-        case OP_MULMULADD: case OP_MULMULSUB: return true;
-        default: return false;
-    }
+int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
+
+// lanes per path: enough lanes for the vectors / tape rounds of the system, never more than a warp
+int group_size_for(int n) {
+    int G = n > 8 ? 32 : 8;
+    G = env_int("HC_B200_GROUP", G);
+    if (G != 8 && G != 32) throw std::string("HC_B200_GROUP must be 8 or 32");
+    return G;
 }
 
-// Repack the reference's 24-byte, 1-based Instruction stream into 16-byte, 0-based PInstr.
+int engine_for(int n);
+
+// Lower the reference's 24-byte, 1-based Instruction stream (hc_lower.h) and upload it.
 void build_program(ProgramH& H, const hc_program_desc* d) {
-    if (d->tape_space >= 65536) throw std::string("tape_space >= 65536 is not supported by the packed format");
-    std::vector<PInstr> ins(d->n_instructions);
-    bool stopped = false;
-    for (int i = 0; i < d->n_instructions; ++i) {
-        const int32_t* s = d->instructions + 6 * (size_t)i;
-        int op = s[4];
-        if (!supported_op(op)) throw std::string("unsupported op in tape: ") + std::to_string(op);
-        PInstr I;
-        if (op == OP_STOP) { I.w0 = OP_STOP; I.w1 = I.w2 = 0; I.lit = 0; ins[i] = I; stopped = true; ins.resize(i + 1); break; }
-        auto slot = [&](int v) {
-            if (v < 1 || v > d->tape_space) throw std::string("tape index out of range");
-            return (uint32_t)(v - 1);
-        };
-        uint32_t a0 = slot(s[0]);
-        uint32_t a1 = (op == OP_POW_INT) ? a0 : slot(s[1]);
-        uint32_t a2 = slot(op == OP_POW_INT ? s[0] : s[2]), a3 = slot(op == OP_POW_INT ? s[0] : s[3]);
-        uint32_t out = slot(s[5]);
-        if ((int)out < d->n_constants) throw std::string("instruction writes into the constants block");
-        I.w0 = (uint32_t)op | (out << 8);
-        I.w1 = a0 | (a1 << 16);
-        I.w2 = a2 | (a3 << 16);
-        I.lit = (op == OP_POW_INT) ? s[1] : 0;
-        ins[i] = I;
-    }
-    if (!stopped) throw std::string("tape is not terminated by OP_STOP");
-    std::vector<cx> consts(d->n_constants);
-    for (int i = 0; i < d->n_constants; ++i) consts[i] = mk(d->constants[2 * i], d->constants[2 * i + 1]);
-    std::vector<int2> ua(d->n_u), Ua(d->n_U);
-    for (int i = 0; i < d->n_u; ++i) {
-        ua[i].x = d->u_assign[2 * i] - 1; ua[i].y = d->u_assign[2 * i + 1] - 1;
-        if (ua[i].x < 0 || ua[i].x >= d->out_dim || ua[i].y < 0 || ua[i].y >= d->tape_space) throw std::string("bad u assignment");
-    }
-    for (int i = 0; i < d->n_U; ++i) {
-        Ua[i].x = d->U_assign[2 * i] - 1; Ua[i].y = d->U_assign[2 * i + 1] - 1;
-        if (Ua[i].x < 0 || Ua[i].x >= d->out_dim * d->n_vars || Ua[i].y < 0 || Ua[i].y >= d->tape_space) throw std::string("bad U assignment");
-    }
-    if (d->param_offset < d->n_constants || d->var_offset < d->n_constants) throw std::string("inputs overlap the constants block");
+#ifdef HC_HOST_SIM
+    const int cap = env_int("HC_B200_ROUND_CAP", 0);
+#else
+    const int cap = engine_for(d->n_vars) == 1 ? 0 : env_int("HC_B200_ROUND_CAP", 2 * group_size_for(d->n_vars));
+#endif
+    H.low = lower_program(d, cap, env_int("HC_B200_PRIO_HEIGHT", 1) != 0, cap == 0 && env_int("HC_B200_TAPE_PAIRS", 0) != 0);
+    const LoweredProgram& L = H.low;
     DevProgram& P = H.dev;
-    P.instr = to_dev(ins); P.consts = to_dev(consts); P.u_assign = to_dev(ua); P.U_assign = to_dev(Ua);
-    H.owned = {(void*)P.instr, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign};
-    H.L = (int)ins.size();
-    P.C = d->n_constants; P.param_off = d->param_offset; P.P = d->n_params;
-    P.t_slot = d->t_index > 0 ? d->t_index - 1 : -1;
-    P.var_off = d->var_offset; P.n = d->n_vars; P.out_dim = d->out_dim; P.W = d->tape_space;
-    P.nu = d->n_u; P.nU = d->n_U;
+    P.ops = to_dev(L.ops); P.level_end = to_dev(L.level_end); P.consts = to_dev(L.consts);
+    P.u_assign = to_dev(L.u_assign); P.U_assign = to_dev(L.U_assign);
+    H.owned = {(void*)P.ops, (void*)P.level_end, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign};
+    P.n_levels = (int)L.level_end.size(); P.n_ops = (int)L.ops.size();
+    P.C = (int)L.consts.size(); P.param_off = L.param_off; P.P = L.P; P.t_slot = L.t_slot;
+    P.var_off = L.var_off; P.n = L.n; P.out_dim = L.out_dim; P.W = L.W;
+    P.nu = (int)L.u_assign.size(); P.nU = (int)L.U_assign.size();
+    if (getenv("HC_B200_VERBOSE"))
+        fprintf(stderr, "[hc_b200] program: %d reference instructions -> %d micro-ops in %d levels (max width %d), tape %d -> %d slots\n",
+                d->n_instructions, P.n_ops, P.n_levels, L.max_width, d->tape_space, P.W);
 }
 
 cx* cvec_dev(const double* p, int n, std::vector<void*>& owned) {
@@ -161,10 +137,14 @@ struct KArgs {
     DevOptions O;
     BatchIn B;
     DevResults R;
-    cx* cslab; double* rslab; int* islab;
     unsigned long long* queue;
-    int stage;  // 1: copy the tapes into shared memory
-    int static_sched;  // debug: 1 = lane l tracks paths l, l + T, ... instead of pulling from the queue
+    int stage;            // 1: copy the programs into shared memory
+    int slab_bytes;       // per-path shared-memory slab
+    int cold_bytes;       // per-group scratch in global memory
+    unsigned char* cold;
+    cx* cslab; double* rslab; int* islab;  // thread-per-path engine: lane-interleaved state slabs
+    int refill_min;       // thread-per-path engine: idle lanes of a warp refill together once this many wait
+    int stage_bytes;      // staged programs (0 when !stage)
 };
 
 #ifndef HC_HOST_SIM
@@ -182,70 +162,118 @@ __device__ const T* stage_array(const T* src, int count, unsigned char*& cur) {
     cur += bytes;
     return dst;
 }
-__device__ void stage_program(DevProgram& P, int L, unsigned char*& cur) {
-    P.instr = stage_array(P.instr, L, cur);
+__device__ void stage_program(DevProgram& P, unsigned char*& cur) {
+    P.ops = stage_array(P.ops, P.n_ops, cur);
+    P.level_end = stage_array(P.level_end, P.n_levels, cur);
     P.consts = stage_array(P.consts, P.C, cur);
     P.u_assign = stage_array(P.u_assign, P.nu, cur);
     P.U_assign = stage_array(P.U_assign, P.nU, cur);
 }
 
-struct StageLens { int LFe, LFj, LGe, LGj; };
-
-__global__ void __launch_bounds__(128) hc_track_kernel(const __grid_constant__ KArgs A, const StageLens SL) {
+// Persistent tracker: each group of G lanes owns one shared-memory slab, pulls path indices from
+// the device-side queue (the `next_k` counter of threaded_solve, src/solve.jl:641, 660-667) and
+// writes its PathResult by path index (src/solve.jl:637, 670).
+template <int G>
+__global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant__ KArgs A) {
     __shared__ KArgs sA;
     if (threadIdx.x == 0) sA = A;
     __syncthreads();
     if (A.stage) {
         DevHomotopy h = A.H;  // every thread computes the same pointers
         unsigned char* cur = hc_smem;
-        stage_program(h.Fe, SL.LFe, cur);
-        stage_program(h.Fj, SL.LFj, cur);
-        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, SL.LGe, cur); stage_program(h.Gj, SL.LGj, cur); }
+        stage_program(h.Fe, cur);
+        stage_program(h.Fj, cur);
+        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur); stage_program(h.Gj, cur); }
         __syncthreads();
         if (threadIdx.x == 0) sA.H = h;
         __syncthreads();
     }
-    Lane L;
+    Lane<G, false> L;
+    L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
-    const int T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, T, tid);
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem + A.stage_bytes + (size_t)(threadIdx.x / G) * A.slab_bytes,
+          A.cold + ((size_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G) * A.cold_bytes);
     L.phase = PH_IDLE;
-    bool drained = false;
     const long long N = sA.B.N;
-    long long next_static = tid;
     while (true) {
-        if (L.phase == PH_IDLE && !drained) {
-            long long k;
-            if (A.static_sched) { k = next_static; next_static += T; }
-            else k = (long long)atomicAdd(A.queue, 1ULL);
-            if (k < N) L.start_path(k, sA.B, sA.R);
-            else drained = true;
+        if (L.phase == PH_IDLE) {
+            long long k = 0;
+            if (L.g.lane == 0) k = (long long)atomicAdd(A.queue, 1ULL);
+            k = L.g.bcast(k, 0);
+            if (k >= N) break;
+            L.start_path(k, sA.B, sA.R);
         }
-        if (__all_sync(0xffffffffu, L.phase == PH_IDLE && drained)) break;
         if (L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
     }
 }
 
-// single-lane operator-API hooks
+// Thread-per-path engine (small systems): every lane tracks its own path, the per-lane state lives
+// in lane-interleaved global memory (L2-resident, coalesced), the programs in shared memory.  Idle
+// lanes of a warp take new paths from the queue together, so that the start-up code of a path
+// (init_newton!, first predictor update) runs converged instead of stalling the warp once per lane.
+__global__ void __launch_bounds__(128) hc_track_tpp_kernel(const __grid_constant__ KArgs A) {
+    __shared__ KArgs sA;
+    if (threadIdx.x == 0) sA = A;
+    __syncthreads();
+    if (A.stage) {
+        DevHomotopy h = A.H;
+        unsigned char* cur = hc_smem;
+        stage_program(h.Fe, cur);
+        stage_program(h.Fj, cur);
+        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur); stage_program(h.Gj, cur); }
+        __syncthreads();
+        if (threadIdx.x == 0) sA.H = h;
+        __syncthreads();
+    }
+    Lane<1, true> L;
+    L.g.init();
+    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
+    const int T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, T, tid);
+    L.phase = PH_IDLE;
+    const long long N = sA.B.N;
+    const unsigned lane = threadIdx.x & 31u;
+    bool drained = false;  // warp-uniform
+    while (true) {
+        const unsigned idle = __ballot_sync(0xffffffffu, L.phase == PH_IDLE);
+        const int n_idle = __popc(idle);
+        if (!drained && (n_idle >= A.refill_min || n_idle == 32)) {
+            long long base = 0;
+            if (lane == 0) base = (long long)atomicAdd(A.queue, (unsigned long long)n_idle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + n_idle >= N) drained = true;
+            if (L.phase == PH_IDLE) {
+                const long long k = base + __popc(idle & ((1u << lane) - 1u));
+                if (k < N) L.start_path(k, sA.B, sA.R);
+            }
+        }
+        if (drained && __all_sync(0xffffffffu, L.phase == PH_IDLE)) break;
+        if (L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
+    }
+}
+
+// single-path operator-API hooks (one thread: valid for levelised and for sequential programs)
 __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, const cx* xlo, cx t, const double* tw, cx* u, cx* U) {
     __shared__ KArgs sA;
     sA = A;
-    Lane L;
+    Lane<1, false> L;
+    L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = 0; L.kind = sA.H.kind;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, 1, 0);
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold);
     L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0;
     const int n = sA.H.n;
     if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
     else for (int i = 0; i < n; ++i) L.M.x[i] = x[i];
+    if (what == 1) for (int i = 0; i < n; ++i) L.M.xhat[i] = xlo[i];
     if (what == 0) L.eval_f64(L.M.u, nullptr, L.M.x, t);
-    else if (what == 1) { for (int i = 0; i < n; ++i) L.M.xhat[i] = xlo[i]; L.eval_dd(L.M.u, L.M.x, &L.M.xhat, t); }
+    else if (what == 1) L.eval_dd(L.M.u, L.M.x, &L.M.xhat, t);
     else if (what == 2) L.eval_f64(L.M.u, &L.M.A, L.M.x, t);
     else {
-        if (K == 1) L.taylor<1>(L.M.u, L.M.tx, t);
-        else if (K == 2) L.taylor<2>(L.M.u, L.M.tx, t);
-        else if (K == 3) L.taylor<3>(L.M.u, L.M.tx, t);
-        else L.taylor<4>(L.M.u, L.M.tx, t);
+        if (K == 1) L.template taylor<1>(L.M.u, L.M.tx, t);
+        else if (K == 2) L.template taylor<2>(L.M.u, L.M.tx, t);
+        else if (K == 3) L.template taylor<3>(L.M.u, L.M.tx, t);
+        else L.template taylor<4>(L.M.u, L.M.tx, t);
     }
     for (int i = 0; i < n; ++i) u[i] = L.M.u[i];
     if (what == 2) for (int i = 0; i < n * n; ++i) U[i] = L.M.A[i];
@@ -263,45 +291,102 @@ __global__ void hc_dfma_kernel(double* out, int iters) {
 #endif  // !HC_HOST_SIM
 
 // ------------------------------------------------------------------ launch planning
-struct Plan { int grid, block, lanes; size_t smem; int stage; MemSizes sz; };
-
-int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
+struct Plan {
+    int engine;  // 0 = group per path (shared-memory state), 1 = thread per path (global state)
+    int grid, block, group, paths_per_block;
+    size_t smem, slab, cold, stage_bytes;
+    int stage;
+    MemSizes sz;  // thread-per-path: elements per lane
+    long long lanes;
+};
 
 size_t program_stage_bytes(const ProgramH& P) {
     auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    return r16((size_t)P.L * sizeof(PInstr)) + r16((size_t)P.dev.C * sizeof(cx)) + r16((size_t)P.dev.nu * sizeof(int2)) +
-           r16((size_t)P.dev.nU * sizeof(int2));
+    return r16((size_t)P.dev.n_ops * sizeof(MOp)) + r16((size_t)P.dev.n_levels * sizeof(int)) + r16((size_t)P.dev.C * sizeof(cx)) +
+           r16((size_t)P.dev.nu * sizeof(int2)) + r16((size_t)P.dev.nU * sizeof(int2));
+}
+
+const size_t kSmemMax = 227 * 1024 - 2048;  // dynamic shared memory per CTA (the kernels keep ~1 KB static)
+
+// Which engine tracks a system of n variables: one thread per path keeps every lane busy but its
+// state (O(n^2) per path) lives in L2/HBM; a lane group per path keeps the state in shared memory
+// but only pays off once the vectors are long enough to fill the group.
+int engine_for(int n) {
+    const char* e = getenv("HC_B200_ENGINE");
+    if (e) {
+        if (!strcmp(e, "tpp")) return 1;
+        if (!strcmp(e, "group")) return 0;
+        throw std::string("HC_B200_ENGINE must be tpp or group");
+    }
+    return n <= env_int("HC_B200_TPP_MAX_N", 16) ? 1 : 0;
 }
 
 Plan make_plan(const HomotopyH& H, long long N) {
     Plan p;
-    PathMem dummy;
-    p.sz = carve(dummy, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr, nullptr, 1, 0);
+    memset(&p, 0, sizeof(p));
+    PathMem<false> dummy;
+    SlabSizes ss = carve(dummy, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr);
+    p.slab = ss.hot; p.cold = ss.cold;
 #ifndef HC_HOST_SIM
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    p.block = env_int("HC_B200_BLOCK", 64);
-    int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 4);
-    long long want = (N + p.block - 1) / p.block;
-    // few paths: spread them over the SMs with one-warp CTAs
-    if (want < sms && p.block > 32) { p.block = 32; want = (N + 31) / 32; }
+    p.engine = engine_for(H.dev.n);
+    p.stage_bytes = program_stage_bytes(H.F->eval) + program_stage_bytes(H.F->jac);
+    if (H.dev.kind == H_STRAIGHT_LINE) p.stage_bytes += program_stage_bytes(H.G->eval) + program_stage_bytes(H.G->jac);
+    p.stage = (p.stage_bytes <= (size_t)env_int("HC_B200_STAGE_MAX", 64 * 1024)) && env_int("HC_B200_STAGE", 1);
+    if (!p.stage) p.stage_bytes = 0;
+    if (p.engine == 1) {
+        PathMem<true> d2;
+        p.sz = carve(d2, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr, nullptr, 1, 0);
+        p.group = 1;
+        p.block = env_int("HC_B200_BLOCK", 64);
+        if (p.block % 32 || p.block < 32 || p.block > 128) throw std::string("HC_B200_BLOCK must be 32, 64, 96 or 128 for the thread-per-path engine");
+        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 512 / p.block);
+        // lanes: at most a fraction of the paths, so that finished lanes have work to refill with
+        long long lanes_cap = (long long)sms * per_sm * p.block;
+        long long want_lanes = (N + env_int("HC_B200_PATHS_PER_LANE", 1) - 1) / env_int("HC_B200_PATHS_PER_LANE", 1);
+        if (want_lanes > lanes_cap) want_lanes = lanes_cap;
+        long long want = (want_lanes + p.block - 1) / p.block;
+        if (want < sms && p.block > 32) { p.block = 32; want = (want_lanes + 31) / 32; }  // few paths: spread over the SMs
+        p.grid = (int)(want < 1 ? 1 : want);
+        p.paths_per_block = p.block;
+        p.smem = p.stage_bytes;
+        p.lanes = (long long)p.grid * p.block;
+        return p;
+    }
+    const int G = group_size_for(H.dev.n);
+    p.group = G;
+    if (p.stage_bytes + p.slab > kSmemMax) {
+        p.stage = 0; p.stage_bytes = 0;
+        if (p.slab > kSmemMax) throw std::string("system too large: one path needs ") + std::to_string(p.slab) + " bytes of shared memory";
+    }
+    // block: up to 256 threads; shrink until the slabs of its paths fit next to the staged programs
+    int block = env_int("HC_B200_BLOCK", 256);
+    if (block % 32 || block < 32 || block > 256) throw std::string("HC_B200_BLOCK must be a multiple of 32 in [32, 256]");
+    long long small = (N * G + sms - 1) / sms;            // few paths: spread them over the SMs
+    while (block > 32 && block / 2 >= small) block /= 2;
+    if (block < G) block = G;
+    while (block > G && p.stage_bytes + (size_t)(block / G) * p.slab > kSmemMax) block -= 32;
+    p.block = block; p.paths_per_block = block / G;
+    p.smem = p.stage_bytes + (size_t)p.paths_per_block * p.slab;
+    int per_sm = (int)((228 * 1024) / (p.smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * block > 512) per_sm = 512 / block;       // register file: 128 registers per thread
+    per_sm = env_int("HC_B200_BLOCKS_PER_SM", per_sm);
+    long long want = (N + p.paths_per_block - 1) / p.paths_per_block;
     long long cap = (long long)sms * per_sm;
     p.grid = (int)(want < cap ? want : cap);
     if (p.grid < 1) p.grid = 1;
-    p.smem = program_stage_bytes(H.F->eval) + program_stage_bytes(H.F->jac);
-    if (H.dev.kind == H_STRAIGHT_LINE) p.smem += program_stage_bytes(H.G->eval) + program_stage_bytes(H.G->jac);
-    p.stage = (p.smem <= (size_t)env_int("HC_B200_STAGE_MAX", 96 * 1024)) && env_int("HC_B200_STAGE", 1);
-    if (!p.stage) p.smem = 0;
+    p.lanes = (long long)p.grid * p.paths_per_block;
 #else
     (void)N;
-    p.block = 1; p.grid = 1; p.smem = 0; p.stage = 0;
+    p.block = 1; p.grid = 1; p.smem = p.slab; p.stage = 0; p.stage_bytes = 0; p.group = 1; p.paths_per_block = 1; p.lanes = 1;
 #endif
-    p.lanes = p.grid * p.block;
     return p;
 }
 
-struct DeviceBatch {  // device-resident inputs, outputs and lane slabs of one batch
+struct DeviceBatch {  // device-resident inputs and outputs of one batch
     HomotopyH* H = nullptr;
     int mode = 0; long long N = 0; int n = 0;
     KArgs A;
@@ -355,27 +440,41 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     R.counters = D.alloc<long long>((size_t)8 * N);
     D.plan = make_plan(*H, N);
     const Plan& pl = D.plan;
-    D.A.cslab = D.alloc<cx>(pl.sz.ncx * pl.lanes);
-    D.A.rslab = D.alloc<double>(pl.sz.nre * pl.lanes);
-    D.A.islab = D.alloc<int>(pl.sz.nint * pl.lanes);
     D.A.queue = D.alloc<unsigned long long>(1);
     D.A.stage = pl.stage;
-    D.A.static_sched = env_int("HC_B200_STATIC_SCHED", 0);
+    D.A.slab_bytes = (int)pl.slab;
+    D.A.cold_bytes = (int)pl.cold;
+    if (pl.engine == 1) {
+        D.A.cslab = D.alloc<cx>(pl.sz.ncx * (size_t)pl.lanes);
+        D.A.rslab = D.alloc<double>(pl.sz.nre * (size_t)pl.lanes);
+        D.A.islab = D.alloc<int>(pl.sz.nint * (size_t)pl.lanes);
+        D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
+    } else D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
+    D.A.stage_bytes = (int)pl.stage_bytes;
 }
+
+#ifndef HC_HOST_SIM
+template <int G>
+void launch_track(const DeviceBatch& D) {
+    static bool attr_set = false;
+    if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
+    hc_track_kernel<G><<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
+}
+#endif
 
 // runs the batch once; returns kernel milliseconds
 double run_batch(DeviceBatch& D) {
     dev_zero(D.A.queue, sizeof(unsigned long long));
 #ifndef HC_HOST_SIM
-    StageLens SL;
-    SL.LFe = D.H->F->eval.L; SL.LFj = D.H->F->jac.L;
-    SL.LGe = D.H->G ? D.H->G->eval.L : 0; SL.LGj = D.H->G ? D.H->G->jac.L : 0;
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, 0));
-    hc_track_kernel<<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A, SL);
+    if (D.plan.engine == 1) {
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
+        hc_track_tpp_kernel<<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
+    } else if (D.plan.group == 32) launch_track<32>(D);
+    else launch_track<8>(D);
     CK(cudaEventRecord(e1, 0));
     CK(cudaGetLastError());
     CK(cudaEventSynchronize(e1));
@@ -384,9 +483,12 @@ double run_batch(DeviceBatch& D) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return ms;
 #else
-    Lane L;
+    std::vector<unsigned char> slab(D.plan.slab + 16);
+    Lane<1, false> L;
+    L.g.init();
     L.H = &D.A.H; L.O = &D.A.O; L.n = D.A.H.n;
-    carve(L.M, D.A.H.n, D.A.H.P, D.A.H.tape_cx, D.A.cslab, D.A.rslab, D.A.islab, 1, 0);
+    unsigned char* base = (unsigned char*)(((uintptr_t)slab.data() + 15) & ~(uintptr_t)15);
+    carve(L.M, D.A.H.n, D.A.H.P, D.A.H.tape_cx, base, D.A.cold);
     for (long long k = 0; k < D.N; ++k) {
         L.phase = PH_IDLE;
         L.start_path(k, D.A.B, D.A.R);
@@ -445,8 +547,8 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
         double tD = now_ms();
         g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
         g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
-        g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.lanes;
-        g_timing.slab_bytes = (int64_t)D.plan.lanes * (int64_t)(D.plan.sz.ncx * 16 + D.plan.sz.nre * 8 + D.plan.sz.nint * 4);
+        g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.group;
+        g_timing.slab_bytes = D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.sz.ncx * 16 + D.plan.sz.nre * 8 + D.plan.sz.nint * 4) : (int64_t)D.plan.slab;
     } catch (const std::string& e) { return fail(e); }
     return 0;
 }
@@ -532,11 +634,10 @@ void* hc_homotopy_create(const hc_homotopy_desc* d) {
             D.p = cvec_dev(d->n_pq ? d->p : dummy, d->n_pq ? d->n_pq : 1, H->owned);
             if (d->kind != HC_TORIC) D.q = cvec_dev(d->n_pq ? d->q : dummy, d->n_pq ? d->n_pq : 1, H->owned);
         }
-        // tape region (cx units): Jacobian tape, DD eval tape (2x), order-3 Taylor eval tape (4x; hooks may ask order 4)
+        // tape region (cx units): Jacobian tape, DD eval tape (2x), order-3 Taylor eval tape (4x)
         int need = W;
-        if (2 * We > need) need = 2 * We;
-        if (5 * We > need) need = 5 * We;
-        D.tape_cx = need + 2;
+        if (4 * We > need) need = 4 * We;
+        D.tape_cx = need;
     } catch (const std::string& e) { delete H; fail(e); return nullptr; }
     return H;
 }
@@ -595,11 +696,14 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         hc_options o; hc_options_default(&o);
         KArgs A; memset(&A, 0, sizeof(A));
         A.H = H->dev; A.H.N = 1; A.O = to_dev_options(&o);
-        PathMem dummy;
-        MemSizes sz = carve(dummy, n, P, A.H.tape_cx, nullptr, nullptr, nullptr, 1, 0);
+        PathMem<false> dummy;
+        A.H.tape_cx = 5 * (H->F->eval.dev.W > (H->G ? H->G->eval.dev.W : 0) ? H->F->eval.dev.W : H->G->eval.dev.W);  // order-4 series
+        if (A.H.tape_cx < H->dev.tape_cx) A.H.tape_cx = H->dev.tape_cx;
+        const SlabSizes ss = carve(dummy, n, P, A.H.tape_cx, nullptr, nullptr);
+        const size_t slab = ss.hot;
         std::vector<void*> owned;
         auto A_ = [&](size_t b) { void* p = dev_alloc(b); owned.push_back(p); return p; };
-        A.cslab = (cx*)A_(sz.ncx * 16); A.rslab = (double*)A_(sz.nre * 8); A.islab = (int*)A_(sz.nint * 4);
+        A.cold = (unsigned char*)A_(ss.cold);
         const int nx = what == 3 ? K * n : n;
         cx* dx = (cx*)A_((size_t)nx * 16); h2d(dx, x, (size_t)nx * 16);
         cx* dlo = nullptr;
@@ -610,13 +714,18 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         cx* dU = (cx*)A_((size_t)n * n * 16);
         cx tt = mk(t[0], t[1]);
 #ifndef HC_HOST_SIM
-        hc_hook_kernel<<<1, 1>>>(A, what, K, dx, dlo, tt, dtw, du, dU);
+        if (slab > kSmemMax) throw std::string("system too large for one shared-memory slab");
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(hc_hook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
+        hc_hook_kernel<<<1, 1, slab>>>(A, what, K, dx, dlo, tt, dtw, du, dU);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
 #else
-        Lane L;
+        std::vector<unsigned char> mem(slab + 16);
+        Lane<1, false> L;
+        L.g.init();
         L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = 0; L.kind = A.H.kind;
-        carve(L.M, n, P, A.H.tape_cx, A.cslab, A.rslab, A.islab, 1, 0);
+        carve(L.M, n, P, A.H.tape_cx, (unsigned char*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15), A.cold);
         L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0;
         if (dtw) for (int i = 0; i < P; ++i) L.M.tw[i] = dtw[i];
         if (what == 3) for (int i = 0; i < K * n; ++i) L.M.tx[i] = dx[i]; else for (int i = 0; i < n; ++i) L.M.x[i] = dx[i];

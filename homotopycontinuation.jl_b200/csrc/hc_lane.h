@@ -1,7 +1,6 @@
-// The lane state machine: one flat loop iteration = (at most) one tracker step for every active
-// lane of the warp, so all lanes stay converged on the expensive primitive (predict + Newton +
-// predictor update) while the cheap phase logic around it diverges.  A lane whose path ends
-// writes its PathResult and refills itself from the device-side path queue.
+// The path state machine of a lane group: one flat loop iteration = (at most) one tracker step,
+// with the cheap phase logic of the endgame / polyhedral drivers around it.  A group whose path
+// ends writes its PathResult and refills itself from the device-side path queue.
 //
 // The phases flatten the reference's nested loops (file:line):
 //   PH_PLAIN    Tracker.track!                              src/tracker.jl:937-968
@@ -59,7 +58,19 @@ struct BatchIn {
     const double* cell_weights;// polyhedral: ncells x P (unscaled s_ij, 0 on the cell's vertices)
 };
 
-struct Lane : Path {
+template <int G, bool S>
+struct Lane : Path<G, S> {
+    using B = Path<G, S>;
+    using CV = typename B::CV; using RV = typename B::RV;
+    using B::g; using B::H; using B::O; using B::M; using B::n; using B::pidx; using B::kind;
+    using B::code; using B::accuracy; using B::omega; using B::mu; using B::tau; using B::winding;
+    using B::extended_prec; using B::used_extended_prec; using B::refined_extended_prec; using B::keep_extended_prec;
+    using B::accepted_steps; using B::rejected_steps; using B::factorized; using B::scaled;
+    using B::min_step_size; using B::min_rel_step_size; using B::st_target;
+    using B::n_fact; using B::n_ldiv; using B::n_evaljac; using B::n_eval; using B::n_evaldd; using B::n_tay1; using B::n_tay2; using B::n_tay3;
+    using B::st_t; using B::tracker_init; using B::jac_cond; using B::cond_at; using B::skeel; using B::a_inf_norm;
+    using B::refine_current_solution; using B::eval_f64; using B::vcopy;
+
     int phase, mode;
     // ---- endgame state (src/endgame_tracker.jl:177-215)
     int eg_code; bool singular_endgame; int eg_winding;  // 0 = nothing
@@ -71,17 +82,12 @@ struct Lane : Path {
     int singular_steps; double sing_t;
     double logt2, logt1;
     // ---- polyhedral
-    int toric_acc, toric_rej; double poly_mu, poly_omega, poly_maxw, saved_min_step;
+    int toric_acc, toric_rej; double poly_maxw, saved_min_step;
     // ---- flop accounting totals of finished stages
     int c_fact, c_ldiv;
 
-    HC_HD RV val_x() { return M.val; }
-    HC_HD RV val_tx() { return M.val.at(n); }
-    HC_HD RV dval_x() { return M.val.at(2 * n); }
-    HC_HD RV dval_tx() { return M.val.at(3 * n); }
-
     // ================================================================ valuation
-    HC_HD void val_init() { for (int i = 0; i < 12 * n; ++i) M.val[i] = 0.0; logt2 = logt1 = HC_NAN; }
+    HC_HD void val_init() { HC_PAR(i, 12 * n) M.val[i] = 0.0; g.sync(); logt2 = logt1 = HC_NAN; }
     HC_HD static double fdiff(double v, double s, double v2, double s2, double v1, double s1) {
         double D1 = s - s1, D2 = s - s2, D12 = s1 - s2;
         return (D2 * v1) / (D12 * D1) - ((D12 + D2) * v2) / (D12 * D2) - (D12 * v) / (D1 * D2);
@@ -97,7 +103,7 @@ struct Lane : Path {
         const double logt = log(t);
         const bool diff = winding > 1 && logt2 == logt2;
         RV V = M.val;  // [val_x, val_tx, dval_x, dval_tx, vx2, vx1, vd2, vd1, lx2, lx1, ld2, ld1] x n
-        for (int i = 0; i < nn; ++i) {
+        HC_PAR(i, nn) {
             cx x = M.tx[i], xd = M.tx[nn + i], x2 = M.tx[2 * nn + i], x3 = M.tx[3 * nn + i];
             double logx = log(cabs(x)), logxd = log(cabs(xd));
             if (diff) {
@@ -119,6 +125,7 @@ struct Lane : Path {
             double o = V[8 * nn + i]; V[8 * nn + i] = logx; V[9 * nn + i] = o;
             o = V[10 * nn + i]; V[10 * nn + i] = logxd; V[11 * nn + i] = o;
         }
+        g.sync();
         logt1 = logt2; logt2 = logt;
     }
     HC_HD double eps_inf(int i) {
@@ -128,21 +135,24 @@ struct Lane : Path {
     HC_HD bool val_is_finite() {  // valuation.jl:175-205
         const double ftol = O->val_finite_tol, delta = 1.0 / O->max_winding_number;
         const bool zero_is_finite = !O->zero_is_at_infinity;
-        for (int i = 0; i < n; ++i) {
+        bool ok = true;
+        HC_PAR(i, n) {
             double vx = M.val[i];
             if (fabs(vx) < ftol) {
-                if (!(fabs(M.val[2 * n + i]) < ftol) || M.val[n + i] < 0.5 * delta) return false;
+                if (!(fabs(M.val[2 * n + i]) < ftol) || M.val[n + i] < 0.5 * delta) ok = false;
             } else if (zero_is_finite && vx > (delta - ftol)) {
-                if (!(eps_inf(i) < ftol)) return false;
-            } else return false;
+                if (!(eps_inf(i) < ftol)) ok = false;
+            } else ok = false;
         }
-        return true;
+        return g.rall(ok);
     }
     HC_HD void estimate_winding(int& m, double& min_err) {  // valuation.jl:207-228
         m = 1; min_err = HC_INF;
         for (int k = 1; k <= O->max_winding_number; ++k) {
             double err = 0.0;
-            for (int i = 0; i < n; ++i) { double mv = k * M.val[n + i]; double e = fabs(rint(mv) - mv); err = e > err ? e : err; }
+            HC_PAR(i, n) { double mv = k * M.val[n + i]; double e = fabs(rint(mv) - mv); err = e > err ? e : err; }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) { double w = g.xshfl(err, o); err = w > err ? w : err; }  // NaN never wins, as in the fold
             if (err < min_err) { m = k; min_err = err; }
         }
     }
@@ -150,7 +160,8 @@ struct Lane : Path {
     // ================================================================ endgame
     HC_HD double eg_jac_cond() { return jac_cond(&M.egrs, &M.egcs); }
     HC_HD void eg_scaling_update() {  // col_scaling .= weights(norm); row_scaling!(...)
-        for (int i = 0; i < n; ++i) M.egcs[i] = M.w[i];
+        HC_PAR(i, n) M.egcs[i] = M.w[i];
+        g.sync();
         skeel(M.egrs, M.egcs, O->scaling_threshold);
     }
     // init!(endgame_tracker, x, t1; omega, mu, extended_precision)  endgame_tracker.jl:260-294
@@ -160,17 +171,16 @@ struct Lane : Path {
         eg_code = convert_code(code);
         singular_endgame = false; jtz_prev = jtz_cur = false;
         val_init(); eg_winding = 0;
-        for (int i = 0; i < n; ++i) M.sol[i] = mk(HC_NAN, HC_NAN);
         eg_accuracy = HC_NAN; eg_cond = HC_NAN; eg_singular = false; steps_eg = 0; ext_steps_eg_start = 0x3fffffff;
-        for (int i = 0; i < n; ++i) { M.egrs[i] = 1.0; M.egcs[i] = 1.0; M.ais[i] = HC_NAN; }
+        HC_PAR(i, n) { M.sol[i] = mk(HC_NAN, HC_NAN); M.egrs[i] = 1.0; M.egcs[i] = 1.0; M.ais[i] = HC_NAN; M.lastp[i] = M.x[i]; }
+        g.sync();
         singular_steps = 0; sidx0 = 0; sidx1 = 1; sidx2 = 2;
         last_t = HC_NAN;
-        for (int i = 0; i < n; ++i) M.lastp[i] = M.x[i];
     }
     HC_HDN void tracking_stopped() {  // :695-721
         eg_accuracy = accuracy;
         if (eg_code == EG_success && eg_accuracy > 1e-14) refine_current_solution(1e-14, O->refine_steps);
-        for (int i = 0; i < n; ++i) M.sol[i] = M.x[i];
+        vcopy(M.sol, M.x, n);
         eg_winding = 0;
         if (eg_code == EG_success) {
             eg_scaling_update();
@@ -195,7 +205,7 @@ struct Lane : Path {
         const bool zero_is_finite = !O->zero_is_at_infinity;
         double kappa = HC_NAN;
         const double t = st_t().re;
-        for (int i = 0; i < n; ++i) {
+        HC_PAR(i, n) {
             // at_infinity_tol!  valuation.jl:143-173
             double vx = M.val[i], e = eps_inf(i), tol;
             if (e != e) tol = HC_INF;
@@ -204,6 +214,8 @@ struct Lane : Path {
             else tol = HC_INF;
             M.ait[i] = tol;
         }
+        g.sync();
+        // the coordinate loop carries state (kappa, first-flag scaling): every lane walks it with the same values
         for (int i = 0; i < n; ++i) {
             if (M.ait[i] < O->val_at_infinity_tol) {
                 if (M.ais[i] != M.ais[i]) {
@@ -211,7 +223,10 @@ struct Lane : Path {
                     for (int k = 0; k < n; ++k) allnan = allnan && (M.ais[k] != M.ais[k]);
                     if (allnan) eg_scaling_update();
                     kappa = eg_jac_cond();
-                    M.aic[i] = kappa; M.aia[i] = cabs(M.x[i]); M.ais[i] = t;
+                    double ax = cabs(M.x[i]);
+                    g.sync();
+                    if (g.lane == 0) { M.aic[i] = kappa; M.aia[i] = ax; M.ais[i] = t; }
+                    g.sync();
                 } else {
                     if (kappa != kappa) kappa = eg_jac_cond();
                     double v = M.val[i];
@@ -224,7 +239,11 @@ struct Lane : Path {
                         return true;
                     }
                 }
-            } else if (M.ais[i] == M.ais[i]) M.ais[i] = HC_NAN;
+            } else if (M.ais[i] == M.ais[i]) {
+                g.sync();
+                if (g.lane == 0) M.ais[i] = HC_NAN;
+                g.sync();
+            }
         }
         return false;
     }
@@ -244,19 +263,20 @@ struct Lane : Path {
         }
         int sid = slot == 0 ? sidx0 : (slot == 1 ? sidx1 : sidx2);
         CV ty = M.samp.at(sid * 2 * nn);
-        for (int i = 0; i < nn; ++i) { ty[i] = M.tx[i]; ty[nn + i] = mu_ * M.tx[nn + i]; }
+        HC_PAR(i, nn) { ty[i] = M.tx[i]; ty[nn + i] = mu_ * M.tx[nn + i]; }
+        g.sync();
         if (slot == 0) { stime[0] = s; scond[0] = kappa; } else if (slot == 1) { stime[1] = s; scond[1] = kappa; } else { stime[2] = s; scond[2] = kappa; }
     }
     HC_HDN double predict_endpoint() {  // :664-693
         const int nn = n;
         if (singular_steps < 2) return HC_INF;
         CV S0 = M.samp.at(sidx0 * 2 * nn), S1 = M.samp.at(sidx1 * 2 * nn), S2 = M.samp.at(sidx2 * 2 * nn);
-        if (singular_steps == 2) cubic_hermite(M.pred, S0, S0.at(nn), mk(stime[0]), S1, S1.at(nn), mk(stime[1]), mk(0.0));
-        for (int i = 0; i < nn; ++i) M.ppred[i] = M.pred[i];
-        cubic_hermite(M.pred, S1, S1.at(nn), mk(stime[1]), S2, S2.at(nn), mk(stime[2]), mk(0.0));
+        if (singular_steps == 2) B::cubic_hermite(M.pred, S0, S0.at(nn), mk(stime[0]), S1, S1.at(nn), mk(stime[1]), mk(0.0));
+        vcopy(M.ppred, M.pred, nn);
+        B::cubic_hermite(M.pred, S1, S1.at(nn), mk(stime[1]), S2, S2.at(nn), mk(stime[2]), mk(0.0));
         double p = stime[2] / stime[1], p2 = p * p;
-        double err = inf_dist(M.pred, M.ppred, nn) / fabs(p2 * p2 - 1);
-        double ns = inf_norm(M.pred, nn);
+        double err = B::inf_dist(M.pred, M.ppred) / fabs(p2 * p2 - 1);
+        double ns = B::inf_norm(M.pred);
         if (ns > 1e-8) err /= ns;
         return err;
     }
@@ -269,19 +289,21 @@ struct Lane : Path {
         add_sample(t);
         singular_steps = 0;
         winding = eg_winding;
-        M.aic[0] = scond[0];
+        g.sync();
+        if (g.lane == 0) M.aic[0] = scond[0];
+        g.sync();
         keep_extended_prec = true;
     }
     HC_HD void switch_to_regular() {  // :525-530
         singular_endgame = false;
         winding = 1;
-        tracker_init_continue(mk(0.0));
+        B::tracker_init_continue(mk(0.0));
         phase = PH_EG;
     }
     // First half of step!(::EndgameTracker): returns false when the path ended without a tracker step.
     HC_HDN bool eg_pre() {  // :329-358
         if (steps_eg >= O->max_endgame_steps) { eg_code = EG_terminated_max_steps; return false; }
-        if (ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) {
+        if (B::ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) {
             bool nonan = true;
             for (int i = 0; i < n; ++i) nonan = nonan && !cisnan(M.sol[i]);
             if (nonan && eg_winding != 0 && eg_accuracy < O->singular_min_accuracy) {
@@ -290,15 +312,15 @@ struct Lane : Path {
             } else eg_code = EG_terminated_max_extended_steps;
             return false;
         }
-        for (int i = 0; i < n; ++i) M.lastp[i] = M.x[i];
+        vcopy(M.lastp, M.x, n);
         last_t = st_t().re;
         if (singular_endgame) {  // begin singular_endgame_step!  :533-540
             sing_t = st_t().re;
-            tracker_init_continue(mk(0.25 * sing_t));
+            B::tracker_init_continue(mk(0.25 * sing_t));
             phase = PH_SING;
             return true;
         }
-        is_jump_to_zero = ciszero(st_tp());
+        is_jump_to_zero = ciszero(B::st_tp());
         return true;
     }
     // Second half of step!(::EndgameTracker) after a regular tracker step  :362-398
@@ -308,7 +330,7 @@ struct Lane : Path {
         jtz_prev = jtz_cur; jtz_cur = is_jump_to_zero;
         double t = st_t().re;
         if (!(t <= O->endgame_start)) return;
-        if (steps_eg == 0) ext_steps_eg_start = ext_steps();
+        if (steps_eg == 0) ext_steps_eg_start = B::ext_steps();
         steps_eg += 1;
         if (!step_success) return;
         val_update(t);
@@ -319,7 +341,7 @@ struct Lane : Path {
     HC_HDN void sing_post() {
         bool max_steps = false;
         if ((steps_eg += 1) >= O->max_endgame_steps) { eg_code = EG_terminated_max_steps; max_steps = true; }
-        else if (ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) { eg_code = EG_terminated_max_extended_steps; max_steps = true; }
+        else if (B::ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) { eg_code = EG_terminated_max_extended_steps; max_steps = true; }
         if (!max_steps && code == TC_tracking) return;  // inner loop continues
         phase = PH_EG;
         singular_steps += 1;
@@ -335,13 +357,14 @@ struct Lane : Path {
             double acc = predict_endpoint();
             if (singular_steps == 2 || (acc < eg_accuracy && eg_accuracy > 1e-12)) {
                 eg_accuracy = acc;
-                for (int i = 0; i < n; ++i) M.sol[i] = M.pred[i];
+                vcopy(M.sol, M.pred, n);
                 return;
             }
         }
         const int mw = eg_winding;
         const double kappa = scond[2], zero_cond = 1.0 / (mw + 1);
-        for (int i = 0; i < n; ++i) M.sol[i] = (M.val[i] < zero_cond ? 1.0 : 0.0) * M.pred[i];
+        HC_PAR(i, n) M.sol[i] = (M.val[i] < zero_cond ? 1.0 : 0.0) * M.pred[i];
+        g.sync();
         double kappa0 = cond_at(M.sol, mk(0.0), &M.egrs, &M.egcs);
         double J0 = a_inf_norm(&M.egrs, nullptr);
         if (eg_accuracy < O->singular_min_accuracy &&
@@ -358,31 +381,33 @@ struct Lane : Path {
     HC_HD void set_weights(const double* raw, bool use_min, double target, double& smin, double& smax) {
         const int P = H->P;
         smax = 0.0; smin = HC_INF;
-        for (int l = 0; l < P; ++l) { double r = ld_real(raw + l); if (r != 0.0) { smax = jmax(smax, r); smin = jmin(smin, r); } }
+        for (int l = 0; l < P; ++l) { double r = raw[l]; if (r != 0.0) { smax = jmax(smax, r); smin = jmin(smin, r); } }
         double lam = use_min ? smin / target : smax / target;
-        for (int l = 0; l < P; ++l) M.tw[l] = ld_real(raw + l) / lam;
+        g.sync();
+        HC_PAR(l, P) M.tw[l] = raw[l] / lam;
+        g.sync();
         if (use_min) { smax = smax / lam; smin = target; } else { smin = smin / lam; smax = target; }
     }
 
     // ================================================================ results
-    HC_HDN void write_result(const DevResults& R, int rc, bool success_at_zero, bool valuation_ok) {
+    HC_HDN void write_result(const DevResults& R, int rc, bool success_at_zero) {
         const long long k = pidx;
         const int nn = n;
-        double tt;
         CV sol = success_at_zero ? M.sol : M.x;
-        if (success_at_zero) tt = 0.0; else tt = st_t().re;
-        R.return_code[k] = rc;
-        for (int i = 0; i < nn; ++i) { R.solution[k * nn + i] = sol[i]; R.last_point[k * nn + i] = M.lastp[i]; }
-        R.t[k] = tt;
-        R.last_t[k] = last_t;
-        R.omega[k] = omega; R.mu[k] = mu;
-        R.extended_precision[k] = extended_prec; R.extended_precision_used[k] = used_extended_prec;
-        R.accepted_steps[k] = accepted_steps; R.rejected_steps[k] = rejected_steps;
-        if (R.counters) {
-            long long* c = R.counters + 8 * k;
-            c[0] = c_fact + n_fact; c[1] = c_ldiv + n_ldiv; c[2] = n_evaljac; c[3] = n_eval; c[4] = n_evaldd; c[5] = n_tay1; c[6] = n_tay2; c[7] = n_tay3;
+        const double tt = success_at_zero ? 0.0 : st_t().re;
+        HC_PAR(i, nn) { R.solution[k * nn + i] = sol[i]; R.last_point[k * nn + i] = M.lastp[i]; }
+        if (g.lane == 0) {
+            R.return_code[k] = rc;
+            R.t[k] = tt;
+            R.last_t[k] = last_t;
+            R.omega[k] = omega; R.mu[k] = mu;
+            R.extended_precision[k] = extended_prec; R.extended_precision_used[k] = used_extended_prec;
+            R.accepted_steps[k] = accepted_steps; R.rejected_steps[k] = rejected_steps;
+            if (R.counters) {
+                long long* c = R.counters + 8 * k;
+                c[0] = c_fact + n_fact; c[1] = c_ldiv + n_ldiv; c[2] = n_evaljac; c[3] = n_eval; c[4] = n_evaldd; c[5] = n_tay1; c[6] = n_tay2; c[7] = n_tay3;
+            }
         }
-        (void)valuation_ok;
     }
     HC_HDN void finish_eg(const DevResults& R) {  // PathResult(::EndgameTracker)  :847-888
         const long long k = pidx;
@@ -390,71 +415,80 @@ struct Lane : Path {
         const bool ok = eg_code == EG_success;
         const double tt = ok ? 0.0 : st_t().re;
         eval_f64(M.r, nullptr, ok ? M.sol : M.x, mk(tt));
-        R.residual[k] = inf_norm(M.r, nn);
-        write_result(R, eg_code, ok, true);
-        R.singular[k] = eg_singular; R.accuracy[k] = eg_accuracy; R.condition_jacobian[k] = eg_cond;
-        R.winding_number[k] = eg_winding; R.steps_eg[k] = steps_eg;
-        R.has_valuation[k] = !(tt > O->endgame_start);
-        for (int i = 0; i < nn; ++i) R.valuation[k * nn + i] = M.val[i];
-        if (mode == MODE_POLYHEDRAL) { R.accepted_steps[k] += toric_acc; R.rejected_steps[k] += toric_rej; }
+        const double res = B::inf_norm(M.r);
+        write_result(R, eg_code, ok);
+        HC_PAR(i, nn) R.valuation[k * nn + i] = M.val[i];
+        if (g.lane == 0) {
+            R.residual[k] = res;
+            R.singular[k] = eg_singular; R.accuracy[k] = eg_accuracy; R.condition_jacobian[k] = eg_cond;
+            R.winding_number[k] = eg_winding; R.steps_eg[k] = steps_eg;
+            R.has_valuation[k] = !(tt > O->endgame_start);
+            if (mode == MODE_POLYHEDRAL) { R.accepted_steps[k] += toric_acc; R.rejected_steps[k] += toric_rej; }
+        }
         phase = PH_IDLE;
     }
     HC_HDN void finish_plain(const DevResults& R) {  // TrackerResult  tracker.jl:998-1012
         const long long k = pidx;
         const int nn = n;
-        for (int i = 0; i < nn; ++i) M.lastp[i] = M.x[i];
+        vcopy(M.lastp, M.x, nn);
         last_t = st_t().im;
-        write_result(R, code, false, false);
-        R.accuracy[k] = accuracy; R.residual[k] = HC_NAN; R.singular[k] = 0; R.condition_jacobian[k] = tau;
-        R.winding_number[k] = 0; R.steps_eg[k] = 0; R.has_valuation[k] = 0;
-        R.extended_precision[k] = extended_prec || refined_extended_prec;
-        R.extended_precision_used[k] = used_extended_prec || refined_extended_prec;
-        for (int i = 0; i < nn; ++i) R.valuation[k * nn + i] = HC_NAN;
+        write_result(R, code, false);
+        HC_PAR(i, nn) R.valuation[k * nn + i] = HC_NAN;
+        if (g.lane == 0) {
+            R.accuracy[k] = accuracy; R.residual[k] = HC_NAN; R.singular[k] = 0; R.condition_jacobian[k] = tau;
+            R.winding_number[k] = 0; R.steps_eg[k] = 0; R.has_valuation[k] = 0;
+            R.extended_precision[k] = extended_prec || refined_extended_prec;
+            R.extended_precision_used[k] = used_extended_prec || refined_extended_prec;
+        }
         phase = PH_IDLE;
     }
     HC_HDN void finish_poly_failed(const DevResults& R) {  // polyhedral.jl:491-513
         const long long k = pidx;
         const int nn = n;
-        for (int i = 0; i < nn; ++i) M.lastp[i] = M.x[i];
+        vcopy(M.lastp, M.x, nn);
         last_t = st_t().re;
-        write_result(R, EG_polyhedral_failed, false, false);
-        R.accuracy[k] = accuracy; R.residual[k] = HC_NAN; R.singular[k] = 0; R.condition_jacobian[k] = HC_NAN;
-        R.winding_number[k] = 0; R.steps_eg[k] = 0; R.has_valuation[k] = 0;
-        for (int i = 0; i < nn; ++i) R.valuation[k * nn + i] = 0.0;
+        write_result(R, EG_polyhedral_failed, false);
+        HC_PAR(i, nn) R.valuation[k * nn + i] = 0.0;
+        if (g.lane == 0) {
+            R.accuracy[k] = accuracy; R.residual[k] = HC_NAN; R.singular[k] = 0; R.condition_jacobian[k] = HC_NAN;
+            R.winding_number[k] = 0; R.steps_eg[k] = 0; R.has_valuation[k] = 0;
+        }
         phase = PH_IDLE;
     }
 
     // ================================================================ driver
-    HC_HDN void start_path(long long k, const BatchIn& B, const DevResults& R) {
-        pidx = k; mode = B.mode;
+    HC_HDN void start_path(long long k, const BatchIn& Bt, const DevResults& R) {
+        pidx = k; mode = Bt.mode;
         const int nn = n;
-        for (int i = 0; i < nn; ++i) M.x[i] = B.starts[k * nn + i];
+        g.sync();
+        HC_PAR(i, nn) M.x[i] = Bt.starts[k * nn + i];
+        g.sync();
         refined_extended_prec = false; factorized = scaled = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
         n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_tay1 = n_tay2 = n_tay3 = 0; c_fact = c_ldiv = 0;
         toric_acc = toric_rej = 0;
         double om = HC_NAN, mu_ = HC_NAN;
-        if (B.omega_mu) { om = B.omega_mu[2 * k]; mu_ = B.omega_mu[2 * k + 1]; }
+        if (Bt.omega_mu) { om = Bt.omega_mu[2 * k]; mu_ = Bt.omega_mu[2 * k + 1]; }
         if (mode == MODE_TRACKER) {
             kind = H->kind;
-            tracker_init(B.t1, B.t0, om, mu_, HC_INF, HC_INF, false, false);
+            tracker_init(Bt.t1, Bt.t0, om, mu_, HC_INF, HC_INF, false, false);
             phase = PH_PLAIN;
             if (code != TC_tracking) finish_plain(R);
         } else if (mode == MODE_ENDGAME) {
             kind = H->kind;
-            eg_init(B.t1.re, om, mu_, false);
+            eg_init(Bt.t1.re, om, mu_, false);
             phase = PH_EG;
             if (eg_code != EG_tracking) finish_eg(R);
         } else {  // polyhedral.jl:414-465
             kind = H_TORIC;
             double smin, smax;
-            const double* raw = B.cell_weights + (size_t)B.cell_index[k] * H->P;
+            const double* raw = Bt.cell_weights + (size_t)Bt.cell_index[k] * H->P;
             set_weights(raw, true, 1.0, smin, smax);
             poly_maxw = smax;
             double tend = smax < 10 ? 1.0 : clampd(pow(0.1, 10 / smax), 0.9, 1 - 1e-6);
             tracker_init(mk(0.0), mk(tend), 20.0, 1e-12, HC_INF, 0.2, false, false);
             phase = PH_TORIC_A;
-            if (code != TC_tracking) toric_transition(B, R);
+            if (code != TC_tracking) toric_transition(Bt, R);
         }
     }
     HC_HDN void toric_done(const DevResults& R) {  // polyhedral.jl:491-529
@@ -467,10 +501,10 @@ struct Lane : Path {
         phase = PH_EG;
         if (eg_code != EG_tracking) finish_eg(R);
     }
-    HC_HDN void toric_transition(const BatchIn& B, const DevResults& R) {
+    HC_HDN void toric_transition(const BatchIn& Bt, const DevResults& R) {
         if (phase == PH_TORIC_A && poly_maxw >= 10 && code == TC_success) {  // :466-489
             double smin, smax;
-            const double* raw = B.cell_weights + (size_t)B.cell_index[pidx] * H->P;
+            const double* raw = Bt.cell_weights + (size_t)Bt.cell_index[pidx] * H->P;
             double t0 = st_target.re;
             set_weights(raw, false, 10.0, smin, smax);
             double t_restart = pow(t0, 1 / smin);
@@ -484,15 +518,15 @@ struct Lane : Path {
         if (phase == PH_TORIC_B) min_step_size = saved_min_step;
         toric_done(R);
     }
-    // One flat iteration of an active lane.
-    HC_HD void iterate(const BatchIn& B, const DevResults& R) {
+    // One flat iteration of an active group.
+    HC_HD void iterate(const BatchIn& Bt, const DevResults& R) {
         bool do_step = true;
         if (phase == PH_EG) do_step = eg_pre();
         bool ok = false;
-        if (do_step) ok = tracker_step();
+        if (do_step) ok = B::tracker_step();
         switch (phase) {
             case PH_PLAIN: if (code != TC_tracking) finish_plain(R); break;
-            case PH_TORIC_A: case PH_TORIC_B: if (code != TC_tracking) toric_transition(B, R); break;
+            case PH_TORIC_A: case PH_TORIC_B: if (code != TC_tracking) toric_transition(Bt, R); break;
             case PH_SING: sing_post(); if (eg_code != EG_tracking) finish_eg(R); break;
             case PH_EG: if (do_step) eg_post(ok); if (eg_code != EG_tracking) finish_eg(R); break;
             default: break;

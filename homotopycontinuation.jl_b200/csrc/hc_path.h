@@ -1,5 +1,7 @@
-// One solution path per thread: per-lane memory views, homotopy evaluation, small dense linear
-// algebra, norms, predictor, Newton corrector and the core tracker step.
+// One solution path per lane group (hc_coop.h): shared-memory views, homotopy evaluation, small
+// dense linear algebra, norms, predictor, Newton corrector and the core tracker step.  Scalars are
+// replicated in every lane of the group, vectors live in the path's shared-memory slab and are
+// processed lane-strided; every routine is entered and left with the slab group-synchronised.
 //
 // Replaces (reference file:line):
 //   src/homotopies/straight_line_homotopy.jl:81-154, parameter_homotopy.jl:66-101,
@@ -9,9 +11,11 @@
 //   src/predictor.jl:158-371;  src/newton_corrector.jl:55-286
 //   src/tracker.jl:509-619, 639-844, 851-926
 #pragma once
-#include "hc_program.h"
+#include "hc_tape.h"
 
 namespace hc {
+
+#define HC_PAR(i, N) for (int i = g.lane; i < (N); i += G)
 
 enum HKind : int { H_STRAIGHT_LINE = 0, H_PARAMETER = 1, H_COEFFICIENT = 2, H_TORIC = 3 };
 
@@ -30,7 +34,7 @@ struct DevOptions {  // same field order as hc_options (include/hc_b200.h)
 
 struct DevHomotopy {
     int kind, n, P;            // square systems: m == n; P = #parameters of F
-    DevProgram Fe, Fj, Ge, Gj; // eval / Jacobian tapes of F (and of G for straight-line)
+    DevProgram Fe, Fj, Ge, Gj; // eval / Jacobian programs of F (and of G for straight-line)
     cx gamma;
     const cx* G_params;        // straight-line: fixed parameters of G (scaling), length Ge.P
     const cx* F_params;        // straight-line: fixed parameters of F
@@ -39,73 +43,68 @@ struct DevHomotopy {
     const cx* path_p;          // optional per-path start parameters, [i * N + path]
     const cx* path_q;          // optional per-path target parameters, [i * N + path]
     long long N;
-    int tape_cx;               // per-lane tape region, in cx units
+    int tape_cx;               // per-path tape region, in cx units
 };
 
-// ---------------------------------------------------------------- per-lane memory
+// ---------------------------------------------------------------- per-path memory
+template <bool S>
 struct PathMem {
+    using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
     CV x, xhat, xbar, tx, ptx1, ty1, pty1, xtemp, u, dx, r, A, LU, wr, wdx, work;
     CV sol, lastp, pred, ppred, samp, tape;
-    DV xbd, rbd, tape_dd;
+    DV<S> rbd;
     RV w, rs, rwork, egrs, egcs, ais, ait, aia, aic, val, tw;
     IV ipiv;
 };
-struct MemSizes { size_t ncx, nre, nint; };
 
-// Carves the per-lane vectors out of three lane-interleaved slabs (element i of lane l at
-// base[i * stride + l]).  With null bases it only counts; the host sizes the allocation so.
-HC_HD MemSizes carve(PathMem& M, int n, int P, int tape_cx, cx* cb, double* rb, int* ib, int stride, int lane) {
-    size_t oc = 0, orr = 0, oi = 0;
-    auto C = [&](size_t k) { CV v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += k; return v; };
-    auto D = [&](size_t k) { DV v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += 2 * k; return v; };
-    auto R = [&](size_t k) { RV v; v.p = rb ? rb + orr * (size_t)stride + lane : nullptr; v.s = stride; orr += k; return v; };
+// Group-per-path layout.  Carves the path's vectors out of two 16-byte aligned slabs: the hot one
+// (everything a regular predictor-corrector step touches) lives in shared memory, the cold one
+// (endgame samples, valuation history, at-infinity bookkeeping, Hermite-mode predictor data, DD
+// accumulators) in a per-group scratch area in global memory.  With null bases it only counts.
+struct SlabSizes { size_t hot, cold; };
+HC_HD SlabSizes carve(PathMem<false>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold) {
+    size_t off = 0;
+    unsigned char* base = hot;
+    auto C = [&](size_t k) { SV<cx, false> v; v.p = base ? (cx*)(base + off) : nullptr; off += 16 * k; return v; };
+    auto R = [&](size_t k) { SV<double, false> v; v.p = base ? (double*)(base + off) : nullptr; off += 8 * k; return v; };
+    M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n);
+    M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
+    M.wr = C(n); M.wdx = C(n); M.work = C(n);
+    M.tape = C((size_t)tape_cx);
+    M.w = R(n); M.rs = R(n); M.rwork = R(n); M.tw = R(P > 0 ? P : 1);
+    M.ipiv.p = base ? (int*)(base + off) : nullptr; off += 4 * (size_t)n;
+    SlabSizes s;
+    s.hot = (off + 15) & ~(size_t)15;
+    off = 0; base = cold;
+    M.ptx1 = C(2 * n); M.ty1 = C(2 * n); M.pty1 = C(2 * n);
+    M.sol = C(n); M.lastp = C(n); M.pred = C(n); M.ppred = C(n); M.samp = C(6 * n);
+    M.rbd.v = C(2 * n);
+    M.egrs = R(n); M.egcs = R(n); M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n);
+    s.cold = (off + 15) & ~(size_t)15;
+    return s;
+}
+
+// Thread-per-path layout: three lane-interleaved slabs in global memory (element i of lane l at
+// base[i * stride + l]).  With null bases it only counts elements per lane.
+struct MemSizes { size_t ncx, nre, nint; };
+HC_HD MemSizes carve(PathMem<true>& M, int n, int P, int tape_cx, cx* cb, double* rb, int* ib, int stride, int lane) {
+    size_t oc = 0, orr = 0;
+    auto C = [&](size_t k) { SV<cx, true> v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += k; return v; };
+    auto R = [&](size_t k) { SV<double, true> v; v.p = rb ? rb + orr * (size_t)stride + lane : nullptr; v.s = stride; orr += k; return v; };
     M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n); M.ptx1 = C(2 * n); M.ty1 = C(2 * n); M.pty1 = C(2 * n);
     M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
     M.wr = C(n); M.wdx = C(n); M.work = C(n);
     M.sol = C(n); M.lastp = C(n); M.pred = C(n); M.ppred = C(n); M.samp = C(6 * n);
-    M.xbd = D(n); M.rbd = D(n);
-    {   // tape region: viewed as cx (F64 / Taylor) or as cdd (DD)
-        size_t tc = (size_t)((tape_cx + 1) & ~1);
-        M.tape.p = cb ? cb + oc * (size_t)stride + lane : nullptr; M.tape.s = stride;
-        M.tape_dd.p = M.tape.p; M.tape_dd.s = stride;
-        oc += tc;
-    }
+    M.rbd.v = C(2 * n);
+    M.tape = C((size_t)tape_cx);
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.egrs = R(n); M.egcs = R(n);
     M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n); M.tw = R(P > 0 ? P : 1);
-    M.ipiv.p = ib ? ib + oi * (size_t)stride + lane : nullptr; M.ipiv.s = stride; oi += n;
-    MemSizes s; s.ncx = oc; s.nre = orr; s.nint = oi;
+    M.ipiv.p = ib ? ib + lane : nullptr; M.ipiv.s = stride;
+    MemSizes s; s.ncx = oc; s.nre = orr; s.nint = (size_t)n;
     return s;
 }
 
-// ---------------------------------------------------------------- norms (src/norm.jl)
-HC_HD double inf_norm(CV x, int n) {
-    double d = abs2(x[0]);
-    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2(x[i]));
-    double r = sqrt(d);
-    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) r = jmax(r, hypot(x[i].re, x[i].im)); }
-    return r;
-}
-HC_HD double inf_dist(CV x, CV y, int n) {
-    double d = abs2(x[0] - y[0]);
-    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2(x[i] - y[i]));
-    double r = sqrt(d);
-    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) { cx z = x[i] - y[i]; r = jmax(r, hypot(z.re, z.im)); } }
-    return r;
-}
-HC_HD double wnorm(CV x, RV w, int n) {
-    double d = abs2(x[0] / w[0]);
-    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2(x[i] / w[i]));
-    double r = sqrt(d);
-    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) { cx z = x[i] / w[i]; r = jmax(r, hypot(z.re, z.im)); } }
-    return r;
-}
-HC_HD double wdist(CV x, CV y, RV w, int n) {
-    double d = abs2((x[0] - y[0]) / w[0]);
-    for (int i = 1; i < n; ++i) d = fmaxq(d, abs2((x[i] - y[i]) / w[i]));
-    double r = sqrt(d);
-    if (r == HC_INF) { r = 0; for (int i = 0; i < n; ++i) { cx z = (x[i] - y[i]) / w[i]; r = jmax(r, hypot(z.re, z.im)); } }
-    return r;
-}
+HC_HD double nmax(double d, double v) { return (d != d || v != v) ? HC_NAN : (v > d ? v : d); }
 
 // ---------------------------------------------------------------- the path
 enum TrackerCode : int {  // src/tracker.jl:166-176
@@ -127,13 +126,15 @@ HC_HD cx t_to_s_plane(cx t, int m) {  // predictor.jl:338-351
     double rr = nthroot(r, m);
     return mk(rr * cos(th / m), rr * sin(th / m));
 }
-HC_HD cx cpow_pos(cx z, int p) { return cpowi(z, p); }
 
+template <int G, bool S>
 struct Path {
+    using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
+    Grp<G> g;
     // ---- immutable context
     const DevHomotopy* H;
     const DevOptions* O;
-    PathMem M;
+    PathMem<S> M;
     int n;
     long long pidx;
     int kind;  // current homotopy kind (polyhedral paths switch TORIC -> COEFFICIENT)
@@ -150,15 +151,89 @@ struct Path {
     // ---- counters (src/linear_algebra.jl:809-826 + flop accounting of SURVEY.md 8(d))
     int n_fact, n_ldiv, n_evaljac, n_eval, n_evaldd, n_tay1, n_tay2, n_tay3;
 
-    // ================================================================ homotopy
-    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)i * H->N + pidx] : ld_const(H->p + i); }
-    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)i * H->N + pidx] : ld_const(H->q + i); }
+    // ================================================================ norms (src/norm.jl)
+    HC_HDN double inf_norm(CV x) {
+        double d = -1.0;
+        HC_PAR(i, n) d = nmax(d, abs2(x[i]));
+        double r = sqrt(g.rmax(d));
+        if (r == HC_INF) { d = 0; HC_PAR(i, n) d = nmax(d, hypot(x[i].re, x[i].im)); r = g.rmax(d); }
+        return r;
+    }
+    HC_HDN double inf_dist(CV x, CV y) {
+        double d = -1.0;
+        HC_PAR(i, n) d = nmax(d, abs2(x[i] - y[i]));
+        double r = sqrt(g.rmax(d));
+        if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = x[i] - y[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
+        return r;
+    }
+    HC_HDN double wnorm(CV x) {
+        double d = -1.0;
+        HC_PAR(i, n) d = nmax(d, abs2(x[i] / M.w[i]));
+        double r = sqrt(g.rmax(d));
+        if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = x[i] / M.w[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
+        return r;
+    }
+    HC_HDN double wdist(CV x, CV y) {
+        double d = -1.0;
+        HC_PAR(i, n) d = nmax(d, abs2((x[i] - y[i]) / M.w[i]));
+        double r = sqrt(g.rmax(d));
+        if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = (x[i] - y[i]) / M.w[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
+        return r;
+    }
+    // Elementwise helpers.  With one thread per path (G == 1) the vectors sit in global memory, so the
+    // loops are unrolled by four with all loads issued before the first store (memory-level parallelism).
+    HC_HDN void vcopy(CV dst, CV src, int len) {
+        if (G == 1) {
+            int i = 0;
+            for (; i + 3 < len; i += 4) { cx a0 = src[i], a1 = src[i + 1], a2 = src[i + 2], a3 = src[i + 3]; dst[i] = a0; dst[i + 1] = a1; dst[i + 2] = a2; dst[i + 3] = a3; }
+            for (; i < len; ++i) dst[i] = src[i];
+        } else { HC_PAR(i, len) dst[i] = src[i]; g.sync(); }
+    }
+    // y[i] -= a[i] * s for i in [lo, hi)
+    HC_HD void col_fnma(CV y, CV a, cx s, int lo, int hi) {
+        if (G == 1) {
+            int i = lo;
+            for (; i + 3 < hi; i += 4) {
+                cx a0 = a[i], a1 = a[i + 1], a2 = a[i + 2], a3 = a[i + 3], y0 = y[i], y1 = y[i + 1], y2 = y[i + 2], y3 = y[i + 3];
+                y[i] = cfnma(a0, s, y0); y[i + 1] = cfnma(a1, s, y1); y[i + 2] = cfnma(a2, s, y2); y[i + 3] = cfnma(a3, s, y3);
+            }
+            for (; i < hi; ++i) y[i] = cfnma(a[i], s, y[i]);
+        } else for (int i = lo + g.lane; i < hi; i += G) y[i] = cfnma(a[i], s, y[i]);
+    }
+    // outputs of a program run: MODE 0 dst = tape, 1 dst = s * tape, 2 dst += s * tape
+    template <int MODE>
+    HC_HDN void extract(CV dst, CV tape, const int2* asg, int cnt, cx s) {
+        if (G == 1) {
+            int k = 0;
+            for (; k + 3 < cnt; k += 4) {
+                int2 a0 = asg[k], a1 = asg[k + 1], a2 = asg[k + 2], a3 = asg[k + 3];
+                cx v0 = tape[a0.y], v1 = tape[a1.y], v2 = tape[a2.y], v3 = tape[a3.y];
+                if (MODE == 0) { dst[a0.x] = v0; dst[a1.x] = v1; dst[a2.x] = v2; dst[a3.x] = v3; }
+                else if (MODE == 1) { dst[a0.x] = s * v0; dst[a1.x] = s * v1; dst[a2.x] = s * v2; dst[a3.x] = s * v3; }
+                else {
+                    cx d0 = dst[a0.x], d1 = dst[a1.x], d2 = dst[a2.x], d3 = dst[a3.x];
+                    dst[a0.x] = cfma(s, v0, d0); dst[a1.x] = cfma(s, v1, d1); dst[a2.x] = cfma(s, v2, d2); dst[a3.x] = cfma(s, v3, d3);
+                }
+            }
+            for (; k < cnt; ++k) {
+                int2 a = asg[k];
+                if (MODE == 0) dst[a.x] = tape[a.y]; else if (MODE == 1) dst[a.x] = s * tape[a.y]; else dst[a.x] = cfma(s, tape[a.y], dst[a.x]);
+            }
+        } else HC_PAR(k, cnt) {
+            int2 a = asg[k];
+            if (MODE == 0) dst[a.x] = tape[a.y]; else if (MODE == 1) dst[a.x] = s * tape[a.y]; else dst[a.x] = cfma(s, tape[a.y], dst[a.x]);
+        }
+    }
 
-    // Taylor coefficients c[0..4] of parameter i at t (only the first `np` are meaningful)
+    // ================================================================ homotopy
+    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)i * H->N + pidx] : H->p[i]; }
+    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)i * H->N + pidx] : H->q[i]; }
+
+    // Taylor coefficients c[0..4] of parameter i at t
     HC_HD void param_series(int i, cx t, cx* c) const {
         c[1] = c[2] = c[3] = c[4] = mk(0.0);
         if (kind == H_TORIC) {  // toric_homotopy.jl:145-177, 220-264 (real t >= 0)
-            cx u = ld_const(H->p + i);
+            cx u = H->p[i];
             double w = M.tw[i], tr = t.re;
             if (tr == 0.0) {
                 c[0] = mk(0.0);
@@ -182,55 +257,62 @@ struct Path {
     // value of parameter i at t (toric t == 0: weights that are exactly 0 survive, toric_homotopy.jl:160-165)
     HC_HD cx param_value(int i, cx t) const {
         if (kind == H_TORIC) {
-            cx u = ld_const(H->p + i);
+            cx u = H->p[i];
             double w = M.tw[i];
             if (t.re == 0.0) return w == 0.0 ? u : mk(0.0);
             return u * exp(w * log(t.re));
         }
-        cx c[5]; param_series(i, t, c); return c[0];
+        cx p = param_p(i), q = param_q(i);
+        if (t.im == 0.0) return t.re * p + (1.0 - t.re) * q;
+        return t * p + (mk(1.0) - t) * q;
     }
 
-    template <class T, class TapeT>
-    HC_HD void load_inputs(const DevProgram& P, TapeT tape, CV x, const CV* xlo, cx t, const cx* fixed) {
-        for (int i = 0; i < P.P; ++i) {
-            cx v = fixed ? ld_const(fixed + i) : param_value(i, t);
-            store_in(tape, P.param_off + i - P.C, v, mk(0.0));
-        }
-        if (P.t_slot >= 0) store_in(tape, P.t_slot - P.C, t, mk(0.0));
-        for (int i = 0; i < P.n; ++i) store_in(tape, P.var_off + i - P.C, x[i], xlo ? (*xlo)[i] : mk(0.0));
+    HC_HD static void store_in(CV tape, int s, cx hi, cx, cx*) { tape[s] = hi; }
+    HC_HD static void store_in(CV tape, int s, cx hi, cx lo, cdd*) { tstore(tape, s, mkcdd(mkdd(hi.re, lo.re), mkdd(hi.im, lo.im))); }
+
+    template <class T>
+    HC_HDN void load_inputs(const DevProgram& P, CV x, const CV* xlo, cx t, const cx* fixed) {
+        T* tag = nullptr;
+        CV tape = M.tape;
+        HC_PAR(i, P.C) store_in(tape, i, P.consts[i], mk(0.0), tag);
+        HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? fixed[i] : param_value(i, t), mk(0.0), tag);
+        if (P.t_slot >= 0 && g.lane == 0) store_in(tape, P.t_slot, t, mk(0.0), tag);
+        HC_PAR(i, P.n) store_in(tape, P.var_off + i, x[i], xlo ? (*xlo)[i] : mk(0.0), tag);
+        g.sync();
     }
-    HC_HD static void store_in(CV tape, int s, cx hi, cx) { tape[s] = hi; }
-    HC_HD static void store_in(DV tape, int s, cx hi, cx lo) { tape.set(s, mkcdd(mkdd(hi.re, lo.re), mkdd(hi.im, lo.im))); }
 
     // u (and optionally the column-major Jacobian U) of H(x, t)
     HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
         const int nn = n;
         const bool jac = U != nullptr;
         if (jac) n_evaljac++; else n_eval++;
-        if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:96-124
+        CV tape = M.tape;
+        if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:96-124: u = (gamma t) G + (1 - t) F
             const cx ts = H->gamma * t, tt = mk(1.0) - t;
             const DevProgram& PG = jac ? H->Gj : H->Ge;
             const DevProgram& PF = jac ? H->Fj : H->Fe;
-            for (int i = 0; i < nn; ++i) u[i] = mk(0.0);
-            if (jac) for (int i = 0; i < nn * nn; ++i) (*U)[i] = mk(0.0);
-            load_inputs<cx>(PG, M.tape, x, nullptr, t, H->G_params);
-            run_tape<cx>(PG, M.tape);
-            for (int k = 0; k < PG.nu; ++k) { int2 a = ld_i2(PG.u_assign + k); u[a.x] = ts * fetch(PG, M.tape, a.y); }
-            if (jac) for (int k = 0; k < PG.nU; ++k) { int2 a = ld_i2(PG.U_assign + k); (*U)[a.x] = ts * fetch(PG, M.tape, a.y); }
-            load_inputs<cx>(PF, M.tape, x, nullptr, t, H->F_params);
-            run_tape<cx>(PF, M.tape);
-            for (int k = 0; k < PF.nu; ++k) { int2 a = ld_i2(PF.u_assign + k); u[a.x] = cfma(tt, fetch(PF, M.tape, a.y), u[a.x]); }
-            if (jac) for (int k = 0; k < PF.nU; ++k) { int2 a = ld_i2(PF.U_assign + k); (*U)[a.x] = cfma(tt, fetch(PF, M.tape, a.y), (*U)[a.x]); }
+            // F first (plain stores), then the few entries of the start system are accumulated
+            if (PF.nu != nn) HC_PAR(i, nn) u[i] = mk(0.0);
+            if (jac && PF.nU != nn * nn) HC_PAR(i, nn * nn) (*U)[i] = mk(0.0);
+            load_inputs<cx>(PF, x, nullptr, t, H->F_params);
+            run_tape<cx, G>(PF, tape, g);
+            extract<1>(u, tape, PF.u_assign, PF.nu, tt);
+            if (jac) extract<1>(*U, tape, PF.U_assign, PF.nU, tt);
+            g.sync();
+            load_inputs<cx>(PG, x, nullptr, t, H->G_params);
+            run_tape<cx, G>(PG, tape, g);
+            extract<2>(u, tape, PG.u_assign, PG.nu, ts);
+            if (jac) extract<2>(*U, tape, PG.U_assign, PG.nU, ts);
+            g.sync();
         } else {
             const DevProgram& PF = jac ? H->Fj : H->Fe;
-            load_inputs<cx>(PF, M.tape, x, nullptr, t, nullptr);
-            run_tape<cx>(PF, M.tape);
-            if (PF.nu != nn) for (int i = 0; i < nn; ++i) u[i] = mk(0.0);
-            for (int k = 0; k < PF.nu; ++k) { int2 a = ld_i2(PF.u_assign + k); u[a.x] = fetch(PF, M.tape, a.y); }
-            if (jac) {
-                if (PF.nU != nn * nn) for (int i = 0; i < nn * nn; ++i) (*U)[i] = mk(0.0);
-                for (int k = 0; k < PF.nU; ++k) { int2 a = ld_i2(PF.U_assign + k); (*U)[a.x] = fetch(PF, M.tape, a.y); }
-            }
+            if (PF.nu != nn) HC_PAR(i, nn) u[i] = mk(0.0);
+            if (jac && PF.nU != nn * nn) HC_PAR(i, nn * nn) (*U)[i] = mk(0.0);
+            load_inputs<cx>(PF, x, nullptr, t, nullptr);
+            run_tape<cx, G>(PF, tape, g);
+            extract<0>(u, tape, PF.u_assign, PF.nu, mk(0.0));
+            if (jac) extract<0>(*U, tape, PF.U_assign, PF.nU, mk(0.0));
+            g.sync();
         }
     }
     // DoubleDouble re-evaluation of the residual, rounded to fp64 on store
@@ -238,101 +320,141 @@ struct Path {
     HC_HDN void eval_dd(CV u, CV x, const CV* xlo, cx t) {
         const int nn = n;
         n_evaldd++;
+        CV tape = M.tape;
+        cdd* tag = nullptr;
         if (kind == H_STRAIGHT_LINE) {
             const cdd ts = tocdd(H->gamma * t), tt = tocdd(mk(1.0) - t);
-            for (int i = 0; i < nn; ++i) M.rbd.set(i, tocdd(mk(0.0)));
-            load_inputs<cdd>(H->Ge, M.tape_dd, x, xlo, t, H->G_params);
-            run_tape<cdd>(H->Ge, M.tape_dd);
-            for (int k = 0; k < H->Ge.nu; ++k) { int2 a = ld_i2(H->Ge.u_assign + k); M.rbd.set(a.x, ts * fetch(H->Ge, M.tape_dd, a.y)); }
-            load_inputs<cdd>(H->Fe, M.tape_dd, x, xlo, t, H->F_params);
-            run_tape<cdd>(H->Fe, M.tape_dd);
-            for (int k = 0; k < H->Fe.nu; ++k) { int2 a = ld_i2(H->Fe.u_assign + k); M.rbd.set(a.x, M.rbd.get(a.x) + tt * fetch(H->Fe, M.tape_dd, a.y)); }
-            for (int i = 0; i < nn; ++i) u[i] = tocx(M.rbd.get(i));
+            HC_PAR(i, nn) M.rbd.set(i, tocdd(mk(0.0)));
+            load_inputs<cdd>(H->Ge, x, xlo, t, H->G_params);
+            run_tape<cdd, G>(H->Ge, tape, g);
+            HC_PAR(k, H->Ge.nu) { int2 a = H->Ge.u_assign[k]; M.rbd.set(a.x, ts * tload(tape, a.y, tag)); }
+            g.sync();
+            load_inputs<cdd>(H->Fe, x, xlo, t, H->F_params);
+            run_tape<cdd, G>(H->Fe, tape, g);
+            HC_PAR(k, H->Fe.nu) { int2 a = H->Fe.u_assign[k]; M.rbd.set(a.x, M.rbd.get(a.x) + tt * tload(tape, a.y, tag)); }
+            g.sync();
+            HC_PAR(i, nn) u[i] = tocx(M.rbd.get(i));
+            g.sync();
         } else {
             const DevProgram& PF = H->Fe;
-            load_inputs<cdd>(PF, M.tape_dd, x, xlo, t, nullptr);
-            run_tape<cdd>(PF, M.tape_dd);
-            if (PF.nu != nn) for (int i = 0; i < nn; ++i) u[i] = mk(0.0);
-            for (int k = 0; k < PF.nu; ++k) { int2 a = ld_i2(PF.u_assign + k); u[a.x] = tocx(fetch(PF, M.tape_dd, a.y)); }
+            if (PF.nu != nn) HC_PAR(i, nn) u[i] = mk(0.0);
+            load_inputs<cdd>(PF, x, xlo, t, nullptr);
+            run_tape<cdd, G>(PF, tape, g);
+            HC_PAR(k, PF.nu) { int2 a = PF.u_assign[k]; u[a.x] = tocx(tload(tape, a.y, tag)); }
+            g.sync();
         }
     }
 
     template <int K>
-    HC_HD void taylor_inputs(const DevProgram& P, CV tx, cx t, const cx* fixed) {
-        for (int i = 0; i < P.P; ++i) {
+    HC_HDN void taylor_inputs(const DevProgram& P, CV tx, cx t, const cx* fixed) {
+        CV tape = M.tape;
+        HC_PAR(i, P.C) {
+            tape[i * (K + 1)] = P.consts[i];
+#pragma unroll
+            for (int k = 1; k <= K; ++k) tape[i * (K + 1) + k] = mk(0.0);
+        }
+        HC_PAR(i, P.P) {
             cx c[5];
-            if (fixed) { c[0] = ld_const(fixed + i); c[1] = c[2] = c[3] = c[4] = mk(0.0); }
+            if (fixed) { c[0] = fixed[i]; c[1] = c[2] = c[3] = c[4] = mk(0.0); }
             else param_series(i, t, c);
-            const int b = (P.param_off + i - P.C) * (K + 1);
+            const int b = (P.param_off + i) * (K + 1);
 #pragma unroll
-            for (int k = 0; k <= K; ++k) M.tape[b + k] = c[k];
+            for (int k = 0; k <= K; ++k) tape[b + k] = c[k];
         }
-        if (P.t_slot >= 0) {
-            const int b = (P.t_slot - P.C) * (K + 1);
-            M.tape[b] = t; M.tape[b + 1] = mk(1.0);
+        if (P.t_slot >= 0 && g.lane == 0) {
+            const int b = P.t_slot * (K + 1);
+            tape[b] = t; tape[b + 1] = mk(1.0);
 #pragma unroll
-            for (int k = 2; k <= K; ++k) M.tape[b + k] = mk(0.0);
+            for (int k = 2; k <= K; ++k) tape[b + k] = mk(0.0);
         }
-        for (int i = 0; i < P.n; ++i) {  // x series: rows 0..K-1 of tx, coefficient K zero padded
-            const int b = (P.var_off + i - P.C) * (K + 1);
+        HC_PAR(i, P.n) {  // x series: rows 0..K-1 of tx, coefficient K zero padded
+            const int b = (P.var_off + i) * (K + 1);
 #pragma unroll
-            for (int k = 0; k < K; ++k) M.tape[b + k] = tx[k * n + i];
-            M.tape[b + K] = mk(0.0);
+            for (int k = 0; k < K; ++k) tape[b + k] = tx[k * n + i];
+            tape[b + K] = mk(0.0);
         }
-    }
-    template <int K>
-    HC_HD cx ser_coeff(const DevProgram& P, int slot, int k) {
-        if (slot < P.C) return k == 0 ? ld_const(P.consts + slot) : mk(0.0);
-        return M.tape[(slot - P.C) * (K + 1) + k];
+        g.sync();
     }
     // u = K-th Taylor coefficient of lambda -> H(x(lambda), t + lambda); tx rows x^0..x^{K-1}
     template <int K>
     HC_HDN void taylor(CV u, CV tx, cx t) {
         if (K == 1) n_tay1++; else if (K == 2) n_tay2++; else n_tay3++;
-        for (int i = 0; i < n; ++i) u[i] = mk(0.0);
+        CV tape = M.tape;
+        HC_PAR(i, n) u[i] = mk(0.0);
         if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:130-154
             taylor_inputs<K>(H->Ge, tx, t, H->G_params);
-            run_taylor_tape<K>(H->Ge, M.tape);
-            for (int k = 0; k < H->Ge.nu; ++k) {
-                int2 a = ld_i2(H->Ge.u_assign + k);
-                u[a.x] = H->gamma * (ser_coeff<K>(H->Ge, a.y, K - 1) + t * ser_coeff<K>(H->Ge, a.y, K));
+            run_taylor_tape<K, G>(H->Ge, tape, g);
+            HC_PAR(k, H->Ge.nu) {
+                int2 a = H->Ge.u_assign[k];
+                u[a.x] = H->gamma * (tape[a.y * (K + 1) + K - 1] + t * tape[a.y * (K + 1) + K]);
             }
+            g.sync();
             taylor_inputs<K>(H->Fe, tx, t, H->F_params);
-            run_taylor_tape<K>(H->Fe, M.tape);
-            for (int k = 0; k < H->Fe.nu; ++k) {
-                int2 a = ld_i2(H->Fe.u_assign + k);
-                u[a.x] = u[a.x] + ((mk(1.0) - t) * ser_coeff<K>(H->Fe, a.y, K) - ser_coeff<K>(H->Fe, a.y, K - 1));
+            run_taylor_tape<K, G>(H->Fe, tape, g);
+            HC_PAR(k, H->Fe.nu) {
+                int2 a = H->Fe.u_assign[k];
+                u[a.x] = u[a.x] + ((mk(1.0) - t) * tape[a.y * (K + 1) + K] - tape[a.y * (K + 1) + K - 1]);
             }
+            g.sync();
         } else {  // parameter / coefficient / toric: parameters are series in lambda
             taylor_inputs<K>(H->Fe, tx, t, nullptr);
-            run_taylor_tape<K>(H->Fe, M.tape);
-            for (int k = 0; k < H->Fe.nu; ++k) { int2 a = ld_i2(H->Fe.u_assign + k); u[a.x] = ser_coeff<K>(H->Fe, a.y, K); }
+            run_taylor_tape<K, G>(H->Fe, tape, g);
+            HC_PAR(k, H->Fe.nu) { int2 a = H->Fe.u_assign[k]; u[a.x] = tape[a.y * (K + 1) + K]; }
+            g.sync();
         }
     }
 
     // ================================================================ linear algebra
-    HC_HD void updated() {  // linear_algebra.jl:88-98
-        factorized = false; scaled = false;
-        const int nn = n * n;
-        for (int i = 0; i < nn; ++i) M.LU[i] = M.A[i];
+    // updated!(J) linear_algebra.jl:88-98: the copy A -> LU buffer is deferred to the factorization
+    // (lu_prepare), where it is fused with the row scaling
+    HC_HD void updated() { factorized = false; scaled = false; }
+    HC_HDN void lu_prepare(bool scale) {
+        const int nn = n;
+        if (!scale) { vcopy(M.LU, M.A, nn * nn); return; }
+        if (G == 1) {
+            for (int j = 0; j < nn; ++j) {
+                int i = 0;
+                for (; i + 3 < nn; i += 4) {
+                    cx a0 = M.A[j * nn + i], a1 = M.A[j * nn + i + 1], a2 = M.A[j * nn + i + 2], a3 = M.A[j * nn + i + 3];
+                    double r0 = M.rs[i], r1 = M.rs[i + 1], r2 = M.rs[i + 2], r3 = M.rs[i + 3];
+                    M.LU[j * nn + i] = a0 * r0; M.LU[j * nn + i + 1] = a1 * r1; M.LU[j * nn + i + 2] = a2 * r2; M.LU[j * nn + i + 3] = a3 * r3;
+                }
+                for (; i < nn; ++i) M.LU[j * nn + i] = M.A[j * nn + i] * M.rs[i];
+            }
+        } else {
+            for (int j = 0; j < nn; ++j) HC_PAR(i, nn) M.LU[j * nn + i] = M.A[j * nn + i] * M.rs[i];
+            g.sync();
+        }
     }
-    HC_HDN void lu_factor() {  // :130-184
+    HC_HDN void lu_factor() {  // :130-184  right-looking, pivot = max abs2, first index wins ties
         const int nn = n;
         CV A = M.LU;
         for (int k = 0; k < nn; ++k) {
-            int kp = k;
-            double amax = abs2(A[k * nn + k]);
-            for (int i = k + 1; i < nn; ++i) { double v = abs2(A[k * nn + i]); if (v > amax) { kp = i; amax = v; } }
-            M.ipiv[k] = kp;
-            if (amax != 0.0) {
-                if (kp != k) for (int j = 0; j < nn; ++j) { cx tmp = A[j * nn + k]; A[j * nn + k] = A[j * nn + kp]; A[j * nn + kp] = tmp; }
+            double amax = -1.0; int kp = k;
+            for (int i = k + g.lane; i < nn; i += G) { double v = abs2(A[k * nn + i]); if (v > amax) { amax = v; kp = i; } }
+            g.argmax(amax, kp);
+            if (g.lane == 0) M.ipiv[k] = kp;
+            if (amax > 0.0) {
+                if (kp != k) { HC_PAR(j, nn) { cx tmp = A[j * nn + k]; A[j * nn + k] = A[j * nn + kp]; A[j * nn + kp] = tmp; } g.sync(); }
                 cx pinv = cinv(A[k * nn + k]);
-                for (int i = k + 1; i < nn; ++i) A[k * nn + i] = A[k * nn + i] * pinv;
+                for (int i = k + 1 + g.lane; i < nn; i += G) A[k * nn + i] = A[k * nn + i] * pinv;
+                g.sync();
             }
-            for (int j = k + 1; j < nn; ++j) {
-                cx akj = A[j * nn + k];
-                for (int i = k + 1; i < nn; ++i) A[j * nn + i] = cfnma(A[k * nn + i], akj, A[j * nn + i]);
+            const int m = nn - k - 1;
+            if (G == 1) {
+                for (int j = k + 1; j < nn; ++j) col_fnma(A.at(j * nn), A.at(k * nn), A[j * nn + k], k + 1, nn);
+            } else if (m > 0) {
+                // trailing update, (column, row) pairs strided over the lanes
+                int jc = g.lane / m, ir = g.lane - jc * m;
+                const int dj = G / m, di = G - dj * m;
+                while (jc < m) {
+                    const int j = k + 1 + jc, i = k + 1 + ir;
+                    A[j * nn + i] = cfnma(A[k * nn + i], A[j * nn + k], A[j * nn + i]);
+                    jc += dj; ir += di;
+                    if (ir >= m) { ir -= m; jc += 1; }
+                }
             }
+            g.sync();
         }
         factorized = true;
         n_fact++;
@@ -340,86 +462,109 @@ struct Path {
     HC_HDN void lu_solve(CV x) {  // :310-316 (in place)
         const int nn = n;
         CV A = M.LU;
-        for (int i = 0; i < nn; ++i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
-        for (int j = 0; j < nn; ++j) { cx xj = x[j]; for (int i = j + 1; i < nn; ++i) x[i] = cfnma(A[j * nn + i], xj, x[i]); }
+        if (g.lane == 0) for (int i = 0; i < nn; ++i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
+        g.sync();
+        for (int j = 0; j < nn - 1; ++j) {
+            cx xj = x[j];
+            col_fnma(x, A.at(j * nn), xj, j + 1, nn);
+            g.sync();
+        }
         for (int j = nn - 1; j >= 0; --j) {
-            cx xj = cdiv(x[j], A[j * nn + j]); x[j] = xj;
-            for (int i = 0; i < j; ++i) x[i] = cfnma(A[j * nn + i], xj, x[i]);
+            cx xj = cdiv(x[j], A[j * nn + j]);
+            g.sync();
+            if (g.lane == 0) x[j] = xj;
+            col_fnma(x, A.at(j * nn), xj, 0, j);
+            g.sync();
         }
     }
     HC_HDN void lu_solve_adj(CV x) {  // :318-354 (in place)
         const int nn = n;
         CV A = M.LU;
-        for (int j = 0; j < nn; ++j) {
-            cx z = x[j];
-            for (int i = 0; i < j; ++i) z = cfnma(conj(A[j * nn + i]), x[i], z);
-            x[j] = cdiv(z, conj(A[j * nn + j]));
+        for (int j = 0; j < nn; ++j) {  // U^H z = x: column j of U gives a dot product
+            double zr = 0.0, zi = 0.0;
+            HC_PAR(i, j) { cx p = conj(A[j * nn + i]) * x[i]; zr += p.re; zi += p.im; }
+            zr = g.rsum(zr); zi = g.rsum(zi);
+            cx z = cdiv(x[j] - mk(zr, zi), conj(A[j * nn + j]));
+            g.sync();
+            if (g.lane == 0) x[j] = z;
+            g.sync();
         }
-        for (int j = nn - 1; j >= 0; --j) {
-            cx z = x[j];
-            for (int i = nn - 1; i > j; --i) z = cfnma(conj(A[j * nn + i]), x[i], z);
-            x[j] = z;
+        for (int j = nn - 1; j >= 0; --j) {  // L^H
+            double zr = 0.0, zi = 0.0;
+            for (int i = j + 1 + g.lane; i < nn; i += G) { cx p = conj(A[j * nn + i]) * x[i]; zr += p.re; zi += p.im; }
+            zr = g.rsum(zr); zi = g.rsum(zi);
+            cx z = x[j] - mk(zr, zi);
+            g.sync();
+            if (g.lane == 0) x[j] = z;
+            g.sync();
         }
-        for (int i = nn - 1; i >= 0; --i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
+        if (g.lane == 0) for (int i = nn - 1; i >= 0; --i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
+        g.sync();
     }
     // skeel_row_scaling!(d, A, c; threshold)  :432-459
     HC_HDN void skeel(RV d, RV c, double threshold) {
         const int nn = n;
-        for (int i = 0; i < nn; ++i) d[i] = 0.0;
-        for (int j = 0; j < nn; ++j) { double cj = c[j]; for (int i = 0; i < nn; ++i) d[i] += cabs(M.A[j * nn + i]) * cj; }
-        double m = d[0];
-        for (int i = 1; i < nn; ++i) m = jmax(m, d[i]);
+        double m = -HC_INF;
+        HC_PAR(i, nn) {
+            double di = 0.0;
+            for (int j = 0; j < nn; ++j) di += cabs(M.A[j * nn + i]) * c[j];
+            d[i] = di;
+            m = nmax(m, di);
+        }
+        m = g.rmax(m);
         double s = threshold + m;
-        for (int i = 0; i < nn; ++i) {
+        HC_PAR(i, nn) {
             int e = 0; double di = d[i];
             if (di != 0.0 && di == di && di < HC_INF) frexp(di, &e);
             d[i] = (e < s) ? 1.0 : ldexp(1.0, -e);
         }
+        g.sync();
     }
     // ldiv!(x, J, b[, norm])  :389-408, 833-862;  x may alias b
     HC_HDN void ldiv(CV x, CV b, bool with_norm) {
         const int nn = n;
         n_ldiv++;
-        if (with_norm && !factorized) {
-            skeel(M.rs, M.w, -30.0);
-            for (int j = 0; j < nn; ++j) for (int i = 0; i < nn; ++i) M.LU[j * nn + i] = M.LU[j * nn + i] * M.rs[i];
-            scaled = true;
-        }
-        if (nn == 1) { x[0] = cdiv(b[0], M.A[0]); return; }
-        if (!factorized) lu_factor();
-        if (scaled) for (int i = 0; i < nn; ++i) x[i] = M.rs[i] * b[i];
-        else if (x.p != b.p) for (int i = 0; i < nn; ++i) x[i] = b[i];
+        if (with_norm && !factorized) { skeel(M.rs, M.w, -30.0); scaled = true; }
+        if (nn == 1) { cx v = cdiv(b[0], M.A[0]); g.sync(); if (g.lane == 0) x[0] = v; g.sync(); return; }
+        if (!factorized) { lu_prepare(scaled); lu_factor(); }
+        if (scaled) { HC_PAR(i, nn) x[i] = M.rs[i] * b[i]; g.sync(); }
+        else if (x.p != b.p) vcopy(x, b, nn);
         lu_solve(x);
     }
     // one sweep of fixed precision refinement (:553-567); returns |dx| / |x| in the given norm
     HC_HDN double refine_fixed(CV x, CV b, bool weighted) {
         const int nn = n;
-        for (int i = 0; i < nn; ++i) M.wr[i] = -b[i];
-        for (int j = 0; j < nn; ++j) { cx xj = x[j]; for (int i = 0; i < nn; ++i) M.wr[i] = cfma(M.A[j * nn + i], xj, M.wr[i]); }
+        HC_PAR(i, nn) {
+            cx acc = -b[i];
+            for (int j = 0; j < nn; ++j) acc = cfma(M.A[j * nn + i], x[j], acc);
+            M.wr[i] = acc;
+        }
+        g.sync();
         n_ldiv--;  // workspace-level ldiv! is not counted by Jacobian.ldivs
         ldiv(M.wdx, M.wr, false);
-        for (int i = 0; i < nn; ++i) x[i] = x[i] - M.wdx[i];
-        return weighted ? wnorm(M.wdx, M.w, nn) / wnorm(x, M.w, nn) : inf_norm(M.wdx, nn) / inf_norm(x, nn);
+        HC_PAR(i, nn) x[i] = x[i] - M.wdx[i];
+        g.sync();
+        return weighted ? wnorm(M.wdx) / wnorm(x) : inf_norm(M.wdx) / inf_norm(x);
     }
     // one sweep of mixed precision refinement (:528-544): residual A x - b accumulated in DD
     HC_HDN double refine_mixed(CV x, CV b, bool weighted) {
         const int nn = n;
-        for (int i = 0; i < nn; ++i) M.rbd.set(i, tocdd(-b[i]));
-        for (int j = 0; j < nn; ++j) {
-            cx xj = x[j];  // x converted exactly to DD, A stays fp64: products are exact two_prods
-            for (int i = 0; i < nn; ++i) {
-                cx a = M.A[j * nn + i];
+        HC_PAR(i, nn) {
+            cdd acc = tocdd(-b[i]);
+            for (int j = 0; j < nn; ++j) {
+                cx a = M.A[j * nn + i], xj = x[j];  // x converted exactly to DD, A stays fp64: products are exact two_prods
                 dd rr = two_prod(a.re, xj.re) - two_prod(a.im, xj.im);
                 dd ri = two_prod(a.re, xj.im) + two_prod(a.im, xj.re);
-                cdd acc = M.rbd.get(i);
-                M.rbd.set(i, mkcdd(acc.re + rr, acc.im + ri));
+                acc = mkcdd(acc.re + rr, acc.im + ri);
             }
+            M.wr[i] = tocx(acc);
         }
-        for (int i = 0; i < nn; ++i) M.wr[i] = tocx(M.rbd.get(i));
+        g.sync();
         n_ldiv--;
         ldiv(M.wdx, M.wr, false);
-        for (int i = 0; i < nn; ++i) x[i] = x[i] - M.wdx[i];
-        return weighted ? wnorm(M.wdx, M.w, nn) / wnorm(x, M.w, nn) : inf_norm(M.wdx, nn) / inf_norm(x, nn);
+        HC_PAR(i, nn) x[i] = x[i] - M.wdx[i];
+        g.sync();
+        return weighted ? wnorm(M.wdx) / wnorm(x) : inf_norm(M.wdx) / inf_norm(x);
     }
     // iterative_refinement!(x, J, b, norm; max_iters, tol)  :864-885
     HC_HDN void iterative_refinement(CV x, CV b, bool weighted, int max_iters, double tol) {
@@ -436,53 +581,65 @@ struct Path {
     // Hager/Higham estimator of |diag(d_r)^-1 A^-1 diag(d_l)^-1|_inf  :585-682
     HC_HDN double inverse_inf_norm_est(const RV* dl, const RV* dr) {
         const int nn = n;
-        if (!factorized) lu_factor();
+        if (!factorized) { lu_prepare(false); lu_factor(); }
         CV y = M.work; RV x = M.rwork;
-        for (int i = 0; i < nn; ++i) { double v = 1.0 / nn; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
+        HC_PAR(i, nn) { double v = 1.0 / nn; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
+        g.sync();
         lu_solve_adj(y);
         double gamma = 0;
-        for (int i = 0; i < nn; ++i) {
+        HC_PAR(i, nn) {
             cx v = y[i]; if (dl) v = v / (*dl)[i]; if (scaled) v = v * M.rs[i];
             double a = cabs(v); gamma += a;
             v = v / a; if (dl) v = v / (*dl)[i]; if (scaled) v = v / M.rs[i];
             y[i] = v;
         }
+        gamma = g.rsum(gamma);
+        g.sync();
         lu_solve(y);
-        for (int i = 0; i < nn; ++i) x[i] = dr ? y[i].re / (*dr)[i] : y[i].re;
+        HC_PAR(i, nn) x[i] = dr ? y[i].re / (*dr)[i] : y[i].re;
+        g.sync();
         int k = 2;
         while (true) {
-            int j = 0; double mx = fabs(x[0]);
-            for (int i = 1; i < nn; ++i) { double a = fabs(x[i]); if (a > mx) { j = i; mx = a; } }
-            for (int i = 0; i < nn; ++i) { double v = (i == j) ? 1.0 : 0.0; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
+            double mx = -1.0; int j = 0;
+            HC_PAR(i, nn) { double a = fabs(x[i]); if (a != a) a = -0.5; if (a > mx) { mx = a; j = i; } }
+            g.argmax(mx, j);
+            g.sync();
+            HC_PAR(i, nn) { double v = (i == j) ? 1.0 : 0.0; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
+            g.sync();
             lu_solve_adj(y);
             double gbar = gamma; gamma = 0;
-            for (int i = 0; i < nn; ++i) {
+            HC_PAR(i, nn) {
                 cx v = y[i]; if (dl) v = v / (*dl)[i]; if (scaled) v = v * M.rs[i];
                 y[i] = v; gamma += cabs(v);
             }
+            gamma = g.rsum(gamma);
+            g.sync();
             if (gamma <= gbar) { gamma = gbar; break; }
-            for (int i = 0; i < nn; ++i) {
+            HC_PAR(i, nn) {
                 cx v = y[i]; v = v / cabs(v); if (dl) v = v / (*dl)[i]; if (scaled) v = v / M.rs[i];
                 y[i] = v;
             }
+            g.sync();
             lu_solve(y);
             double ninf = 0;
-            for (int i = 0; i < nn; ++i) { double v = dr ? y[i].re / (*dr)[i] : y[i].re; x[i] = v; ninf = jmax(ninf, fabs(v)); }
+            HC_PAR(i, nn) { double v = dr ? y[i].re / (*dr)[i] : y[i].re; x[i] = v; double a = fabs(v); ninf = a > ninf ? a : ninf; }
+            ninf = g.rmax(ninf);
+            g.sync();
             k += 1;
             if (x[j] == ninf || k > 2) break;
         }
         return nanmin(gamma, HC_INF);
     }
-    HC_HD double a_inf_norm(const RV* dl, const RV* dr) {  // :684-707
+    HC_HDN double a_inf_norm(const RV* dl, const RV* dr) {  // :684-707
         const int nn = n;
         double nrm = -HC_INF;
-        for (int i = 0; i < nn; ++i) {
+        HC_PAR(i, nn) {
             double ni = 0.0;
             for (int j = 0; j < nn; ++j) ni += dr ? cabs(M.A[j * nn + i]) * (*dr)[j] : cabs(M.A[j * nn + i]);
             if (dl) ni *= (*dl)[i];
-            nrm = fmaxq(nrm, ni);
+            nrm = ni > nrm ? ni : nrm;
         }
-        return nrm;
+        return g.rmax(nrm);
     }
     HC_HDN double jac_cond(const RV* dl, const RV* dr) {  // :745-774
         if (n == 1) {
@@ -491,7 +648,8 @@ struct Path {
             if (dr) a *= (*dr)[0];
             return 1.0 / a;
         }
-        return inverse_inf_norm_est(dl, dr) * a_inf_norm(dl, dr);
+        double e = inverse_inf_norm_est(dl, dr);
+        return e * a_inf_norm(dl, dr);
     }
     // LA.cond(tracker, x, t, d_l, d_r)  tracker.jl:509-514
     HC_HDN double cond_at(CV x, cx t, const RV* dl, const RV* dr) {
@@ -501,23 +659,25 @@ struct Path {
     }
 
     // ================================================================ norm weights (norm.jl:101-136)
-    HC_HD void norm_init(CV x) {
-        const double pn = inf_norm(x, n);
-        for (int i = 0; i < n; ++i) {
+    HC_HDN void norm_init(CV x) {
+        const double pn = inf_norm(x);
+        HC_PAR(i, n) {
             double wi = cabs(x[i]);
             if (wi < O->scale_min * pn) wi = O->scale_min * pn;
             else if (wi > O->scale_max * pn) wi = O->scale_max * pn;
             M.w[i] = jmax(wi, O->scale_abs_min);
         }
+        g.sync();
     }
-    HC_HD void norm_update(CV x) {
-        const double nx = wnorm(x, M.w, n);
-        for (int i = 0; i < n; ++i) {
+    HC_HDN void norm_update(CV x) {
+        const double nx = wnorm(x);
+        HC_PAR(i, n) {
             double wi = (cabs(x[i]) + M.w[i]) / 2;
             if (wi < O->scale_min * nx) wi = O->scale_min * nx;
             else if (wi > O->scale_max * nx) wi = O->scale_max * nx;
             if (wi == wi && wi < HC_INF && wi > -HC_INF) M.w[i] = jmax(wi, O->scale_abs_min);
         }
+        g.sync();
     }
 
     // ================================================================ stepper (utils.jl:300-394)
@@ -559,50 +719,55 @@ struct Path {
     HC_HDN void pred_update(cx t, bool have_xhat) {
         const int nn = n;
         CV x0 = M.tx, x1 = M.tx.at(nn), x2 = M.tx.at(2 * nn), x3 = M.tx.at(3 * nn);
-        for (int i = 0; i < 2 * nn; ++i) M.ptx1[i] = M.tx[i];
+        HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i];
+        g.sync();
         pprev_t = pt; pt = t;
         if (winding > 1) { pprev_s = ps; ps = t_to_s_plane(t, winding); }
         if (!have_xhat) local_error = HC_NAN;
         else {
             double ds = cabs(t - pprev_t), d2 = ds * ds;
-            local_error = wdist(M.xhat, M.x, M.w, nn) / (d2 * d2);
+            local_error = wdist(M.xhat, M.x) / (d2 * d2);
         }
-        for (int i = 0; i < nn; ++i) x0[i] = M.x[i];
-        double nrm0 = wnorm(M.x, M.w, nn);
-        if (winding > 1) for (int i = 0; i < nn; ++i) M.ty1[i] = M.x[i];
+        HC_PAR(i, nn) { x0[i] = M.x[i]; if (winding > 1) M.ty1[i] = M.x[i]; }
+        g.sync();
+        double nrm0 = wnorm(M.x);
 
         taylor<1>(M.u, M.tx, t);
-        for (int i = 0; i < nn; ++i) M.u[i] = -M.u[i];
+        HC_PAR(i, nn) M.u[i] = -M.u[i];
+        g.sync();
         ldiv(M.xtemp, M.u, false);
         double delta = refine_fixed(M.xtemp, M.u, true);
         cond_H = delta / HC_EPS;
         if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, false, 5, 1e-10);
-        double nrm1 = wnorm(M.xtemp, M.w, nn);
-        for (int i = 0; i < nn; ++i) x1[i] = M.xtemp[i];
+        double nrm1 = wnorm(M.xtemp);
         if (winding > 1) {
-            cx mu = winding == 2 ? 2.0 * ps : (double)winding * cpow_pos(ps, winding - 1);
-            for (int i = 0; i < nn; ++i) M.ty1[nn + i] = mu * M.xtemp[i];
+            cx mu_ = winding == 2 ? 2.0 * ps : (double)winding * cpowi(ps, winding - 1);
+            HC_PAR(i, nn) { x1[i] = M.xtemp[i]; M.ty1[nn + i] = mu_ * M.xtemp[i]; }
+            g.sync();
             pm_hermite = 1;
             trust_region = nrm0 / nrm1;
             if (local_error != local_error) { double q = nrm1 / nrm0; local_error = q * q * q; }
             return;
         }
+        vcopy(x1, M.xtemp, nn);
         taylor<2>(M.u, M.tx, t);
-        for (int i = 0; i < nn; ++i) M.u[i] = -M.u[i];
+        HC_PAR(i, nn) M.u[i] = -M.u[i];
+        g.sync();
         ldiv(M.xtemp, M.u, false);
         if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, true, 4, 1e-10);
-        double nrm2 = wnorm(M.xtemp, M.w, nn);
-        for (int i = 0; i < nn; ++i) x2[i] = M.xtemp[i];
+        double nrm2 = wnorm(M.xtemp);
+        vcopy(x2, M.xtemp, nn);
 
         taylor<3>(M.u, M.tx, t);
-        for (int i = 0; i < nn; ++i) M.u[i] = -M.u[i];
+        HC_PAR(i, nn) M.u[i] = -M.u[i];
+        g.sync();
         ldiv(M.xtemp, M.u, false);
         if (delta > 1e-4) iterative_refinement(M.xtemp, M.u, true, 3, 1e-4);
-        double nrm3 = wnorm(M.xtemp, M.w, nn);
-        for (int i = 0; i < nn; ++i) x3[i] = M.xtemp[i];
+        double nrm3 = wnorm(M.xtemp);
+        vcopy(x3, M.xtemp, nn);
 
         double tau_ = HC_INF;
-        for (int i = 0; i < nn; ++i) {
+        HC_PAR(i, nn) {
             double c1 = cabs(x1[i]), c2 = cabs(x2[i]), c3 = cabs(x3[i]);
             double lam = jmax(1e-6, c1);
             c1 /= lam; c2 /= lam * lam; c3 /= lam * lam * lam;
@@ -612,30 +777,36 @@ struct Path {
                 if (ti < tau_) tau_ = ti;
             }
         }
+        {   // min over the lanes; NaN candidates never win (as in the sequential `ti < tau`)
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) { double w = g.xshfl(tau_, o); tau_ = w < tau_ ? w : tau_; }
+            tau_ = g.bcast(tau_, 0);
+        }
         if (!(tau_ < HC_INF && tau_ > -HC_INF)) tau_ = nrm2 / nrm3;
         if (!(tau_ < HC_INF && tau_ > -HC_INF)) tau_ = nrm0 / jmax(jmax(nrm0, nrm1), jmax(nrm2, nrm3));
         pm_hermite = 0;
         trust_region = tau_;
         if (local_error != local_error) { double q = 1.0 / tau_; local_error = (q * q) * (q * q); }
     }
-    HC_HD void cubic_hermite(CV xh, CV v0, CV d0, cx t0, CV v1, CV d1, cx t1, cx t) {  // predictor.jl:354-371
+    HC_HDN void cubic_hermite(CV xh, CV v0, CV d0, cx t0, CV v1, CV d1, cx t1, cx t) {  // predictor.jl:354-371
         const int nn = n;
         if (t0.im == 0 && t1.im == 0 && t.im == 0) {
             double T = t.re, T0 = t0.re, T1 = t1.re;
             double s = (T - T0) / (T1 - T0), oms2 = (1 - s) * (1 - s);
             double h00 = (1 + 2 * s) * oms2, h10 = (T - T0) * oms2, h01 = (s * s) * (3 - 2 * s), h11 = (T - T0) * s * (s - 1);
-            for (int i = 0; i < nn; ++i) xh[i] = h00 * v0[i] + h10 * d0[i] + h01 * v1[i] + h11 * d1[i];
+            HC_PAR(i, nn) xh[i] = h00 * v0[i] + h10 * d0[i] + h01 * v1[i] + h11 * d1[i];
         } else {
             cx one = mk(1.0), s = cdiv(t - t0, t1 - t0), oms2 = (one - s) * (one - s);
             cx h00 = (one + 2.0 * s) * oms2, h10 = (t - t0) * oms2, h01 = (s * s) * (mk(3.0) - 2.0 * s), h11 = (t - t0) * s * (s - one);
-            for (int i = 0; i < nn; ++i) xh[i] = h00 * v0[i] + h10 * d0[i] + h01 * v1[i] + h11 * d1[i];
+            HC_PAR(i, nn) xh[i] = h00 * v0[i] + h10 * d0[i] + h01 * v1[i] + h11 * d1[i];
         }
+        g.sync();
     }
     HC_HDN void predict(cx t, cx dt) {  // predictor.jl:286-329
         const int nn = n;
         if (!pm_hermite) {
             double lam = trust_region, lam2 = lam * lam, lam3 = lam2 * lam;
-            for (int i = 0; i < nn; ++i) {
+            HC_PAR(i, nn) {
                 cx X = M.tx[i], X1 = M.tx[nn + i], X2 = M.tx[2 * nn + i], X3 = M.tx[3 * nn + i];
                 double c = cabs(X), a1 = cabs(X1) * lam, a2 = cabs(X2) * lam2, a3 = cabs(X3) * lam3;
                 double tau_ = 1e-12 * sqrt(c * c + a1 * a1 + a2 * a2 + a3 * a3);
@@ -645,92 +816,103 @@ struct Path {
                     M.xhat[i] = X + dt * (X1 + cdiv(dt * X2, d));
                 }
             }
+            g.sync();
         } else {
             int mw = winding;
             cx s0 = t_to_s_plane(pprev_t, mw), s1 = t_to_s_plane(t, mw), sp = t_to_s_plane(t + dt, mw);
             cx psm, sm;
             if (mw == 2) { psm = 2.0 * s0; sm = 2.0 * s1; }
-            else { psm = (double)mw * cpow_pos(s0, mw - 1); sm = (double)mw * cpow_pos(s1, mw - 1); }
-            for (int i = 0; i < nn; ++i) { M.pty1[i] = M.ptx1[i]; M.pty1[nn + i] = psm * M.ptx1[nn + i]; }
-            for (int i = 0; i < nn; ++i) { M.ty1[i] = M.tx[i]; M.ty1[nn + i] = sm * M.tx[nn + i]; }
+            else { psm = (double)mw * cpowi(s0, mw - 1); sm = (double)mw * cpowi(s1, mw - 1); }
+            HC_PAR(i, nn) {
+                M.pty1[i] = M.ptx1[i]; M.pty1[nn + i] = psm * M.ptx1[nn + i];
+                M.ty1[i] = M.tx[i]; M.ty1[nn + i] = sm * M.tx[nn + i];
+            }
+            g.sync();
             cubic_hermite(M.xhat, M.pty1, M.pty1.at(nn), s0, M.ty1, M.ty1.at(nn), s1, sp);
         }
     }
 
     // ================================================================ Newton corrector
+    HC_HDN void axmy(CV out, CV a, CV b) { HC_PAR(i, n) out[i] = a[i] - b[i]; g.sync(); }  // out = a - b
     // extended_prec_refinement_step!  newton_corrector.jl:55-78 (xout may alias xin)
     HC_HDN double ext_refinement_step(CV xout, CV xin, cx t, bool simple_newton_step) {
-        const int nn = n;
         eval_f64(M.r, &M.A, xin, t);
         eval_dd(M.r, xin, nullptr, t);
         updated();
         ldiv(M.dx, M.r, true);
         iterative_refinement(M.dx, M.r, true, 3, 1e-8);
-        for (int i = 0; i < nn; ++i) xout[i] = xin[i] - M.dx[i];
+        axmy(xout, xin, M.dx);
         if (simple_newton_step) {
             eval_dd(M.r, xout, nullptr, t);
             ldiv(M.dx, M.r, true);
         }
-        return wnorm(M.dx, M.w, nn);
+        return wnorm(M.dx);
     }
-    // newton!  newton_corrector.jl:80-205; iterates live in xbar (x0 may alias xbar)
+    // newton!  newton_corrector.jl:80-205; iterates live in xbar (x0 may alias xbar).
+    // The reference's loop body and its convergence branch (:142-197, one more Jacobian + solve)
+    // are folded into ONE loop with a single evaluate/factorize/solve call site (`final` marks the
+    // convergence pass), so that lanes of a warp that are in different Newton iterations still
+    // execute the expensive primitives together.
     HC_HDN NewtonResult newton(CV x0, cx t, double mu_, double omega_, bool ext, bool accurate_mu, bool first_correction) {
         const int nn = n;
         const double a = O->a, h_a = hfun(a);
         CV xi = M.xbar;
-        if (xi.p != x0.p) for (int i = 0; i < nn; ++i) xi[i] = x0[i];
+        if (xi.p != x0.p) vcopy(xi, x0, nn);
         NewtonResult R; R.mu_low = R.theta = R.norm_dx0 = HC_NAN; R.omega = omega_;
         double ndxi = HC_NAN, ndxim1 = HC_NAN, abar = a;
-        for (int i = 0; i <= 10; ++i) {
+        bool final = false;
+        int i = 0;
+        while (true) {
             eval_f64(M.r, &M.A, xi, t);
-            if (ext) eval_dd(M.r, xi, nullptr, t);
+            if (ext && !final) eval_dd(M.r, xi, nullptr, t);
             updated();
-            ldiv(M.dx, M.r, true);
-            if (ext) iterative_refinement(M.dx, M.r, true, 3, abar * abar);
-            ndxi = wnorm(M.dx, M.w, nn);
-            if (ndxi != ndxi) { R.code = NEWT_SINGULARITY; R.accuracy = ndxi; R.iters = i + 1; return R; }
-            for (int k = 0; k < nn; ++k) xi[k] = xi[k] - M.dx[k];
-            if (i == 0) R.norm_dx0 = ndxi;
-            if (i == 1) R.omega = 2 * ndxi / (ndxim1 * ndxim1);
-            if (i >= 1) R.theta = ndxi / ndxim1;
-            if ((i >= 1 && R.theta > abar) || (i == 0 && !first_correction && 0.125 * R.norm_dx0 * R.omega > h_a)) {
-                R.code = NEWT_TERMINATED; R.accuracy = ndxi; R.iters = i + 1; return R;
-            } else if (R.omega * ndxi * ndxi < 2 * mu_ * sqrt(1 - 2 * h_a)) {
-                eval_f64(M.r, &M.A, xi, t);
-                updated();
-                if (ext) {
-                    ldiv(M.dx, M.r, false);
-                    R.mu_low = wnorm(M.dx, M.w, nn);
-                    eval_dd(M.r, xi, nullptr, t);
-                }
+            if (ext && final) {
                 ldiv(M.dx, M.r, false);
-                if (ext) iterative_refinement(M.dx, M.r, true, 3, abar * abar);
-                for (int k = 0; k < nn; ++k) xi[k] = xi[k] - M.dx[k];
-                double ndxip1 = wnorm(M.dx, M.w, nn);
-                if (ndxip1 != ndxip1) { R.code = NEWT_SINGULARITY; R.accuracy = ndxip1; R.iters = i + 1; return R; }
-                if (ndxip1 > sqrt(ndxi)) {
-                    R.theta = ndxip1 / ndxi; R.code = NEWT_TERMINATED; R.accuracy = ndxip1; R.iters = i + 2; return R;
-                }
-                if (ndxip1 > 2 * mu_ && ext) {
-                    eval_dd(M.r, xi, nullptr, t);
-                    ldiv(M.dx, M.r, false);
-                    ndxi = ndxip1;
-                    mu_ = ndxip1 = wnorm(M.dx, M.w, nn);
-                } else if (ndxip1 > 2 * mu_ || accurate_mu) {
-                    eval_f64(M.r, nullptr, xi, t);
-                    ldiv(M.dx, M.r, false);
-                    mu_ = wnorm(M.dx, M.w, nn);
-                } else mu_ = ndxip1;
-                if (i == 0) {
-                    double ob = 2 * ndxi / (ndxip1 * ndxip1);
-                    if (ob < R.omega) R.omega = ob; else R.omega *= 0.25;
-                }
-                R.code = NEWT_CONVERGED; R.accuracy = mu_; R.iters = i + 2; return R;
+                R.mu_low = wnorm(M.dx);
+                eval_dd(M.r, xi, nullptr, t);
             }
-            ndxim1 = ndxi;
-            if (i >= 1) abar *= abar;
+            ldiv(M.dx, M.r, !final);
+            if (ext) iterative_refinement(M.dx, M.r, true, 3, abar * abar);
+            const double nd = wnorm(M.dx);
+            if (!final) {
+                ndxi = nd;
+                if (ndxi != ndxi) { R.code = NEWT_SINGULARITY; R.accuracy = ndxi; R.iters = i + 1; return R; }
+                axmy(xi, xi, M.dx);
+                if (i == 0) R.norm_dx0 = ndxi;
+                if (i == 1) R.omega = 2 * ndxi / (ndxim1 * ndxim1);
+                if (i >= 1) R.theta = ndxi / ndxim1;
+                if ((i >= 1 && R.theta > abar) || (i == 0 && !first_correction && 0.125 * R.norm_dx0 * R.omega > h_a)) {
+                    R.code = NEWT_TERMINATED; R.accuracy = ndxi; R.iters = i + 1; return R;
+                }
+                if (R.omega * ndxi * ndxi < 2 * mu_ * sqrt(1 - 2 * h_a)) { final = true; continue; }
+                if (i == 10) { R.code = NEWT_MAX_ITERS; R.accuracy = mu_; R.iters = 11; return R; }
+                ndxim1 = ndxi;
+                if (i >= 1) abar *= abar;
+                ++i;
+                continue;
+            }
+            axmy(xi, xi, M.dx);
+            double ndxip1 = nd;
+            if (ndxip1 != ndxip1) { R.code = NEWT_SINGULARITY; R.accuracy = ndxip1; R.iters = i + 1; return R; }
+            if (ndxip1 > sqrt(ndxi)) {
+                R.theta = ndxip1 / ndxi; R.code = NEWT_TERMINATED; R.accuracy = ndxip1; R.iters = i + 2; return R;
+            }
+            if (ndxip1 > 2 * mu_ && ext) {
+                eval_dd(M.r, xi, nullptr, t);
+                ldiv(M.dx, M.r, false);
+                ndxi = ndxip1;
+                mu_ = ndxip1 = wnorm(M.dx);
+            } else if (ndxip1 > 2 * mu_ || accurate_mu) {
+                eval_f64(M.r, nullptr, xi, t);
+                ldiv(M.dx, M.r, false);
+                mu_ = wnorm(M.dx);
+            } else mu_ = ndxip1;
+            if (i == 0) {
+                double ob = 2 * ndxi / (ndxip1 * ndxip1);
+                if (ob < R.omega) R.omega = ob; else R.omega *= 0.25;
+            }
+            R.code = NEWT_CONVERGED; R.accuracy = mu_; R.iters = i + 2; return R;
         }
-        R.code = NEWT_MAX_ITERS; R.accuracy = mu_; R.iters = 11; return R;
     }
     // init_newton!  newton_corrector.jl:207-286
     HC_HDN bool init_newton(cx t, bool ext, double& omega_out, double& mu_out) {
@@ -740,22 +922,23 @@ struct Path {
         if (ext) eval_dd(M.r, M.x, nullptr, t);
         updated();
         ldiv(M.dx, M.r, true);
-        double v = wnorm(M.dx, M.w, nn) + HC_EPS;
+        double v = wnorm(M.dx) + HC_EPS;
         bool valid = false;
         omega_out = mu_out = HC_NAN;
         double e = sqrt(v);
         for (int k = 1; k <= 3; ++k) {
-            for (int i = 0; i < nn; ++i) M.xbar[i] = M.x[i] + mk(e * M.w[i]);
+            HC_PAR(i, nn) M.xbar[i] = M.x[i] + mk(e * M.w[i]);
+            g.sync();
             eval_f64(M.r, &M.A, M.xbar, t);
             if (ext) eval_dd(M.r, M.xbar, nullptr, t);
             updated();
             ldiv(M.dx, M.r, true);
-            for (int i = 0; i < nn; ++i) M.xbar[i] = M.xbar[i] - M.dx[i];
-            double nd0 = wnorm(M.dx, M.w, nn);
+            axmy(M.xbar, M.xbar, M.dx);
+            double nd0 = wnorm(M.dx);
             if (ext) eval_dd(M.r, M.xbar, nullptr, t); else eval_f64(M.r, nullptr, M.xbar, t);
             ldiv(M.dx, M.r, true);
-            for (int i = 0; i < nn; ++i) M.xbar[i] = M.xbar[i] - M.dx[i];
-            double nd1 = wnorm(M.dx, M.w, nn) + HC_EPS;
+            axmy(M.xbar, M.xbar, M.dx);
+            double nd1 = wnorm(M.dx) + HC_EPS;
             if (nd1 < a * nd0) {
                 omega_out = 2 * nd1 / (nd0 * nd0);
                 mu_out = nd1;
@@ -782,7 +965,7 @@ struct Path {
         double ds = nanmin(ds1, ds2);
         return jmin(jmin(ds, O->max_step_size), O->max_initial_step_size);
     }
-    HC_HD void update_stepsize(const NewtonResult& R) {  // tracker.jl:541-588
+    HC_HDN void update_stepsize(const NewtonResult& R) {  // tracker.jl:541-588
         double a = O->beta_a * O->a;
         double om = clampd(omega + 2 * (omega - omega_prev), omega, 8 * omega);
         double ds;
@@ -807,7 +990,7 @@ struct Path {
         }
         st_propose(ds);
     }
-    HC_HD void check_terminated() {  // tracker.jl:591-619
+    HC_HDN void check_terminated() {  // tracker.jl:591-619
         double tol_acc = HC_INF;
         if (extended_prec || !O->extended_precision) {
             double a = O->a;
@@ -822,37 +1005,46 @@ struct Path {
         else if (min_rel_step_size > 0 && !(tp.re == st_target.re && tp.im == st_target.im) && cabs(tp - t) < cabs(t) * min_rel_step_size)
             code = TC_terminated_step_size_too_small;
     }
-    // rank(J; rtol = 1e-14) < n ?  (tracker.jl:711-737).  One-sided Jacobi on the columns of LU (scratch).
+    // rank(J; rtol = 1e-14) < n ?  (tracker.jl:711-737).  One-sided Jacobi on the columns of LU (scratch);
+    // only reached for invalid start values, so lane 0 does it alone.
     HC_HDN bool jacobian_rank_deficient() {
         const int nn = n;
-        CV V = M.LU;
-        for (int i = 0; i < nn * nn; ++i) { V[i] = M.A[i]; if (cisnan(M.A[i])) return false; }
-        for (int sweep = 0; sweep < 60; ++sweep) {
-            double off = 0;
-            for (int p = 0; p < nn; ++p)
-                for (int q = p + 1; q < nn; ++q) {
-                    double app = 0, aqq = 0; cx apq = mk(0.0);
-                    for (int i = 0; i < nn; ++i) { cx vp = V[p * nn + i], vq = V[q * nn + i]; app += abs2(vp); aqq += abs2(vq); apq = cfma(conj(vp), vq, apq); }
-                    double g = hypot(apq.re, apq.im);
-                    if (g <= 1e-300 || g <= 1e-17 * sqrt(app * aqq)) continue;
-                    off = fmax(off, g / sqrt(app * aqq));
-                    cx ph = apq / g;
-                    double zeta = (aqq - app) / (2 * g);
-                    double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
-                    double c = 1 / sqrt(1 + tt * tt), s = c * tt;
-                    for (int i = 0; i < nn; ++i) {
-                        cx vp = V[p * nn + i], vq = V[q * nn + i] * conj(ph);
-                        V[p * nn + i] = c * vp - s * vq;
-                        V[q * nn + i] = (s * vp + c * vq) * ph;
-                    }
+        int deficient = 0;
+        if (g.lane == 0) {
+            CV V = M.LU;
+            bool has_nan = false;
+            for (int i = 0; i < nn * nn; ++i) { V[i] = M.A[i]; has_nan = has_nan || cisnan(M.A[i]); }
+            if (!has_nan) {
+                for (int sweep = 0; sweep < 60; ++sweep) {
+                    double off = 0;
+                    for (int p = 0; p < nn; ++p)
+                        for (int q = p + 1; q < nn; ++q) {
+                            double app = 0, aqq = 0; cx apq = mk(0.0);
+                            for (int i = 0; i < nn; ++i) { cx vp = V[p * nn + i], vq = V[q * nn + i]; app += abs2(vp); aqq += abs2(vq); apq = cfma(conj(vp), vq, apq); }
+                            double gg = hypot(apq.re, apq.im);
+                            if (gg <= 1e-300 || gg <= 1e-17 * sqrt(app * aqq)) continue;
+                            off = fmax(off, gg / sqrt(app * aqq));
+                            cx ph = apq / gg;
+                            double zeta = (aqq - app) / (2 * gg);
+                            double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+                            double c = 1 / sqrt(1 + tt * tt), s = c * tt;
+                            for (int i = 0; i < nn; ++i) {
+                                cx vp = V[p * nn + i], vq = V[q * nn + i] * conj(ph);
+                                V[p * nn + i] = c * vp - s * vq;
+                                V[q * nn + i] = (s * vp + c * vq) * ph;
+                            }
+                        }
+                    if (off < 1e-15) break;
                 }
-            if (off < 1e-15) break;
+                double smax = 0;
+                for (int p = 0; p < nn; ++p) { double s2 = 0; for (int i = 0; i < nn; ++i) s2 += abs2(V[p * nn + i]); smax = fmax(smax, sqrt(s2)); }
+                int r = 0;
+                for (int p = 0; p < nn; ++p) { double s2 = 0; for (int i = 0; i < nn; ++i) s2 += abs2(V[p * nn + i]); if (sqrt(s2) > 1e-14 * smax) ++r; }
+                deficient = r < nn;
+            }
         }
-        double smax = 0;
-        for (int p = 0; p < nn; ++p) { double s2 = 0; for (int i = 0; i < nn; ++i) s2 += abs2(V[p * nn + i]); smax = fmax(smax, sqrt(s2)); }
-        int r = 0;
-        for (int p = 0; p < nn; ++p) { double s2 = 0; for (int i = 0; i < nn; ++i) s2 += abs2(V[p * nn + i]); if (sqrt(s2) > 1e-14 * smax) ++r; }
-        return r < nn;
+        g.sync();
+        return g.bcast(deficient, 0) != 0;
     }
 
     // init!(tracker, x1, t1, t0; omega, mu, tau, max_initial_step_size, keep_steps, extended_precision)
@@ -916,11 +1108,11 @@ struct Path {
         const int nn = n;
         double m_ = accuracy;
         double mb = ext_refinement_step(M.xbar, M.x, st_t(), false);
-        if (mb < m_) { for (int i = 0; i < nn; ++i) M.x[i] = M.xbar[i]; m_ = mb; }
+        if (mb < m_) { vcopy(M.x, M.xbar, nn); m_ = mb; }
         int k = 1;
         while (m_ > min_tol && k <= nsteps) {
             mb = ext_refinement_step(M.xbar, M.x, st_t(), true);
-            if (mb < m_) { for (int i = 0; i < nn; ++i) M.x[i] = M.xbar[i]; m_ = mb; }
+            if (mb < m_) { vcopy(M.x, M.xbar, nn); m_ = mb; }
             k += 1;
         }
         return m_;
@@ -933,7 +1125,7 @@ struct Path {
         norm_update(M.xhat);
         NewtonResult R = newton(M.xhat, tp, mu, omega, extended_prec, false, accepted_steps == 0);
         if (R.code == NEWT_CONVERGED) {
-            for (int i = 0; i < nn; ++i) M.x[i] = M.xbar[i];
+            vcopy(M.x, M.xbar, nn);
             ds_prev = st_ds();
             st_s = st_sp;
             accuracy = R.accuracy;

@@ -1,0 +1,254 @@
+// Device-side ModelKit tape: levelised micro-op format and the three cooperative interpreters
+// (ComplexF64, ComplexDF64, truncated Taylor series of order K <= 4).
+//
+// The host (hc_lower.h) lowers the reference's InstructionSequence into micro-ops of a handful of
+// arithmetic classes, puts them into dependency levels and re-allocates the tape slots, so that
+// the G lanes that track one path execute the independent instructions of a level together:
+// lane l runs instructions l, l + G, ... of the level, then the group synchronises.  The working
+// tape of the path (constants, parameters, t, variables, registers) lives in shared memory.
+//
+// Replaces (reference file:line):
+//   src/model_kit/instruction_interpreter.jl:136-192, 252-332  execute!/execute_instructions!
+//   src/model_kit/instruction_interpreter.jl:335-491           execute_taylor!
+//   src/model_kit/taylor.jl:607-878                            taylor_op_*
+//   src/model_kit/operations.jl:5-49, 184-248                  OpType, op_*
+#pragma once
+#include "hc_coop.h"
+
+namespace hc {
+
+enum Op : int {  // reference OpType, declaration order of src/model_kit/operations.jl:5-49
+    OP_STOP = 0, OP_CB, OP_ACOS, OP_ASIN, OP_COS, OP_COSH, OP_EXP, OP_INV, OP_INV_NOT_ZERO,
+    OP_INVSQR, OP_NEG, OP_SIN, OP_SINH, OP_SQR, OP_SQRT, OP_TAN, OP_TANH, OP_IDENTITY,
+    OP_ADD, OP_DIV, OP_MUL, OP_SUB, OP_POW_INT, OP_POW,
+    OP_ADD3, OP_MUL3, OP_MULADD, OP_MULSUB, OP_SUBMUL,
+    OP_ADD4, OP_MUL4, OP_MULMULADD, OP_MULMULSUB
+};
+
+// micro-op classes: every reference op is a short sequence of these
+enum MClass : int {
+    MC_MM = 0,    // r = s1 a*b + s2 c*d
+    MC_MA = 1,    // r = s1 a*b + s2 c
+    MC_M = 2,     // r = s1 a*b
+    MC_AA = 3,    // r = s1 a + s2 c
+    MC_A = 4,     // r = s1 a
+    MC_INV = 5,   // r = 1 / a            (inv_fast)
+    MC_DIV = 6,   // r = a / b            (div_fast)
+    MC_INVNZ = 7  // r = a == 0 ? a : 1/a (op_inv_not_zero)
+};
+
+struct alignas(16) MOp {  // 16 B, 0-based physical tape slots (< 2^16)
+    uint32_t w0;  // out | cls << 16 | neg1 << 19 | neg2 << 20 | pair << 21 (independent of the next op)
+    uint32_t w1;  // a | b << 16
+    uint32_t w2;  // c | d << 16
+    uint32_t pad;
+};
+
+#if !defined(__CUDACC__)
+struct int2 { int x, y; };
+#endif
+
+struct DevProgram {
+    const MOp* ops;          // sorted by level
+    const int* level_end;    // cumulative op count at the end of each level
+    int n_levels, n_ops;
+    const cx* consts; int C; // tape slots [0, C)
+    int param_off, P;        // first parameter slot
+    int t_slot;              // -1 = none
+    int var_off, n;
+    int out_dim, W;          // W = number of tape slots (inputs + registers)
+    const int2* u_assign; int nu;  // (i, slot) 0-based
+    const int2* U_assign; int nU;  // (j, slot) 0-based, j column-major over (out_dim, n)
+};
+
+// ------------------------------------------------------------------ vector views
+// S = false: contiguous (the path's shared-memory slab, or the host in HC_HOST_SIM).
+// S = true : lane-interleaved global memory, element i of lane l at base[i * stride + l], so that
+//            a warp whose 32 lanes track 32 paths (G = 1) touches one coalesced 512 B segment.
+template <class T, bool S> struct SV;
+template <class T>
+struct SV<T, false> {
+    T* p;
+    HC_HD T& operator[](int i) const { return p[i]; }
+    HC_HD SV at(int off) const { SV r; r.p = p + off; return r; }
+};
+template <class T>
+struct SV<T, true> {
+    T* p;
+    int s;
+    // 32-bit index arithmetic (rows * lanes < 2^31) and a global-address-space hint: without them
+    // every access costs a 64-bit multiply and a generic LD/ST
+    HC_HD T& operator[](int i) const {
+#if defined(__CUDA_ARCH__)
+        __builtin_assume(__isGlobal(p));
+#endif
+        return p[(unsigned)i * (unsigned)s];
+    }
+    HC_HD SV at(int off) const { SV r; r.p = p + (unsigned)off * (unsigned)s; r.s = s; return r; }
+};
+
+template <bool S>
+struct DV {  // vector of ComplexDF64: element i = cx 2i (re.hi, re.lo) and 2i+1 (im.hi, im.lo)
+    SV<cx, S> v;
+    HC_HD cdd get(int i) const { cx a = v[2 * i], b = v[2 * i + 1]; return mkcdd(mkdd(a.re, a.im), mkdd(b.re, b.im)); }
+    HC_HD void set(int i, cdd x) const { v[2 * i] = mk(x.re.hi, x.re.lo); v[2 * i + 1] = mk(x.im.hi, x.im.lo); }
+};
+
+// ------------------------------------------------------------------ scalar micro-ops
+HC_HD cx mneg(cx a, bool s) { return s ? -a : a; }
+HC_HD cdd mneg(cdd a, bool s) { return s ? -a : a; }
+HC_HD cx mfma(cx a, cx b, cx c) { return cfma(a, b, c); }
+HC_HD cdd mfma(cdd a, cdd b, cdd c) { return a * b + c; }
+
+template <class TV> HC_HD cx tload(TV tape, int s, cx*) { return tape[s]; }
+template <class TV> HC_HD cdd tload(TV tape, int s, cdd*) { cx a = tape[2 * s], b = tape[2 * s + 1]; return mkcdd(mkdd(a.re, a.im), mkdd(b.re, b.im)); }
+template <class TV> HC_HD void tstore(TV tape, int s, cx v) { tape[s] = v; }
+template <class TV> HC_HD void tstore(TV tape, int s, cdd v) { tape[2 * s] = mk(v.re.hi, v.re.lo); tape[2 * s + 1] = mk(v.im.hi, v.im.lo); }
+
+template <class T, class TV>
+HC_HD T eval_mop(const MOp I, TV tape) {
+    const int cls = (I.w0 >> 16) & 7;
+    const bool n1 = (I.w0 >> 19) & 1, n2 = (I.w0 >> 20) & 1;
+    T* tag = nullptr;
+    T a = mneg(tload(tape, I.w1 & 0xffff, tag), n1), r;
+    switch (cls) {
+        case MC_MM: {
+            T b = tload(tape, I.w1 >> 16, tag), c = mneg(tload(tape, I.w2 & 0xffff, tag), n2), d = tload(tape, I.w2 >> 16, tag);
+            r = mfma(c, d, a * b);
+        } break;
+        case MC_MA: { T b = tload(tape, I.w1 >> 16, tag), c = mneg(tload(tape, I.w2 & 0xffff, tag), n2); r = mfma(a, b, c); } break;
+        case MC_M: { T b = tload(tape, I.w1 >> 16, tag); r = a * b; } break;
+        case MC_AA: { T c = mneg(tload(tape, I.w2 & 0xffff, tag), n2); r = a + c; } break;
+        case MC_A: r = a; break;
+        case MC_INV: r = cinv(a); break;
+        case MC_DIV: { T b = tload(tape, I.w1 >> 16, tag); r = cdiv(a, b); } break;
+        default: r = ciszero(a) ? a : cinv(a); break;
+    }
+    return r;
+}
+
+// runs the levelised tape; the inputs must already be in the tape and visible (group-synced)
+template <class T, int G, class TV>
+HC_HDN void run_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
+    int beg = 0;
+    for (int L = 0; L < P.n_levels; ++L) {
+        const int end = P.level_end[L];
+        if (G == 1) {  // thread-per-path: sequential program; flagged ops are independent of their successor
+            for (int i = beg; i < end; ++i) {
+                const MOp I = P.ops[i];
+                if (sizeof(T) == sizeof(cx) && ((I.w0 >> 21) & 1)) {  // 2-way ILP: both ops' loads are in flight together
+                    const MOp J = P.ops[++i];
+                    T r0 = eval_mop<T>(I, tape), r1 = eval_mop<T>(J, tape);
+                    tstore(tape, I.w0 & 0xffff, r0);
+                    tstore(tape, J.w0 & 0xffff, r1);
+                } else tstore(tape, I.w0 & 0xffff, eval_mop<T>(I, tape));
+            }
+        } else
+        // two independent micro-ops per lane and trip: their loads overlap (ops of a level never alias)
+        for (int i = beg + g.lane; i < end; i += 2 * G) {
+            const MOp I0 = P.ops[i];
+            if (i + G < end) {
+                const MOp I1 = P.ops[i + G];
+                T r0 = eval_mop<T>(I0, tape), r1 = eval_mop<T>(I1, tape);
+                tstore(tape, I0.w0 & 0xffff, r0);
+                tstore(tape, I1.w0 & 0xffff, r1);
+            } else tstore(tape, I0.w0 & 0xffff, eval_mop<T>(I0, tape));
+        }
+        g.sync();
+        beg = end;
+    }
+}
+
+// ------------------------------------------------------------------ Taylor micro-ops
+template <int K>
+struct Ser { cx c[K + 1]; };
+
+template <int K, class TV> HC_HD Ser<K> ser_load(TV tape, int s, bool neg) {
+    Ser<K> r;
+#pragma unroll
+    for (int k = 0; k <= K; ++k) r.c[k] = mneg(tape[s * (K + 1) + k], neg);
+    return r;
+}
+template <int K> HC_HD Ser<K> t_mul(const Ser<K>& x, const Ser<K>& y) {
+    Ser<K> r;
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+        cx c = x.c[0] * y.c[k];
+#pragma unroll
+        for (int j = 1; j <= k; ++j) c = cfma(x.c[j], y.c[k - j], c);
+        r.c[k] = c;
+    }
+    return r;
+}
+template <int K> HC_HD Ser<K> t_muladd(const Ser<K>& x, const Ser<K>& y, const Ser<K>& z) {
+    Ser<K> r;
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+        cx c = z.c[k];
+#pragma unroll
+        for (int j = 0; j <= k; ++j) c = cfma(x.c[j], y.c[k - j], c);
+        r.c[k] = c;
+    }
+    return r;
+}
+template <int K> HC_HD Ser<K> t_div(const Ser<K>& x, const Ser<K>& y) {  // taylor.jl:689-716
+    Ser<K> r;
+    cx yinv = cinv(y.c[0]);
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+        cx s = x.c[k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) s = cfnma(r.c[j], y.c[k - j], s);
+        r.c[k] = s * yinv;
+    }
+    return r;
+}
+template <int K> HC_HD Ser<K> t_one() {
+    Ser<K> r;
+#pragma unroll
+    for (int k = 0; k <= K; ++k) r.c[k] = mk(k == 0 ? 1.0 : 0.0);
+    return r;
+}
+
+template <int K, class TV>
+HC_HD void exec_mop_taylor(const MOp I, TV tape) {
+    const int out = I.w0 & 0xffff, cls = (I.w0 >> 16) & 7;
+    const bool n1 = (I.w0 >> 19) & 1, n2 = (I.w0 >> 20) & 1;
+    Ser<K> a = ser_load<K>(tape, I.w1 & 0xffff, n1), r;
+    switch (cls) {
+        case MC_MM: {
+            Ser<K> b = ser_load<K>(tape, I.w1 >> 16, false);
+            r = t_mul<K>(a, b);
+            Ser<K> c = ser_load<K>(tape, I.w2 & 0xffff, n2), d = ser_load<K>(tape, I.w2 >> 16, false);
+            r = t_muladd<K>(c, d, r);
+        } break;
+        case MC_MA: {
+            Ser<K> b = ser_load<K>(tape, I.w1 >> 16, false), c = ser_load<K>(tape, I.w2 & 0xffff, n2);
+            r = t_muladd<K>(a, b, c);
+        } break;
+        case MC_M: { Ser<K> b = ser_load<K>(tape, I.w1 >> 16, false); r = t_mul<K>(a, b); } break;
+        case MC_AA: {
+            Ser<K> c = ser_load<K>(tape, I.w2 & 0xffff, n2);
+#pragma unroll
+            for (int k = 0; k <= K; ++k) r.c[k] = a.c[k] + c.c[k];
+        } break;
+        case MC_A: r = a; break;
+        case MC_DIV: { Ser<K> b = ser_load<K>(tape, I.w1 >> 16, false); r = t_div<K>(a, b); } break;
+        default: r = t_div<K>(t_one<K>(), a); break;  // MC_INV, MC_INVNZ (taylor.jl: inv and inv_not_zero share the rule)
+    }
+#pragma unroll
+    for (int k = 0; k <= K; ++k) tape[out * (K + 1) + k] = r.c[k];
+}
+
+template <int K, int G, class TV>
+HC_HDN void run_taylor_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
+    int beg = 0;
+    for (int L = 0; L < P.n_levels; ++L) {
+        const int end = P.level_end[L];
+        for (int i = beg + g.lane; i < end; i += G) exec_mop_taylor<K>(P.ops[i], tape);
+        g.sync();
+        beg = end;
+    }
+}
+
+}  // namespace hc
