@@ -62,14 +62,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
-def make_workload(name, replicas):
+WORKLOADS = ("cyclic7_polyhedral", "katsura8", "cyclic7_td", "tritangents", "cyclooctane_td", "biochem_sweep")
+
+
+def make_workload(name, replicas, api=None):
+    """The BASELINE.json configs (hcb200.workloads); `replicas` multiplies the small ones so that one
+    B200 has enough independent paths (identical work distribution per replica)."""
     import hcb200
     from hcb200 import workloads
-    if name == "katsura8":
+    if name == "cyclic7_polyhedral":      # configs[1], the default: 924 mixed-volume paths per replica
+        return workloads.cyclic_polyhedral(7, replicas)
+    if name == "katsura8":                # configs[0]
         return workloads.katsura8(replicas)
     if name == "cyclic7_td":
         return workloads.cyclic7_total_degree(replicas)
-    raise SystemExit(f"unknown workload {name}")
+    if name == "tritangents":             # configs[2]: 110 592 paths
+        return workloads.tritangents_total_degree()
+    if name == "cyclooctane_td":          # configs[3] on the total-degree start system: 32 768 paths
+        return workloads.cyclooctane_total_degree()
+    if name == "biochem_sweep":           # configs[4]: `replicas` x 1024 parameter points per GPU
+        return workloads.biochem_sweep(api, replicas * 1024)
+    raise SystemExit(f"unknown workload {name}; choose from {WORKLOADS}")
 
 
 def cpu_baseline(w, budget_paths, threads, fast=True):
@@ -89,7 +102,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    w = make_workload(args.workload, args.replicas)
+    import pyoracle
+    w = make_workload(args.workload, args.replicas, pyoracle.load(fast=True))
     per_step = args.cpu_sample
     for _ in range(args.warmup):
         cpu_baseline(w, max(64, per_step // 8), threads)
@@ -114,8 +128,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="katsura8")
-    ap.add_argument("--replicas", type=int, default=148, help="replicas of the config per GPU (weak scaling)")
+    ap.add_argument("--workload", default="cyclic7_polyhedral", choices=WORKLOADS)
+    ap.add_argument("--replicas", type=int, default=160, help="replicas of the config per GPU (weak scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="paths per step of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -136,7 +150,13 @@ def main():
     torch.cuda.set_device(local)
     api = lib.load(local)
     raw = api.raw
-    w = make_workload(args.workload, args.replicas)
+    # the job = `replicas x world` replicas of the config; this rank tracks its contiguous shard of
+    # the path index range (hcb200.sharding), no collective until the final reduction of the counts
+    from hcb200 import sharding
+    wg = make_workload(args.workload, args.replicas * (world if args.workload not in ("tritangents", "cyclooctane_td") else 1), api)
+    lo, hi = sharding.shard_range(wg.N, rank, world)
+    w = wg.slice(lo, hi)
+    w.expected = wg.expected
     handles = w.build(api)
     opts = api.default_options()
     dp = lambda a: a.ctypes.data_as(capi.c_double_p)
@@ -144,8 +164,13 @@ def main():
     # ---- device-resident arm (value): upload once, run K times
     starts = np.ascontiguousarray(w.starts)
     t1 = np.array([1.0, 0.0]); t0 = np.array([0.0, 0.0])
-    res_h = raw.hc_resident_create(handles["H"].handle, None, C.byref(opts), w.mode, w.N, dp(starts.view(np.float64)), dp(t1), dp(t0),
-                                   None, None, None, None, 0)
+    pq = np.ascontiguousarray(w.path_q).view(np.float64).reshape(-1) if w.path_q is not None else None
+    ci = np.ascontiguousarray(w.cell_index, dtype=np.int32) if w.cell_index is not None else None
+    cw = np.ascontiguousarray(w.cell_weights, dtype=np.float64) if w.cell_weights is not None else None
+    res_h = raw.hc_resident_create(handles["H"].handle, handles["Hcoeff"].handle if "Hcoeff" in handles else None, C.byref(opts), w.mode,
+                                   w.N, dp(starts.view(np.float64)), dp(t1), dp(t0), None, dp(pq) if pq is not None else None,
+                                   ci.ctypes.data_as(capi.c_int32_p) if ci is not None else None, dp(cw) if cw is not None else None,
+                                   cw.shape[0] if cw is not None else 0)
     if not res_h:
         raise SystemExit("hc_resident_create failed: " + raw.hc_last_error().decode())
     res_h = C.c_void_p(res_h)
@@ -179,7 +204,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s_max, wall_max = float(t[0]), float(t[1])
-    total_paths = w.N * world * args.steps
+    total_paths = wg.N * args.steps
     value = total_paths / dev_s_max
 
     # ---- end-to-end arm: host buffers through the public call
@@ -196,10 +221,16 @@ def main():
     tm = lib.timing()
     e2e = total_paths / float(te[0])
 
+    # ---- final reduction of the solution-class counts (the only cross-rank exchange of the job)
+    counts = sharding.class_counts(res)
+    ct = torch.tensor([counts[k] for k in sorted(counts)], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ct)
+    counts = {k: int(v) for k, v in zip(sorted(counts), ct.tolist())}
     if rank != 0:
         return
     # ---- roofline of the dominant (only) kernel
-    n_ok = int((res.return_code == 1).sum())
+    n_ok = counts["success"]
     fl = flops.batch_flops(w.costs, res.counters, res.accepted_steps, res.rejected_steps)
     peak_gflops = raw.hc_dfma_peak(200000)
     ach_tflops = fl / (np.mean(kernel_ms) * 1e-3) / 1e12
@@ -209,9 +240,12 @@ def main():
         "metric": "paths tracked/sec", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w.description, "paths_per_gpu_per_step": w.N, "parallelism": f"paths sharded over {world} GPU(s), no collective",
-                   "l2": f"per-lane state slabs {tm.slab_bytes / 2**20:.0f} MiB > 126 MiB L2; inputs are KBs",
-                   "grid": tm.grid, "block": tm.block, "success_paths": n_ok, "expected": w.expected},
+        "config": {"workload": wg.description, "paths_per_gpu_per_step": w.N,
+                   "parallelism": f"path index range sharded over {world} GPU(s), no collective on the hot path",
+                   "l2": (f"per-lane state slabs {tm.slab_bytes / 2**20:.0f} MiB > 126 MiB L2; inputs are KBs" if tm.lanes == 1 else
+                          f"path state in shared memory ({tm.slab_bytes} B per path); inputs are KBs"),
+                   "engine": "thread-per-path" if tm.lanes == 1 else f"{tm.lanes}-lane group per path",
+                   "grid": tm.grid, "block": tm.block, "success_paths": n_ok, "class_counts": counts, "expected": wg.expected},
         "e2e": {"value": e2e, "unit": "paths/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(tm.d2h_bytes)},
         "gpu_launches": args.steps,
         "clocks": clocks,

@@ -318,7 +318,7 @@ int engine_for(int n) {
         if (!strcmp(e, "group")) return 0;
         throw std::string("HC_B200_ENGINE must be tpp or group");
     }
-    return n <= env_int("HC_B200_TPP_MAX_N", 16) ? 1 : 0;
+    return n <= env_int("HC_B200_TPP_MAX_N", 14) ? 1 : 0;
 }
 
 Plan make_plan(const HomotopyH& H, long long N) {

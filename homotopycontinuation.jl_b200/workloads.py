@@ -38,6 +38,12 @@ class Workload:
                      None if self.cell_index is None else self.cell_index[:count], self.cell_weights, self.costs, {})
         return w
 
+    def slice(self, lo: int, hi: int) -> "Workload":
+        """Paths lo .. hi-1 (a shard of the batch; cell weights and homotopies are shared)."""
+        return Workload(self.name, self.description, self.n, self.starts[lo:hi], self.mode, self.build,
+                        None if self.path_q is None else self.path_q[lo:hi],
+                        None if self.cell_index is None else self.cell_index[lo:hi], self.cell_weights, self.costs, {})
+
     def track(self, api, handles, options=None, nthreads=1):
         if self.mode == 2:
             return capi.polyhedral_track_batch(api, handles["H"], handles["Hcoeff"], self.starts, self.cell_index,
@@ -87,17 +93,89 @@ def cyclic_polyhedral(n: int = 7, replicas: int = 1) -> Workload:
                     costs=flops.homotopy_costs(ps.F), expected={"success": len(S) * replicas})
 
 
-def biochem_sweep(points: int, seed: int = 6) -> Workload:
-    """BASELINE.json configs[4]: parameter homotopy sweep of bio-chemical network 1
-    (benchmarks/bio-chemical-rection-networks.jl:19-26); the generic start solutions come from one
-    total-degree solve at p1 and are replicated for every parameter point."""
-    raise NotImplementedError("needs start solutions: use biochem_sweep_from_starts")
+def tritangents_total_degree(limit: int | None = None) -> Workload:
+    """BASELINE.json configs[2]: tritangents (reference test/test_systems.jl:31-54) with a fixed seeded
+    real cubic (seed 3), total-degree homotopy, (2*2*3*4)^3 = 110 592 paths, 720 finite solutions."""
+    F = systems.tritangents()
+    c = np.random.default_rng(3).normal(size=20)
+    td = start_systems.total_degree(F, 0.4 + 1.3j, c)
+
+    def build(api):
+        hF, hG = api.system(td.F), api.system(td.G)
+        return {"H": api.homotopy(capi.H_STRAIGHT_LINE, hF, hG, gamma=td.gamma, G_params=td.scaling, F_params=c)}
+    S = td.start_solutions()
+    if limit is not None:
+        S = S[:limit]
+    return Workload("tritangents", f"tritangents total-degree homotopy, {len(S)} of 110592 paths", 12, S, 0, build,
+                    costs=flops.homotopy_costs(td.F, td.G), expected={"success": 720 if limit is None else None})
 
 
-def biochem_sweep_from_starts(starts: np.ndarray, p1: np.ndarray, points: int, seed: int = 6) -> Workload:
+def cyclooctane_parameters() -> np.ndarray:
+    """A0 (2 x 17, column-major) and b0 ~ CN(0, 1), seed 4 (benchmarks/cyclooctane.jl:22-25)."""
+    rng = np.random.default_rng(4)
+    return (rng.normal(size=36) + 1j * rng.normal(size=36)) / np.sqrt(2)
+
+
+def cyclooctane_total_degree(limit: int | None = None) -> Workload:
+    """BASELINE.json configs[3] on the total-degree start system: 2^15 = 32 768 paths, 1408 finite
+    solutions, the rest diverge (endgame at-infinity checks)."""
+    F = systems.cyclooctane()
+    p0 = cyclooctane_parameters()
+    td = start_systems.total_degree(F, 0.4 + 1.3j, p0)
+
+    def build(api):
+        hF, hG = api.system(td.F), api.system(td.G)
+        return {"H": api.homotopy(capi.H_STRAIGHT_LINE, hF, hG, gamma=td.gamma, G_params=td.scaling, F_params=p0)}
+    S = td.start_solutions()
+    if limit is not None:
+        S = S[:limit]
+    return Workload("cyclooctane_td", f"cyclooctane total-degree homotopy, {len(S)} of 32768 paths", 17, S, 0, build,
+                    costs=flops.homotopy_costs(td.F, td.G), expected={"success": 1408 if limit is None else None})
+
+
+def cyclooctane_polyhedral() -> Workload:
+    """BASELINE.json configs[3]: cyclooctane (benchmarks/cyclooctane.jl:4-27) on the polyhedral start system."""
+    ps = polyhedral.polyhedral(systems.cyclooctane(), target_parameters=cyclooctane_parameters(), seed_coeffs=14, seed_origin=15,
+                               seed_lifting=16, cache=os.path.join(_GOLDEN, "cyclooctane_cells.json"))
+    S, ci = ps.start_solutions()
+    cw = ps.cell_weights()
+
+    def build(api):
+        h = api.system(ps.F)
+        return {"H": api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs),
+                "Hcoeff": api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)}
+    return Workload("cyclooctane_polyhedral", f"cyclooctane polyhedral homotopy, {len(S)} mixed-volume paths", 17, S, 2, build,
+                    cell_index=ci, cell_weights=cw, costs=flops.homotopy_costs(ps.F), expected={"success": 1408})
+
+
+def biochem_generic_start(api, seed: int = 5):
+    """Generic parameters p1 ~ CN(0,1)^10 (seed 5) and the start solutions of bio-chemical network 1 at p1,
+    obtained by one total-degree solve on `api` (reference: solve(F; target_parameters = p1))."""
     F = systems.biochem1()
     rng = np.random.default_rng(seed)
-    q = systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * rng.normal(size=(points, 10)))
+    p1 = rng.normal(size=10) + 1j * rng.normal(size=10)
+    td = start_systems.total_degree(F, 0.4 + 1.3j, p1)
+    hF, hG = api.system(td.F), api.system(td.G)
+    H = api.homotopy(capi.H_STRAIGHT_LINE, hF, hG, gamma=td.gamma, G_params=td.scaling, F_params=p1)
+    r = H.track_batch(td.start_solutions())
+    ok = (r.return_code == 1) & (r.singular == 0)
+    return p1, r.solution[ok]
+
+
+def biochem_sweep(api, points: int, seed: int = 6, first: int = 0) -> Workload:
+    """BASELINE.json configs[4]: parameter homotopy sweep of bio-chemical network 1
+    (benchmarks/bio-chemical-rection-networks.jl:19-26): `points` target parameter vectors
+    q_j = p_vals * exp(0.5 z_j), z_j ~ N(0,1)^10 (seed 6, j = first .. first + points - 1), each
+    tracked from every generic start solution."""
+    p1, starts = biochem_generic_start(api)
+    return biochem_sweep_from_starts(starts, p1, points, seed, first)
+
+
+def biochem_sweep_from_starts(starts: np.ndarray, p1: np.ndarray, points: int, seed: int = 6, first: int = 0) -> Workload:
+    F = systems.biochem1()
+    rng = np.random.default_rng(seed)
+    z = rng.normal(size=(first + points, 10))[first:]       # the stream is indexed by parameter point: shards agree
+    q = systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * z)
     k = len(starts)
     S = np.repeat(starts[None], points, axis=0).reshape(-1, 3)
     Q = np.repeat(q[:, None, :], k, axis=1).reshape(-1, 10).astype(np.complex128)
