@@ -97,23 +97,28 @@ int engine_for(int n);
 // Lower the reference's 24-byte, 1-based Instruction stream (hc_lower.h) and upload it.
 void build_program(ProgramH& H, const hc_program_desc* d) {
 #ifdef HC_HOST_SIM
-    const int cap = env_int("HC_B200_ROUND_CAP", 0);
+    const bool tpp = true;
 #else
-    const int cap = engine_for(d->n_vars) == 1 ? 0 : env_int("HC_B200_ROUND_CAP", 2 * group_size_for(d->n_vars));
+    const bool tpp = engine_for(d->n_vars) != 0;
 #endif
-    H.low = lower_program(d, cap, env_int("HC_B200_PRIO_HEIGHT", 1) != 0, cap == 0 && env_int("HC_B200_TAPE_PAIRS", 0) != 0);
+    // thread per path: segment scheduling (window of tape-order ops) feeds the segment loops of hc_tape.h;
+    // lane groups: rounds of at most `cap` independent ops
+    const int cap = tpp ? 0 : env_int("HC_B200_ROUND_CAP", 2 * group_size_for(d->n_vars));
+    const int win = tpp ? env_int("HC_B200_SEG_WINDOW", 32) : 0;
+    H.low = lower_program(d, cap, env_int("HC_B200_PRIO_HEIGHT", 1) != 0, false, win);
     const LoweredProgram& L = H.low;
     DevProgram& P = H.dev;
     P.ops = to_dev(L.ops); P.level_end = to_dev(L.level_end); P.consts = to_dev(L.consts);
     P.u_assign = to_dev(L.u_assign); P.U_assign = to_dev(L.U_assign);
-    H.owned = {(void*)P.ops, (void*)P.level_end, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign};
+    P.fops = to_dev(L.fops); P.segs = to_dev(L.segs); P.n_segs = (int)L.segs.size(); P.n_fops = (int)L.fops.size();
+    H.owned = {(void*)P.ops, (void*)P.level_end, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign, (void*)P.fops, (void*)P.segs};
     P.n_levels = (int)L.level_end.size(); P.n_ops = (int)L.ops.size();
     P.C = (int)L.consts.size(); P.param_off = L.param_off; P.P = L.P; P.t_slot = L.t_slot;
     P.var_off = L.var_off; P.n = L.n; P.out_dim = L.out_dim; P.W = L.W;
     P.nu = (int)L.u_assign.size(); P.nU = (int)L.U_assign.size();
     if (getenv("HC_B200_VERBOSE"))
-        fprintf(stderr, "[hc_b200] program: %d reference instructions -> %d micro-ops in %d levels (max width %d), tape %d -> %d slots\n",
-                d->n_instructions, P.n_ops, P.n_levels, L.max_width, d->tape_space, P.W);
+        fprintf(stderr, "[hc_b200] program: %d reference instructions -> %d micro-ops in %d levels (max width %d), %d segments, tape %d -> %d slots\n",
+                d->n_instructions, P.n_ops, P.n_levels, L.max_width, P.n_segs, d->tape_space, P.W);
 }
 
 cx* cvec_dev(const double* p, int n, std::vector<void*>& owned) {
@@ -162,8 +167,13 @@ __device__ const T* stage_array(const T* src, int count, unsigned char*& cur) {
     cur += bytes;
     return dst;
 }
-__device__ void stage_program(DevProgram& P, unsigned char*& cur) {
-    P.ops = stage_array(P.ops, P.n_ops, cur);
+// fast = thread-per-path kernels: they interpret fops + segs; the packed ops (only read by the
+// DoubleDouble interpreter) stay in global memory
+__device__ void stage_program(DevProgram& P, unsigned char*& cur, bool fast = false) {
+    if (fast) {
+        P.fops = stage_array(P.fops, P.n_fops, cur);
+        P.segs = stage_array(P.segs, P.n_segs, cur);
+    } else P.ops = stage_array(P.ops, P.n_ops, cur);
     P.level_end = stage_array(P.level_end, P.n_levels, cur);
     P.consts = stage_array(P.consts, P.C, cur);
     P.u_assign = stage_array(P.u_assign, P.nu, cur);
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant_
         if (threadIdx.x == 0) sA.H = h;
         __syncthreads();
     }
-    Lane<G, false> L;
+    Lane<G, 0> L;
     L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem + A.stage_bytes + (size_t)(threadIdx.x / G) * A.slab_bytes,
@@ -207,29 +217,11 @@ __global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant_
     }
 }
 
-// Thread-per-path engine (small systems): every lane tracks its own path, the per-lane state lives
-// in lane-interleaved global memory (L2-resident, coalesced), the programs in shared memory.  Idle
-// lanes of a warp take new paths from the queue together, so that the start-up code of a path
-// (init_newton!, first predictor update) runs converged instead of stalling the warp once per lane.
-__global__ void __launch_bounds__(128) hc_track_tpp_kernel(const __grid_constant__ KArgs A) {
-    __shared__ KArgs sA;
-    if (threadIdx.x == 0) sA = A;
-    __syncthreads();
-    if (A.stage) {
-        DevHomotopy h = A.H;
-        unsigned char* cur = hc_smem;
-        stage_program(h.Fe, cur);
-        stage_program(h.Fj, cur);
-        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur); stage_program(h.Gj, cur); }
-        __syncthreads();
-        if (threadIdx.x == 0) sA.H = h;
-        __syncthreads();
-    }
-    Lane<1, true> L;
-    L.g.init();
-    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
-    const int T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, T, tid);
+// Main loop of the thread-per-path engines.  Idle lanes of a warp take new paths from the queue
+// together, so that the start-up code of a path (init_newton!, first predictor update) runs
+// converged instead of stalling the warp once per lane.
+template <class LaneT>
+__device__ __forceinline__ void tpp_loop(LaneT& L, const KArgs& A, const KArgs& sA) {
     L.phase = PH_IDLE;
     const long long N = sA.B.N;
     const unsigned lane = threadIdx.x & 31u;
@@ -252,11 +244,64 @@ __global__ void __launch_bounds__(128) hc_track_tpp_kernel(const __grid_constant
     }
 }
 
+// Thread-per-path engine (small systems): every lane tracks its own path, the per-lane state lives
+// in lane-interleaved global memory (L2-resident, coalesced), the programs in shared memory.  Idle
+// lanes of a warp take new paths from the queue together, so that the start-up code of a path
+// (init_newton!, first predictor update) runs converged instead of stalling the warp once per lane.
+__global__ void __launch_bounds__(128) hc_track_tpp_kernel(const __grid_constant__ KArgs A) {
+    __shared__ KArgs sA;
+    if (threadIdx.x == 0) sA = A;
+    __syncthreads();
+    if (A.stage) {
+        DevHomotopy h = A.H;
+        unsigned char* cur = hc_smem;
+        stage_program(h.Fe, cur, true);
+        stage_program(h.Fj, cur, true);
+        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur, true); stage_program(h.Gj, cur, true); }
+        __syncthreads();
+        if (threadIdx.x == 0) sA.H = h;
+        __syncthreads();
+    }
+    Lane<1, 1> L;
+    L.g.init();
+    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
+    const int T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, T, tid);
+    tpp_loop(L, A, sA);
+}
+
+// Thread-per-path engine with the lane state in LOCAL memory: the hardware interleaves the lanes of
+// a warp (a warp access to element i is one contiguous 512 B segment, as in the explicit slabs
+// above), element addresses are base + immediate (no per-access stride multiply), and L1 keeps
+// local lines write-back, so the state that a step re-reads stays on the SM.
+template <int SLAB>
+__global__ void __launch_bounds__(128) hc_track_tpl_kernel(const __grid_constant__ KArgs A) {
+    __shared__ KArgs sA;
+    if (threadIdx.x == 0) sA = A;
+    __syncthreads();
+    if (A.stage) {
+        DevHomotopy h = A.H;
+        unsigned char* cur = hc_smem;
+        stage_program(h.Fe, cur, true);
+        stage_program(h.Fj, cur, true);
+        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur, true); stage_program(h.Gj, cur, true); }
+        __syncthreads();
+        if (threadIdx.x == 0) sA.H = h;
+        __syncthreads();
+    }
+    __align__(16) unsigned char slab[SLAB];
+    Lane<1, 2> L;
+    L.g.init();
+    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, slab, slab + A.slab_bytes);
+    tpp_loop(L, A, sA);
+}
+
 // single-path operator-API hooks (one thread: valid for levelised and for sequential programs)
 __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, const cx* xlo, cx t, const double* tw, cx* u, cx* U) {
     __shared__ KArgs sA;
     sA = A;
-    Lane<1, false> L;
+    Lane<1, 0> L;
     L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = 0; L.kind = sA.H.kind;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold);
@@ -292,7 +337,7 @@ __global__ void hc_dfma_kernel(double* out, int iters) {
 
 // ------------------------------------------------------------------ launch planning
 struct Plan {
-    int engine;  // 0 = group per path (shared-memory state), 1 = thread per path (global state)
+    int engine;  // 0 = group per path (shared-memory state), 1 = thread per path (global slabs), 2 = thread per path (local memory)
     int grid, block, group, paths_per_block;
     size_t smem, slab, cold, stage_bytes;
     int stage;
@@ -300,12 +345,13 @@ struct Plan {
     long long lanes;
 };
 
-size_t program_stage_bytes(const ProgramH& P) {
+size_t program_stage_bytes(const ProgramH& P, bool fast) {
     auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    return r16((size_t)P.dev.n_ops * sizeof(MOp)) + r16((size_t)P.dev.n_levels * sizeof(int)) + r16((size_t)P.dev.C * sizeof(cx)) +
+    return (fast ? r16(P.low.fops.size() * sizeof(FOp)) + r16(P.low.segs.size() * sizeof(int2)) : r16((size_t)P.dev.n_ops * sizeof(MOp))) + r16((size_t)P.dev.n_levels * sizeof(int)) + r16((size_t)P.dev.C * sizeof(cx)) +
            r16((size_t)P.dev.nu * sizeof(int2)) + r16((size_t)P.dev.nU * sizeof(int2));
 }
 
+const size_t kLocalSlabMax = 48 * 1024;      // largest instantiated local-memory slab (hc_track_tpl_kernel)
 const size_t kSmemMax = 227 * 1024 - 2048;  // dynamic shared memory per CTA (the kernels keep ~1 KB static)
 
 // Which engine tracks a system of n variables: one thread per path keeps every lane busy but its
@@ -316,7 +362,8 @@ int engine_for(int n) {
     if (e) {
         if (!strcmp(e, "tpp")) return 1;
         if (!strcmp(e, "group")) return 0;
-        throw std::string("HC_B200_ENGINE must be tpp or group");
+        if (!strcmp(e, "local")) return 2;
+        throw std::string("HC_B200_ENGINE must be tpp, local or group");
     }
     return n <= env_int("HC_B200_TPP_MAX_N", 14) ? 1 : 0;
 }
@@ -324,7 +371,7 @@ int engine_for(int n) {
 Plan make_plan(const HomotopyH& H, long long N) {
     Plan p;
     memset(&p, 0, sizeof(p));
-    PathMem<false> dummy;
+    PathMem<0> dummy;
     SlabSizes ss = carve(dummy, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr);
     p.slab = ss.hot; p.cold = ss.cold;
 #ifndef HC_HOST_SIM
@@ -332,12 +379,14 @@ Plan make_plan(const HomotopyH& H, long long N) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     p.engine = engine_for(H.dev.n);
-    p.stage_bytes = program_stage_bytes(H.F->eval) + program_stage_bytes(H.F->jac);
-    if (H.dev.kind == H_STRAIGHT_LINE) p.stage_bytes += program_stage_bytes(H.G->eval) + program_stage_bytes(H.G->jac);
+    const bool fast = p.engine != 0;
+    p.stage_bytes = program_stage_bytes(H.F->eval, fast) + program_stage_bytes(H.F->jac, fast);
+    if (H.dev.kind == H_STRAIGHT_LINE) p.stage_bytes += program_stage_bytes(H.G->eval, fast) + program_stage_bytes(H.G->jac, fast);
     p.stage = (p.stage_bytes <= (size_t)env_int("HC_B200_STAGE_MAX", 64 * 1024)) && env_int("HC_B200_STAGE", 1);
     if (!p.stage) p.stage_bytes = 0;
-    if (p.engine == 1) {
-        PathMem<true> d2;
+    if (p.engine == 2 && p.slab + p.cold > kLocalSlabMax) p.engine = 1;
+    if (p.engine != 0) {
+        PathMem<1> d2;
         p.sz = carve(d2, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr, nullptr, 1, 0);
         p.group = 1;
         p.block = env_int("HC_B200_BLOCK", 64);
@@ -449,11 +498,24 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
         D.A.rslab = D.alloc<double>(pl.sz.nre * (size_t)pl.lanes);
         D.A.islab = D.alloc<int>(pl.sz.nint * (size_t)pl.lanes);
         D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
-    } else D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
+    } else if (pl.engine == 2) D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
+    else D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
     D.A.stage_bytes = (int)pl.stage_bytes;
 }
 
 #ifndef HC_HOST_SIM
+template <int SLAB>
+void launch_tpl(const DeviceBatch& D) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(hc_track_tpl_kernel<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+        size_t cur = 0;
+        CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        if (cur < (size_t)SLAB + 8192) CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)SLAB + 8192));
+        attr_set = true;
+    }
+    hc_track_tpl_kernel<SLAB><<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
+}
 template <int G>
 void launch_track(const DeviceBatch& D) {
     static bool attr_set = false;
@@ -469,7 +531,12 @@ double run_batch(DeviceBatch& D) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, 0));
-    if (D.plan.engine == 1) {
+    if (D.plan.engine == 2) {
+        const size_t need = D.plan.slab + D.plan.cold;
+        if (need <= 12 * 1024) launch_tpl<12 * 1024>(D);
+        else if (need <= 24 * 1024) launch_tpl<24 * 1024>(D);
+        else launch_tpl<48 * 1024>(D);
+    } else if (D.plan.engine == 1) {
         static bool attr_set = false;
         if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
         hc_track_tpp_kernel<<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
@@ -484,7 +551,7 @@ double run_batch(DeviceBatch& D) {
     return ms;
 #else
     std::vector<unsigned char> slab(D.plan.slab + 16);
-    Lane<1, false> L;
+    Lane<1, 0> L;
     L.g.init();
     L.H = &D.A.H; L.O = &D.A.O; L.n = D.A.H.n;
     unsigned char* base = (unsigned char*)(((uintptr_t)slab.data() + 15) & ~(uintptr_t)15);
@@ -548,7 +615,7 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
         g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
         g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
         g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.group;
-        g_timing.slab_bytes = D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.sz.ncx * 16 + D.plan.sz.nre * 8 + D.plan.sz.nint * 4) : (int64_t)D.plan.slab;
+        g_timing.slab_bytes = D.plan.engine == 2 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.slab + D.plan.cold) : D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.sz.ncx * 16 + D.plan.sz.nre * 8 + D.plan.sz.nint * 4) : (int64_t)D.plan.slab;
     } catch (const std::string& e) { return fail(e); }
     return 0;
 }
@@ -696,7 +763,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         hc_options o; hc_options_default(&o);
         KArgs A; memset(&A, 0, sizeof(A));
         A.H = H->dev; A.H.N = 1; A.O = to_dev_options(&o);
-        PathMem<false> dummy;
+        PathMem<0> dummy;
         A.H.tape_cx = 5 * (H->F->eval.dev.W > (H->G ? H->G->eval.dev.W : 0) ? H->F->eval.dev.W : H->G->eval.dev.W);  // order-4 series
         if (A.H.tape_cx < H->dev.tape_cx) A.H.tape_cx = H->dev.tape_cx;
         const SlabSizes ss = carve(dummy, n, P, A.H.tape_cx, nullptr, nullptr);
@@ -722,7 +789,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         CK(cudaDeviceSynchronize());
 #else
         std::vector<unsigned char> mem(slab + 16);
-        Lane<1, false> L;
+        Lane<1, 0> L;
         L.g.init();
         L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = 0; L.kind = A.H.kind;
         carve(L.M, n, P, A.H.tape_cx, (unsigned char*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15), A.cold);

@@ -58,7 +58,7 @@ struct BatchIn {
     const double* cell_weights;// polyhedral: ncells x P (unscaled s_ij, 0 on the cell's vertices)
 };
 
-template <int G, bool S>
+template <int G, int S>
 struct Lane : Path<G, S> {
     using B = Path<G, S>;
     using CV = typename B::CV; using RV = typename B::RV;

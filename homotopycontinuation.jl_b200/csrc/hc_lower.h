@@ -22,6 +22,8 @@ namespace hc {
 
 struct LoweredProgram {
     std::vector<MOp> ops;
+    std::vector<FOp> fops;        // thread-per-path fast format (hc_tape.h), same order as ops
+    std::vector<int2> segs;
     std::vector<int> level_end;
     std::vector<cx> consts;
     int param_off = 0, P = 0, t_slot = -1, var_off = 0, n = 0, out_dim = 0, W = 0;
@@ -39,7 +41,7 @@ inline bool supported_op(int op) {
     }
 }
 
-inline LoweredProgram lower_program(const hc_program_desc* d, int cap, bool prio_height = true, bool pair = false) {
+inline LoweredProgram lower_program(const hc_program_desc* d, int cap, bool prio_height = true, bool pair = false, int seg_window = 0) {
     struct VOp { int cls, n1, n2, a, b, c, d, out, level; };
     LoweredProgram R;
     const int C0 = d->n_constants, P = d->n_params, n = d->n_vars;
@@ -171,9 +173,52 @@ inline LoweredProgram lower_program(const hc_program_desc* d, int cap, bool prio
         std::vector<int> done_round((size_t)NV, 0);     // round in which a value becomes available (inputs: 0)
         std::vector<char> scheduled((size_t)nops, 0);
         int remaining = nops, round = 0;
-        std::vector<int> ready;
+        std::vector<int> ready, newly;
+        std::vector<int> wait_since((size_t)nops, 0);
         if (pair) cap = 2;  // thread-per-path engine with 2-way ILP: rounds of two independent ops, flattened below
-        if (cap <= 0) {  // sequential program (thread-per-path engine): original order, one op per allocation level
+        if (seg_window > 0) {
+            // Segment scheduling (thread-per-path engines): a round = the ready ops of ONE (class, sign) key
+            // among the next `seg_window` unscheduled ops in tape order -- long same-key runs for the
+            // segment loops, while the window keeps the live ranges (tape slots) close to the reference's.
+            std::vector<int> pending;
+            for (int i = 0; i < nops; ++i) pending.push_back(i);
+            while (!pending.empty()) {
+                ++round;
+                int cnt[32] = {0}, first[32];
+                const int lim = std::min<int>((int)pending.size(), seg_window);
+                std::vector<char> rdy((size_t)lim, 0);
+                for (int p = 0; p < lim; ++p) {
+                    const VOp& o = v[pending[p]];
+                    bool ok = true;
+                    for (int in : {o.a, o.b, o.c, o.d}) if (in >= Nin && done_round[in] == 0) ok = false;
+                    if (!ok) continue;
+                    rdy[p] = 1;
+                    const int key = o.cls | (o.n1 << 3) | (o.n2 << 4);
+                    if (cnt[key]++ == 0) first[key] = p;
+                }
+                int best = -1;
+                for (int k = 0; k < 32; ++k) if (cnt[k] && (best < 0 || cnt[k] > cnt[best] || (cnt[k] == cnt[best] && first[k] < first[best]))) best = k;
+                // the oldest pending op must not starve: take its key once it has waited for `seg_window` rounds
+                {
+                    const VOp& o = v[pending[0]];
+                    const int key0 = o.cls | (o.n1 << 3) | (o.n2 << 4);
+                    if (round - wait_since[pending[0]] >= 4) best = key0;
+                }
+                std::vector<int> rest;
+                for (int p = 0; p < (int)pending.size(); ++p) {
+                    const int i = pending[p];
+                    const VOp& o = v[i];
+                    if (p < lim && rdy[p] && (o.cls | (o.n1 << 3) | (o.n2 << 4)) == best) { v[i].level = round; level[o.out] = round; newly.push_back(o.out); }
+                    else rest.push_back(i);
+                }
+                for (int id : newly) done_round[id] = round;  // results become visible to the NEXT round
+                newly.clear();
+                for (int p = 0; p < (int)rest.size() && p < seg_window; ++p) if (wait_since[rest[p]] == 0) wait_since[rest[p]] = round;
+                pending.swap(rest);
+            }
+            remaining = 0;
+        }
+        if (cap <= 0 && seg_window <= 0) {  // sequential program (thread-per-path engine): original order, one op per allocation level
             for (int i = 0; i < nops; ++i) { v[i].level = i + 1; level[v[i].out] = i + 1; }
             remaining = 0;
         }
@@ -243,7 +288,7 @@ inline LoweredProgram lower_program(const hc_program_desc* d, int cap, bool prio
         int beg = 0;
         for (int e : R.level_end) { if (e - beg == 2) paired_first[beg] = 1; beg = e; }
     }
-    if (cap <= 0 || pair) { R.level_end.assign(1, nops); R.max_width = pair ? 2 : 1; }
+    if ((cap <= 0 && seg_window <= 0) || pair) { R.level_end.assign(1, nops); R.max_width = pair ? 2 : 1; }
     R.W = next_slot;
     if (R.W >= 65536) throw std::string("tape_space >= 65536 is not supported by the packed format");
     R.ops.resize(v.size());
@@ -257,6 +302,27 @@ inline LoweredProgram lower_program(const hc_program_desc* d, int cap, bool prio
         m.w2 = ph(o.c) | (ph(o.d) << 16);
         m.pad = 0;
         R.ops[i] = m;
+    }
+    // fast format + segment table: a segment = maximal run of ops of one level with the same key
+    {
+        for (size_t i = 0; i < order.size(); ++i) {
+            const VOp& o = v[order[i]];
+            const int key = o.cls | (o.n1 << 3) | (o.n2 << 4);
+            switch (key) {
+                case HC_KEY(MC_MM, 0, 0): case HC_KEY(MC_MM, 0, 1): case HC_KEY(MC_MA, 0, 0): case HC_KEY(MC_MA, 0, 1):
+                case HC_KEY(MC_MA, 1, 0): case HC_KEY(MC_M, 0, 0): case HC_KEY(MC_AA, 0, 0): case HC_KEY(MC_AA, 0, 1):
+                case HC_KEY(MC_A, 0, 0): case HC_KEY(MC_A, 1, 0): case HC_KEY(MC_INV, 0, 0): case HC_KEY(MC_DIV, 0, 0):
+                case HC_KEY(MC_INVNZ, 0, 0): break;
+                default: throw std::string("internal: micro-op (class, sign) pair without a segment loop");
+            }
+            auto ph = [&](int id) { return (uint32_t)(id >= 0 ? phys[id] : 0); };
+            FOp f; f.a = ph(o.a); f.b = ph(o.b); f.c = ph(o.c); f.out = (uint32_t)phys[o.out];
+            R.fops.push_back(f);
+            if (o.cls == MC_MM) { FOp g; g.a = ph(o.d); g.b = g.c = g.out = 0; R.fops.push_back(g); }
+            const bool new_level = i == 0 || v[order[i - 1]].level != o.level;  // (sequential programs: one op per level)
+            if (new_level || R.segs.back().x != key) { int2 sg; sg.x = key; sg.y = 0; R.segs.push_back(sg); }
+            R.segs.back().y += 1;
+        }
     }
     R.u_assign.resize(d->n_u); R.U_assign.resize(d->n_U);
     for (int i = 0; i < d->n_u; ++i) { R.u_assign[i].x = d->u_assign[2 * i] - 1; R.u_assign[i].y = phys[uv[i]]; }

@@ -47,14 +47,14 @@ struct DevHomotopy {
 };
 
 // ---------------------------------------------------------------- per-path memory
-template <bool S>
+template <int S>
 struct PathMem {
     using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
     CV x, xhat, xbar, tx, ptx1, ty1, pty1, xtemp, u, dx, r, A, LU, wr, wdx, work;
     CV sol, lastp, pred, ppred, samp, tape;
     DV<S> rbd;
     RV w, rs, rwork, egrs, egcs, ais, ait, aia, aic, val, tw;
-    IV ipiv;
+    IV ipiv, perm;
 };
 
 // Group-per-path layout.  Carves the path's vectors out of two 16-byte aligned slabs: the hot one
@@ -62,17 +62,20 @@ struct PathMem {
 // (endgame samples, valuation history, at-infinity bookkeeping, Hermite-mode predictor data, DD
 // accumulators) in a per-group scratch area in global memory.  With null bases it only counts.
 struct SlabSizes { size_t hot, cold; };
-HC_HD SlabSizes carve(PathMem<false>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold) {
+template <int S>
+HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold) {
+    static_assert(S == 0 || S == 2, "flat layouts only");
     size_t off = 0;
     unsigned char* base = hot;
-    auto C = [&](size_t k) { SV<cx, false> v; v.p = base ? (cx*)(base + off) : nullptr; off += 16 * k; return v; };
-    auto R = [&](size_t k) { SV<double, false> v; v.p = base ? (double*)(base + off) : nullptr; off += 8 * k; return v; };
+    auto C = [&](size_t k) { SV<cx, S> v; v.p = base ? (cx*)(base + off) : nullptr; off += 16 * k; return v; };
+    auto R = [&](size_t k) { SV<double, S> v; v.p = base ? (double*)(base + off) : nullptr; off += 8 * k; return v; };
     M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n);
     M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
     M.wr = C(n); M.wdx = C(n); M.work = C(n);
     M.tape = C((size_t)tape_cx);
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.tw = R(P > 0 ? P : 1);
     M.ipiv.p = base ? (int*)(base + off) : nullptr; off += 4 * (size_t)n;
+    M.perm.p = base ? (int*)(base + off) : nullptr; off += 4 * (size_t)n;
     SlabSizes s;
     s.hot = (off + 15) & ~(size_t)15;
     off = 0; base = cold;
@@ -87,10 +90,10 @@ HC_HD SlabSizes carve(PathMem<false>& M, int n, int P, int tape_cx, unsigned cha
 // Thread-per-path layout: three lane-interleaved slabs in global memory (element i of lane l at
 // base[i * stride + l]).  With null bases it only counts elements per lane.
 struct MemSizes { size_t ncx, nre, nint; };
-HC_HD MemSizes carve(PathMem<true>& M, int n, int P, int tape_cx, cx* cb, double* rb, int* ib, int stride, int lane) {
+HC_HD MemSizes carve(PathMem<1>& M, int n, int P, int tape_cx, cx* cb, double* rb, int* ib, int stride, int lane) {
     size_t oc = 0, orr = 0;
-    auto C = [&](size_t k) { SV<cx, true> v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += k; return v; };
-    auto R = [&](size_t k) { SV<double, true> v; v.p = rb ? rb + orr * (size_t)stride + lane : nullptr; v.s = stride; orr += k; return v; };
+    auto C = [&](size_t k) { SV<cx, 1> v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += k; return v; };
+    auto R = [&](size_t k) { SV<double, 1> v; v.p = rb ? rb + orr * (size_t)stride + lane : nullptr; v.s = stride; orr += k; return v; };
     M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n); M.ptx1 = C(2 * n); M.ty1 = C(2 * n); M.pty1 = C(2 * n);
     M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
     M.wr = C(n); M.wdx = C(n); M.work = C(n);
@@ -100,7 +103,8 @@ HC_HD MemSizes carve(PathMem<true>& M, int n, int P, int tape_cx, cx* cb, double
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.egrs = R(n); M.egcs = R(n);
     M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n); M.tw = R(P > 0 ? P : 1);
     M.ipiv.p = ib ? ib + lane : nullptr; M.ipiv.s = stride;
-    MemSizes s; s.ncx = oc; s.nre = orr; s.nint = (size_t)n;
+    M.perm.p = ib ? ib + (size_t)n * (size_t)stride + lane : nullptr; M.perm.s = stride;
+    MemSizes s; s.ncx = oc; s.nre = orr; s.nint = 2 * (size_t)n;
     return s;
 }
 
@@ -127,7 +131,7 @@ HC_HD cx t_to_s_plane(cx t, int m) {  // predictor.jl:338-351
     return mk(rr * cos(th / m), rr * sin(th / m));
 }
 
-template <int G, bool S>
+template <int G, int S>
 struct Path {
     using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
     Grp<G> g;
@@ -281,6 +285,13 @@ struct Path {
         g.sync();
     }
 
+    // thread-per-path engines run the segmented interpreters, lane groups the levelised ones
+    HC_HD void run_f64(const DevProgram& P) {
+        if (G == 1) run_tape_seg(P, M.tape); else run_tape<cx, G>(P, M.tape, g);
+    }
+    template <int K> HC_HD void run_taylor(const DevProgram& P) {
+        if (G == 1) run_taylor_tape_seg<K>(P, M.tape); else run_taylor_tape<K, G>(P, M.tape, g);
+    }
     // u (and optionally the column-major Jacobian U) of H(x, t)
     HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
         const int nn = n;
@@ -295,12 +306,12 @@ struct Path {
             if (PF.nu != nn) HC_PAR(i, nn) u[i] = mk(0.0);
             if (jac && PF.nU != nn * nn) HC_PAR(i, nn * nn) (*U)[i] = mk(0.0);
             load_inputs<cx>(PF, x, nullptr, t, H->F_params);
-            run_tape<cx, G>(PF, tape, g);
+            run_f64(PF);
             extract<1>(u, tape, PF.u_assign, PF.nu, tt);
             if (jac) extract<1>(*U, tape, PF.U_assign, PF.nU, tt);
             g.sync();
             load_inputs<cx>(PG, x, nullptr, t, H->G_params);
-            run_tape<cx, G>(PG, tape, g);
+            run_f64(PG);
             extract<2>(u, tape, PG.u_assign, PG.nu, ts);
             if (jac) extract<2>(*U, tape, PG.U_assign, PG.nU, ts);
             g.sync();
@@ -309,7 +320,7 @@ struct Path {
             if (PF.nu != nn) HC_PAR(i, nn) u[i] = mk(0.0);
             if (jac && PF.nU != nn * nn) HC_PAR(i, nn * nn) (*U)[i] = mk(0.0);
             load_inputs<cx>(PF, x, nullptr, t, nullptr);
-            run_tape<cx, G>(PF, tape, g);
+            run_f64(PF);
             extract<0>(u, tape, PF.u_assign, PF.nu, mk(0.0));
             if (jac) extract<0>(*U, tape, PF.U_assign, PF.nU, mk(0.0));
             g.sync();
@@ -383,14 +394,14 @@ struct Path {
         HC_PAR(i, n) u[i] = mk(0.0);
         if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:130-154
             taylor_inputs<K>(H->Ge, tx, t, H->G_params);
-            run_taylor_tape<K, G>(H->Ge, tape, g);
+            run_taylor<K>(H->Ge);
             HC_PAR(k, H->Ge.nu) {
                 int2 a = H->Ge.u_assign[k];
                 u[a.x] = H->gamma * (tape[a.y * (K + 1) + K - 1] + t * tape[a.y * (K + 1) + K]);
             }
             g.sync();
             taylor_inputs<K>(H->Fe, tx, t, H->F_params);
-            run_taylor_tape<K, G>(H->Fe, tape, g);
+            run_taylor<K>(H->Fe);
             HC_PAR(k, H->Fe.nu) {
                 int2 a = H->Fe.u_assign[k];
                 u[a.x] = u[a.x] + ((mk(1.0) - t) * tape[a.y * (K + 1) + K] - tape[a.y * (K + 1) + K - 1]);
@@ -398,7 +409,7 @@ struct Path {
             g.sync();
         } else {  // parameter / coefficient / toric: parameters are series in lambda
             taylor_inputs<K>(H->Fe, tx, t, nullptr);
-            run_taylor_tape<K, G>(H->Fe, tape, g);
+            run_taylor<K>(H->Fe);
             HC_PAR(k, H->Fe.nu) { int2 a = H->Fe.u_assign[k]; u[a.x] = tape[a.y * (K + 1) + K]; }
             g.sync();
         }
@@ -477,6 +488,96 @@ struct Path {
             g.sync();
         }
     }
+    // ---- thread-per-path (G == 1) variants for n <= HC_REG_LU_MAX with the active column / the
+    // right-hand side in REGISTERS (N is a compile-time size, every loop fully unrolled).
+    // Left-looking (jki) order: column j is loaded once (fused with the A -> LU copy and the Skeel
+    // row scaling of lu_prepare), receives the updates of the finished columns k < j from memory
+    // -- loads that no longer sit on the dependency chain, so they overlap -- and is stored once:
+    // n^3/3 loads + n^2 stores instead of 2n^3/3 loads + n^3/3 stores.  Every element still sees
+    // its updates in increasing k with the same cfnma, so LU, ipiv and the solutions are bit-identical
+    // to lu_prepare + lu_factor / lu_solve above (linear_algebra.jl:130-184, 310-316).
+    template <int N>
+    HC_HDN void lu_factor_reg(bool scale) {
+        CV A = M.A, LU = M.LU;
+        int rowof[N];  // original row that currently sits in position i
+#pragma unroll
+        for (int i = 0; i < N; ++i) rowof[i] = i;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            cx col[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) col[i] = A[j * N + rowof[i]];
+            if (scale) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) col[i] = col[i] * M.rs[rowof[i]];
+            }
+#pragma unroll
+            for (int k = 0; k < j; ++k) {
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) col[i] = cfnma(LU[k * N + i], col[k], col[i]);
+            }
+            double amax = -1.0; int kp = j;
+#pragma unroll
+            for (int i = j; i < N; ++i) { double v = abs2(col[i]); if (v > amax) { amax = v; kp = i; } }
+            M.ipiv[j] = kp;
+            if (amax > 0.0) {
+                if (kp != j) {
+                    const cx cj = col[j]; cx ck = cj;
+                    const int rj = rowof[j]; int rk = rj;
+#pragma unroll
+                    for (int i = j + 1; i < N; ++i) if (i == kp) { ck = col[i]; col[i] = cj; rk = rowof[i]; rowof[i] = rj; }
+                    col[j] = ck; rowof[j] = rk;
+#pragma unroll
+                    for (int k = 0; k < j; ++k) { cx t0 = LU[k * N + j], t1 = LU[k * N + kp]; LU[k * N + j] = t1; LU[k * N + kp] = t0; }
+                }
+                const cx pinv = cinv(col[j]);
+#pragma unroll
+                for (int i = j + 1; i < N; ++i) col[i] = col[i] * pinv;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) M.perm[i] = rowof[i];
+        factorized = true;
+        n_fact++;
+    }
+    // x = (LU)^-1 P (scaled ? rs .* b : b); x may alias b
+    template <int N>
+    HC_HDN void lu_solve_reg(CV x, CV b, bool scale) {
+        CV A = M.LU;
+        cx xr[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const int r = M.perm[i]; xr[i] = b[r]; if (scale) xr[i] = M.rs[r] * xr[i]; }
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) {
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) xr[i] = cfnma(A[j * N + i], xr[j], xr[i]);
+        }
+#pragma unroll
+        for (int j = N - 1; j >= 0; --j) {
+            xr[j] = cdiv(xr[j], A[j * N + j]);
+#pragma unroll
+            for (int i = 0; i < j; ++i) xr[i] = cfnma(A[j * N + i], xr[j], xr[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = xr[i];
+    }
+#define HC_REG_LU_MAX 12
+#define HC_REG_LU_DISPATCH(CALL)                                                                    \
+    switch (n) {                                                                                    \
+        case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; \
+        case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; case 9: CALL(9); break; \
+        case 10: CALL(10); break; case 11: CALL(11); break; default: CALL(12); break;               \
+    }
+    HC_HD bool use_reg_lu() const { return G == 1 && S != 1 && n >= 2 && n <= HC_REG_LU_MAX; }
+    HC_HD void factorize(bool scale) {
+        if (use_reg_lu()) {
+#define HC_CALL_(NN) lu_factor_reg<NN>(scale)
+            HC_REG_LU_DISPATCH(HC_CALL_)
+#undef HC_CALL_
+        } else { lu_prepare(scale); lu_factor(); }
+    }
     HC_HDN void lu_solve_adj(CV x) {  // :318-354 (in place)
         const int nn = n;
         CV A = M.LU;
@@ -526,7 +627,14 @@ struct Path {
         n_ldiv++;
         if (with_norm && !factorized) { skeel(M.rs, M.w, -30.0); scaled = true; }
         if (nn == 1) { cx v = cdiv(b[0], M.A[0]); g.sync(); if (g.lane == 0) x[0] = v; g.sync(); return; }
-        if (!factorized) { lu_prepare(scaled); lu_factor(); }
+        if (!factorized) factorize(scaled);
+        if (use_reg_lu()) {
+            const bool sc = scaled;
+#define HC_CALL_(NN) lu_solve_reg<NN>(x, b, sc)
+            HC_REG_LU_DISPATCH(HC_CALL_)
+#undef HC_CALL_
+            return;
+        }
         if (scaled) { HC_PAR(i, nn) x[i] = M.rs[i] * b[i]; g.sync(); }
         else if (x.p != b.p) vcopy(x, b, nn);
         lu_solve(x);
@@ -581,7 +689,7 @@ struct Path {
     // Hager/Higham estimator of |diag(d_r)^-1 A^-1 diag(d_l)^-1|_inf  :585-682
     HC_HDN double inverse_inf_norm_est(const RV* dl, const RV* dr) {
         const int nn = n;
-        if (!factorized) { lu_prepare(false); lu_factor(); }
+        if (!factorized) factorize(false);
         CV y = M.work; RV x = M.rwork;
         HC_PAR(i, nn) { double v = 1.0 / nn; if (dr) v /= (*dr)[i]; x[i] = v; y[i] = mk(v); }
         g.sync();

@@ -48,7 +48,14 @@ struct alignas(16) MOp {  // 16 B, 0-based physical tape slots (< 2^16)
 struct int2 { int x, y; };
 #endif
 
+// Thread-per-path fast format: 32-bit slot fields (no unpacking), the class + signs live in the
+// segment table.  An MC_MM op occupies two entries (the second one carries d in .a).
+struct alignas(16) FOp { uint32_t a, b, c, out; };
+
 struct DevProgram {
+    const FOp* fops;         // same order as ops
+    const int2* segs;        // runs of ops of one level with the same (class, signs): (key, count); key = cls | n1 << 3 | n2 << 4
+    int n_segs, n_fops;
     const MOp* ops;          // sorted by level
     const int* level_end;    // cumulative op count at the end of each level
     int n_levels, n_ops;
@@ -62,18 +69,30 @@ struct DevProgram {
 };
 
 // ------------------------------------------------------------------ vector views
-// S = false: contiguous (the path's shared-memory slab, or the host in HC_HOST_SIM).
-// S = true : lane-interleaved global memory, element i of lane l at base[i * stride + l], so that
+// S = 0: contiguous (the path's shared-memory slab, or the host in HC_HOST_SIM).
+// S = 1: lane-interleaved global memory, element i of lane l at base[i * stride + l], so that
 //            a warp whose 32 lanes track 32 paths (G = 1) touches one coalesced 512 B segment.
-template <class T, bool S> struct SV;
+template <class T, int S> struct SV;
 template <class T>
-struct SV<T, false> {
+struct SV<T, 0> {
     T* p;
     HC_HD T& operator[](int i) const { return p[i]; }
     HC_HD SV at(int off) const { SV r; r.p = p + off; return r; }
 };
 template <class T>
-struct SV<T, true> {
+struct SV<T, 2> {  // contiguous in the thread's LOCAL memory (G = 1): the hardware interleaves the lanes of a warp,
+                   // addresses need no stride arithmetic, and L1 caches local lines write-back
+    T* p;
+    HC_HD T& operator[](int i) const {
+#if defined(__CUDA_ARCH__) && defined(HC_LOCAL_ASSUME)  // off: nvcc 12.9 miscompiles the tracker with this hint (all paths fail at init)
+        __builtin_assume(__isLocal(p));
+#endif
+        return p[i];
+    }
+    HC_HD SV at(int off) const { SV r; r.p = p + off; return r; }
+};
+template <class T>
+struct SV<T, 1> {
     T* p;
     int s;
     // 32-bit index arithmetic (rows * lanes < 2^31) and a global-address-space hint: without them
@@ -87,7 +106,7 @@ struct SV<T, true> {
     HC_HD SV at(int off) const { SV r; r.p = p + (unsigned)off * (unsigned)s; r.s = s; return r; }
 };
 
-template <bool S>
+template <int S>
 struct DV {  // vector of ComplexDF64: element i = cx 2i (re.hi, re.lo) and 2i+1 (im.hi, im.lo)
     SV<cx, S> v;
     HC_HD cdd get(int i) const { cx a = v[2 * i], b = v[2 * i + 1]; return mkcdd(mkdd(a.re, a.im), mkdd(b.re, b.im)); }
@@ -156,6 +175,78 @@ HC_HDN void run_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
         }
         g.sync();
         beg = end;
+    }
+}
+
+// ------------------------------------------------------------------ segmented interpreter (G == 1)
+// One dispatch per segment instead of one per micro-op: the loop of a segment knows class and
+// signs at compile time (negations fold into the DFMA operand modifiers), reads the slot numbers
+// straight out of the 16-byte FOp and handles two independent ops per trip with all loads issued
+// before the first store (ops of a level never alias).  Results are bit-identical to eval_mop.
+#define HC_KEY(cls, n1, n2) ((cls) | ((n1) << 3) | ((n2) << 4))
+
+template <int CLS, bool N1, bool N2>
+HC_HD cx fop_eval(cx a, cx b, cx c, cx d) {
+    a = mneg(a, N1);
+    if (CLS == MC_MM) return mfma(mneg(c, N2), d, a * b);
+    if (CLS == MC_MA) return mfma(a, b, mneg(c, N2));
+    if (CLS == MC_M) return a * b;
+    if (CLS == MC_AA) return a + mneg(c, N2);
+    if (CLS == MC_A) return a;
+    if (CLS == MC_INV) return cinv(a);
+    if (CLS == MC_DIV) return cdiv(a, b);
+    return ciszero(a) ? a : cinv(a);
+}
+template <int CLS, bool N1, bool N2, class TV>
+HC_HD const FOp* run_segment(const FOp* op, int cnt, TV tape) {
+    constexpr bool useB = CLS == MC_MM || CLS == MC_MA || CLS == MC_M || CLS == MC_DIV;
+    constexpr bool useC = CLS == MC_MM || CLS == MC_MA || CLS == MC_AA;
+    constexpr int STEP = CLS == MC_MM ? 2 : 1;
+    const cx z = mk(0.0);
+    for (; cnt >= 2; cnt -= 2, op += 2 * STEP) {
+        const FOp I0 = op[0], I1 = op[STEP];
+        const cx a0 = tape[I0.a], a1 = tape[I1.a];
+        const cx b0 = useB ? tape[I0.b] : z, b1 = useB ? tape[I1.b] : z;
+        const cx c0 = useC ? tape[I0.c] : z, c1 = useC ? tape[I1.c] : z;
+        const cx d0 = CLS == MC_MM ? tape[op[1].a] : z, d1 = CLS == MC_MM ? tape[op[STEP + 1].a] : z;
+        const cx r0 = fop_eval<CLS, N1, N2>(a0, b0, c0, d0), r1 = fop_eval<CLS, N1, N2>(a1, b1, c1, d1);
+        tape[I0.out] = r0;
+        tape[I1.out] = r1;
+    }
+    if (cnt) {
+        const FOp I0 = op[0];
+        const cx a0 = tape[I0.a];
+        const cx b0 = useB ? tape[I0.b] : z, c0 = useC ? tape[I0.c] : z, d0 = CLS == MC_MM ? tape[op[1].a] : z;
+        tape[I0.out] = fop_eval<CLS, N1, N2>(a0, b0, c0, d0);
+        op += STEP;
+    }
+    return op;
+}
+#define HC_SEG_CASES(RUN)                                                                           \
+    case HC_KEY(MC_MM, 0, 0): RUN(MC_MM, false, false); break;                                       \
+    case HC_KEY(MC_MM, 0, 1): RUN(MC_MM, false, true); break;                                        \
+    case HC_KEY(MC_MA, 0, 0): RUN(MC_MA, false, false); break;                                       \
+    case HC_KEY(MC_MA, 0, 1): RUN(MC_MA, false, true); break;                                        \
+    case HC_KEY(MC_MA, 1, 0): RUN(MC_MA, true, false); break;                                        \
+    case HC_KEY(MC_M, 0, 0): RUN(MC_M, false, false); break;                                         \
+    case HC_KEY(MC_AA, 0, 0): RUN(MC_AA, false, false); break;                                       \
+    case HC_KEY(MC_AA, 0, 1): RUN(MC_AA, false, true); break;                                        \
+    case HC_KEY(MC_A, 0, 0): RUN(MC_A, false, false); break;                                         \
+    case HC_KEY(MC_A, 1, 0): RUN(MC_A, true, false); break;                                          \
+    case HC_KEY(MC_INV, 0, 0): RUN(MC_INV, false, false); break;                                     \
+    case HC_KEY(MC_DIV, 0, 0): RUN(MC_DIV, false, false); break;                                     \
+    default: RUN(MC_INVNZ, false, false); break;  // the lowering emits no other (class, sign) pair
+
+template <class TV>
+HC_HDN void run_tape_seg(const DevProgram& P, TV tape) {
+    const FOp* op = P.fops;
+    for (int s = 0; s < P.n_segs; ++s) {
+        const int2 sg = P.segs[s];
+        switch (sg.x) {
+#define HC_RUN_(CLS, N1, N2) op = run_segment<CLS, N1, N2>(op, sg.y, tape)
+            HC_SEG_CASES(HC_RUN_)
+#undef HC_RUN_
+        }
     }
 }
 
@@ -248,6 +339,49 @@ HC_HDN void run_taylor_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
         for (int i = beg + g.lane; i < end; i += G) exec_mop_taylor<K>(P.ops[i], tape);
         g.sync();
         beg = end;
+    }
+}
+
+// segmented Taylor interpreter (G == 1): class and signs are compile-time per segment
+template <int K, int CLS, bool N1, bool N2, class TV>
+HC_HD const FOp* run_taylor_segment(const FOp* op, int cnt, TV tape) {
+    constexpr int STEP = CLS == MC_MM ? 2 : 1;
+    for (; cnt > 0; --cnt, op += STEP) {
+        const FOp I = op[0];
+        Ser<K> a = ser_load<K>(tape, I.a, N1), r;
+        if (CLS == MC_MM) {
+            Ser<K> b = ser_load<K>(tape, I.b, false);
+            r = t_mul<K>(a, b);
+            Ser<K> c = ser_load<K>(tape, I.c, N2), d = ser_load<K>(tape, op[1].a, false);
+            r = t_muladd<K>(c, d, r);
+        } else if (CLS == MC_MA) {
+            Ser<K> b = ser_load<K>(tape, I.b, false), c = ser_load<K>(tape, I.c, N2);
+            r = t_muladd<K>(a, b, c);
+        } else if (CLS == MC_M) {
+            Ser<K> b = ser_load<K>(tape, I.b, false);
+            r = t_mul<K>(a, b);
+        } else if (CLS == MC_AA) {
+            Ser<K> c = ser_load<K>(tape, I.c, N2);
+#pragma unroll
+            for (int k = 0; k <= K; ++k) r.c[k] = a.c[k] + c.c[k];
+        } else if (CLS == MC_A) r = a;
+        else if (CLS == MC_DIV) { Ser<K> b = ser_load<K>(tape, I.b, false); r = t_div<K>(a, b); }
+        else r = t_div<K>(t_one<K>(), a);
+#pragma unroll
+        for (int k = 0; k <= K; ++k) tape[I.out * (K + 1) + k] = r.c[k];
+    }
+    return op;
+}
+template <int K, class TV>
+HC_HDN void run_taylor_tape_seg(const DevProgram& P, TV tape) {
+    const FOp* op = P.fops;
+    for (int s = 0; s < P.n_segs; ++s) {
+        const int2 sg = P.segs[s];
+        switch (sg.x) {
+#define HC_RUN_(CLS, N1, N2) op = run_taylor_segment<K, CLS, N1, N2>(op, sg.y, tape)
+            HC_SEG_CASES(HC_RUN_)
+#undef HC_RUN_
+        }
     }
 }
 

@@ -8,7 +8,7 @@ import os
 from .capi import CApi, Options, ResultsDesc, c_double_p, c_int32_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhc_b200.so")
+LIB_PATH = os.environ.get("HC_B200_LIB", os.path.join(_HERE, "libhc_b200.so"))  # override: debugging builds only
 
 _api: CApi | None = None
 
