@@ -147,7 +147,6 @@ struct KArgs {
     int slab_bytes;       // per-path shared-memory slab
     int cold_bytes;       // per-group scratch in global memory
     unsigned char* cold;
-    cx* cslab; double* rslab; int* islab;  // thread-per-path engine: lane-interleaved state slabs
     int refill_min;       // thread-per-path engine: idle lanes of a warp refill together once this many wait
     int stage_bytes;      // staged programs (0 when !stage)
 };
@@ -244,33 +243,8 @@ __device__ __forceinline__ void tpp_loop(LaneT& L, const KArgs& A, const KArgs& 
     }
 }
 
-// Thread-per-path engine (small systems): every lane tracks its own path, the per-lane state lives
-// in lane-interleaved global memory (L2-resident, coalesced), the programs in shared memory.  Idle
-// lanes of a warp take new paths from the queue together, so that the start-up code of a path
-// (init_newton!, first predictor update) runs converged instead of stalling the warp once per lane.
-__global__ void __launch_bounds__(128) hc_track_tpp_kernel(const __grid_constant__ KArgs A) {
-    __shared__ KArgs sA;
-    if (threadIdx.x == 0) sA = A;
-    __syncthreads();
-    if (A.stage) {
-        DevHomotopy h = A.H;
-        unsigned char* cur = hc_smem;
-        stage_program(h.Fe, cur, true);
-        stage_program(h.Fj, cur, true);
-        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur, true); stage_program(h.Gj, cur, true); }
-        __syncthreads();
-        if (threadIdx.x == 0) sA.H = h;
-        __syncthreads();
-    }
-    Lane<1, 1> L;
-    L.g.init();
-    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
-    const int T = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, A.cslab, A.rslab, A.islab, T, tid);
-    tpp_loop(L, A, sA);
-}
-
-// Thread-per-path engine with the lane state in LOCAL memory: the hardware interleaves the lanes of
+// Thread-per-path engine (n <= 14): every lane tracks its own path, the programs sit in shared memory,
+// the lane state in LOCAL memory: the hardware interleaves the lanes of
 // a warp (a warp access to element i is one contiguous 512 B segment, as in the explicit slabs
 // above), element addresses are base + immediate (no per-access stride multiply), and L1 keeps
 // local lines write-back, so the state that a step re-reads stays on the SM.
@@ -337,11 +311,10 @@ __global__ void hc_dfma_kernel(double* out, int iters) {
 
 // ------------------------------------------------------------------ launch planning
 struct Plan {
-    int engine;  // 0 = group per path (shared-memory state), 1 = thread per path (global slabs), 2 = thread per path (local memory)
+    int engine;  // 0 = lane group per path (state in shared memory), 1 = thread per path (state in local memory)
     int grid, block, group, paths_per_block;
     size_t smem, slab, cold, stage_bytes;
     int stage;
-    MemSizes sz;  // thread-per-path: elements per lane
     long long lanes;
 };
 
@@ -360,10 +333,9 @@ const size_t kSmemMax = 227 * 1024 - 2048;  // dynamic shared memory per CTA (th
 int engine_for(int n) {
     const char* e = getenv("HC_B200_ENGINE");
     if (e) {
-        if (!strcmp(e, "tpp")) return 1;
+        if (!strcmp(e, "tpp") || !strcmp(e, "local")) return 1;
         if (!strcmp(e, "group")) return 0;
-        if (!strcmp(e, "local")) return 2;
-        throw std::string("HC_B200_ENGINE must be tpp, local or group");
+        throw std::string("HC_B200_ENGINE must be tpp or group");
     }
     return n <= env_int("HC_B200_TPP_MAX_N", 14) ? 1 : 0;
 }
@@ -379,19 +351,24 @@ Plan make_plan(const HomotopyH& H, long long N) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     p.engine = engine_for(H.dev.n);
-    const bool fast = p.engine != 0;
-    p.stage_bytes = program_stage_bytes(H.F->eval, fast) + program_stage_bytes(H.F->jac, fast);
-    if (H.dev.kind == H_STRAIGHT_LINE) p.stage_bytes += program_stage_bytes(H.G->eval, fast) + program_stage_bytes(H.G->jac, fast);
-    p.stage = (p.stage_bytes <= (size_t)env_int("HC_B200_STAGE_MAX", 64 * 1024)) && env_int("HC_B200_STAGE", 1);
-    if (!p.stage) p.stage_bytes = 0;
-    if (p.engine == 2 && p.slab + p.cold > kLocalSlabMax) p.engine = 1;
+    auto stage_plan = [&](bool fast) {
+        p.stage_bytes = program_stage_bytes(H.F->eval, fast) + program_stage_bytes(H.F->jac, fast);
+        if (H.dev.kind == H_STRAIGHT_LINE) p.stage_bytes += program_stage_bytes(H.G->eval, fast) + program_stage_bytes(H.G->jac, fast);
+        p.stage = (p.stage_bytes <= (size_t)env_int("HC_B200_STAGE_MAX", 96 * 1024)) && env_int("HC_B200_STAGE", 1);
+        if (!p.stage) p.stage_bytes = 0;
+    };
+    stage_plan(p.engine != 0);
+    // the thread-per-path kernel reads its programs with ld.shared and its state with ld.local: both must fit
+    if (p.engine == 1 && (p.slab + p.cold > kLocalSlabMax || !p.stage)) {
+        if (getenv("HC_B200_ENGINE")) throw std::string("thread-per-path engine: state or programs of this system do not fit (use the group engine)");
+        p.engine = 0;  // (the segment-scheduled programs are valid, if narrow, level programs for a lane group)
+        stage_plan(false);
+    }
     if (p.engine != 0) {
-        PathMem<1> d2;
-        p.sz = carve(d2, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr, nullptr, 1, 0);
         p.group = 1;
         p.block = env_int("HC_B200_BLOCK", 64);
         if (p.block % 32 || p.block < 32 || p.block > 128) throw std::string("HC_B200_BLOCK must be 32, 64, 96 or 128 for the thread-per-path engine");
-        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 512 / p.block);
+        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 256 / p.block);  // 8 warps per SM measured best (profiles/r01_sweep.md)
         // lanes: at most a fraction of the paths, so that finished lanes have work to refill with
         long long lanes_cap = (long long)sms * per_sm * p.block;
         long long want_lanes = (N + env_int("HC_B200_PATHS_PER_LANE", 1) - 1) / env_int("HC_B200_PATHS_PER_LANE", 1);
@@ -493,12 +470,7 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     D.A.stage = pl.stage;
     D.A.slab_bytes = (int)pl.slab;
     D.A.cold_bytes = (int)pl.cold;
-    if (pl.engine == 1) {
-        D.A.cslab = D.alloc<cx>(pl.sz.ncx * (size_t)pl.lanes);
-        D.A.rslab = D.alloc<double>(pl.sz.nre * (size_t)pl.lanes);
-        D.A.islab = D.alloc<int>(pl.sz.nint * (size_t)pl.lanes);
-        D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
-    } else if (pl.engine == 2) D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
+    if (pl.engine == 1) D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
     else D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
     D.A.stage_bytes = (int)pl.stage_bytes;
 }
@@ -531,15 +503,11 @@ double run_batch(DeviceBatch& D) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, 0));
-    if (D.plan.engine == 2) {
+    if (D.plan.engine == 1) {
         const size_t need = D.plan.slab + D.plan.cold;
         if (need <= 12 * 1024) launch_tpl<12 * 1024>(D);
         else if (need <= 24 * 1024) launch_tpl<24 * 1024>(D);
         else launch_tpl<48 * 1024>(D);
-    } else if (D.plan.engine == 1) {
-        static bool attr_set = false;
-        if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_tpp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
-        hc_track_tpp_kernel<<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
     } else if (D.plan.group == 32) launch_track<32>(D);
     else launch_track<8>(D);
     CK(cudaEventRecord(e1, 0));
@@ -615,7 +583,7 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
         g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
         g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
         g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.group;
-        g_timing.slab_bytes = D.plan.engine == 2 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.slab + D.plan.cold) : D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.sz.ncx * 16 + D.plan.sz.nre * 8 + D.plan.sz.nint * 4) : (int64_t)D.plan.slab;
+        g_timing.slab_bytes = D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.slab + D.plan.cold) : (int64_t)D.plan.slab;
     } catch (const std::string& e) { return fail(e); }
     return 0;
 }

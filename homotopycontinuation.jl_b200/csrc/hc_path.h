@@ -67,15 +67,15 @@ HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* h
     static_assert(S == 0 || S == 2, "flat layouts only");
     size_t off = 0;
     unsigned char* base = hot;
-    auto C = [&](size_t k) { SV<cx, S> v; v.p = base ? (cx*)(base + off) : nullptr; off += 16 * k; return v; };
-    auto R = [&](size_t k) { SV<double, S> v; v.p = base ? (double*)(base + off) : nullptr; off += 8 * k; return v; };
+    auto C = [&](size_t k) { SV<cx, S> v = SV<cx, S>::make(base ? base + off : nullptr); off += 16 * k; return v; };
+    auto R = [&](size_t k) { SV<double, S> v = SV<double, S>::make(base ? base + off : nullptr); off += 8 * k; return v; };
     M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n);
     M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
     M.wr = C(n); M.wdx = C(n); M.work = C(n);
     M.tape = C((size_t)tape_cx);
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.tw = R(P > 0 ? P : 1);
-    M.ipiv.p = base ? (int*)(base + off) : nullptr; off += 4 * (size_t)n;
-    M.perm.p = base ? (int*)(base + off) : nullptr; off += 4 * (size_t)n;
+    M.ipiv = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
+    M.perm = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
     SlabSizes s;
     s.hot = (off + 15) & ~(size_t)15;
     off = 0; base = cold;
@@ -84,27 +84,6 @@ HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* h
     M.rbd.v = C(2 * n);
     M.egrs = R(n); M.egcs = R(n); M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n);
     s.cold = (off + 15) & ~(size_t)15;
-    return s;
-}
-
-// Thread-per-path layout: three lane-interleaved slabs in global memory (element i of lane l at
-// base[i * stride + l]).  With null bases it only counts elements per lane.
-struct MemSizes { size_t ncx, nre, nint; };
-HC_HD MemSizes carve(PathMem<1>& M, int n, int P, int tape_cx, cx* cb, double* rb, int* ib, int stride, int lane) {
-    size_t oc = 0, orr = 0;
-    auto C = [&](size_t k) { SV<cx, 1> v; v.p = cb ? cb + oc * (size_t)stride + lane : nullptr; v.s = stride; oc += k; return v; };
-    auto R = [&](size_t k) { SV<double, 1> v; v.p = rb ? rb + orr * (size_t)stride + lane : nullptr; v.s = stride; orr += k; return v; };
-    M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n); M.ptx1 = C(2 * n); M.ty1 = C(2 * n); M.pty1 = C(2 * n);
-    M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
-    M.wr = C(n); M.wdx = C(n); M.work = C(n);
-    M.sol = C(n); M.lastp = C(n); M.pred = C(n); M.ppred = C(n); M.samp = C(6 * n);
-    M.rbd.v = C(2 * n);
-    M.tape = C((size_t)tape_cx);
-    M.w = R(n); M.rs = R(n); M.rwork = R(n); M.egrs = R(n); M.egcs = R(n);
-    M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n); M.tw = R(P > 0 ? P : 1);
-    M.ipiv.p = ib ? ib + lane : nullptr; M.ipiv.s = stride;
-    M.perm.p = ib ? ib + (size_t)n * (size_t)stride + lane : nullptr; M.perm.s = stride;
-    MemSizes s; s.ncx = oc; s.nre = orr; s.nint = 2 * (size_t)n;
     return s;
 }
 
@@ -160,7 +139,7 @@ struct Path {
         double d = -1.0;
         HC_PAR(i, n) d = nmax(d, abs2(x[i]));
         double r = sqrt(g.rmax(d));
-        if (r == HC_INF) { d = 0; HC_PAR(i, n) d = nmax(d, hypot(x[i].re, x[i].im)); r = g.rmax(d); }
+        if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = x[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
         return r;
     }
     HC_HDN double inf_dist(CV x, CV y) {
@@ -287,10 +266,10 @@ struct Path {
 
     // thread-per-path engines run the segmented interpreters, lane groups the levelised ones
     HC_HD void run_f64(const DevProgram& P) {
-        if (G == 1) run_tape_seg(P, M.tape); else run_tape<cx, G>(P, M.tape, g);
+        if (G == 1) run_tape_seg(P.fops, P.segs, P.n_segs, M.tape); else run_tape<cx, G>(P, M.tape, g);
     }
     template <int K> HC_HD void run_taylor(const DevProgram& P) {
-        if (G == 1) run_taylor_tape_seg<K>(P, M.tape); else run_taylor_tape<K, G>(P, M.tape, g);
+        if (G == 1) run_taylor_tape_seg<K>(P.fops, P.segs, P.n_segs, M.tape); else run_taylor_tape<K, G>(P, M.tape, g);
     }
     // u (and optionally the column-major Jacobian U) of H(x, t)
     HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
@@ -704,7 +683,7 @@ struct Path {
         gamma = g.rsum(gamma);
         g.sync();
         lu_solve(y);
-        HC_PAR(i, nn) x[i] = dr ? y[i].re / (*dr)[i] : y[i].re;
+        HC_PAR(i, nn) { cx yi = y[i]; x[i] = dr ? yi.re / (*dr)[i] : yi.re; }
         g.sync();
         int k = 2;
         while (true) {
@@ -730,7 +709,7 @@ struct Path {
             g.sync();
             lu_solve(y);
             double ninf = 0;
-            HC_PAR(i, nn) { double v = dr ? y[i].re / (*dr)[i] : y[i].re; x[i] = v; double a = fabs(v); ninf = a > ninf ? a : ninf; }
+            HC_PAR(i, nn) { cx yi = y[i]; double v = dr ? yi.re / (*dr)[i] : yi.re; x[i] = v; double a = fabs(v); ninf = a > ninf ? a : ninf; }
             ninf = g.rmax(ninf);
             g.sync();
             k += 1;
@@ -751,7 +730,7 @@ struct Path {
     }
     HC_HDN double jac_cond(const RV* dl, const RV* dr) {  // :745-774
         if (n == 1) {
-            double a = hypot(M.A[0].re, M.A[0].im);
+            cx a0 = M.A[0]; double a = hypot(a0.re, a0.im);
             if (dl) a *= (*dl)[0];
             if (dr) a *= (*dr)[0];
             return 1.0 / a;

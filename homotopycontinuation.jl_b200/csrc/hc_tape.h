@@ -69,41 +69,89 @@ struct DevProgram {
 };
 
 // ------------------------------------------------------------------ vector views
-// S = 0: contiguous (the path's shared-memory slab, or the host in HC_HOST_SIM).
-// S = 1: lane-interleaved global memory, element i of lane l at base[i * stride + l], so that
-//            a warp whose 32 lanes track 32 paths (G = 1) touches one coalesced 512 B segment.
+// S = 0: contiguous behind a generic pointer (the lane group's shared-memory slab + its global
+//        scratch, or the host in HC_HOST_SIM).
+// S = 2: contiguous in the thread's LOCAL memory (thread-per-path engine, G = 1): the hardware
+//        interleaves the lanes of a warp (a warp access to element i is one 512 B segment), L1 keeps
+//        local lines write-back, and every access is an explicit ld.local / st.local on a 32-bit
+//        window address -- a generic LD/ST costs a descriptor (2 x R2UR) and 64-bit address
+//        arithmetic per access on sm_100a.  operator[] therefore returns a proxy, not a reference.
 template <class T, int S> struct SV;
 template <class T>
 struct SV<T, 0> {
     T* p;
     HC_HD T& operator[](int i) const { return p[i]; }
     HC_HD SV at(int off) const { SV r; r.p = p + off; return r; }
+    static HC_HD SV make(void* q) { SV r; r.p = (T*)q; return r; }
 };
-template <class T>
-struct SV<T, 2> {  // contiguous in the thread's LOCAL memory (G = 1): the hardware interleaves the lanes of a warp,
-                   // addresses need no stride arithmetic, and L1 caches local lines write-back
-    T* p;
-    HC_HD T& operator[](int i) const {
-#if defined(__CUDA_ARCH__) && defined(HC_LOCAL_ASSUME)  // off: nvcc 12.9 miscompiles the tracker with this hint (all paths fail at init)
-        __builtin_assume(__isLocal(p));
-#endif
-        return p[i];
-    }
-    HC_HD SV at(int off) const { SV r; r.p = p + off; return r; }
-};
-template <class T>
-struct SV<T, 1> {
-    T* p;
-    int s;
-    // 32-bit index arithmetic (rows * lanes < 2^31) and a global-address-space hint: without them
-    // every access costs a 64-bit multiply and a generic LD/ST
-    HC_HD T& operator[](int i) const {
+
+template <class T> struct LRef;  // element of a local-memory vector (device only)
+template <>
+struct LRef<cx> {
+    unsigned a;
+    HC_HD operator cx() const {
+        cx v = mk(0.0);
 #if defined(__CUDA_ARCH__)
-        __builtin_assume(__isGlobal(p));
+        asm volatile("ld.local.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(a));
 #endif
-        return p[(unsigned)i * (unsigned)s];
+        return v;
     }
-    HC_HD SV at(int off) const { SV r; r.p = p + (unsigned)off * (unsigned)s; r.s = s; return r; }
+    HC_HD const LRef& operator=(cx v) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.local.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.re), "d"(v.im));
+#endif
+        return *this;
+    }
+    HC_HD const LRef& operator=(const LRef& o) const { return *this = (cx)o; }
+};
+template <>
+struct LRef<double> {
+    unsigned a;
+    HC_HD operator double() const {
+        double v = 0.0;
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.local.f64 %0, [%1];" : "=d"(v) : "r"(a));
+#endif
+        return v;
+    }
+    HC_HD const LRef& operator=(double v) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.local.f64 [%0], %1;" ::"r"(a), "d"(v));
+#endif
+        return *this;
+    }
+    HC_HD const LRef& operator=(const LRef& o) const { return *this = (double)o; }
+};
+template <>
+struct LRef<int> {
+    unsigned a;
+    HC_HD operator int() const {
+        int v = 0;
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.local.s32 %0, [%1];" : "=r"(v) : "r"(a));
+#endif
+        return v;
+    }
+    HC_HD const LRef& operator=(int v) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.local.s32 [%0], %1;" ::"r"(a), "r"(v));
+#endif
+        return *this;
+    }
+    HC_HD const LRef& operator=(const LRef& o) const { return *this = (int)o; }
+};
+template <class T>
+struct SV<T, 2> {
+    unsigned p;  // byte address in the thread's local window
+    HC_HD LRef<T> operator[](int i) const { LRef<T> r; r.a = p + (unsigned)i * (unsigned)sizeof(T); return r; }
+    HC_HD SV at(int off) const { SV r; r.p = p + (unsigned)off * (unsigned)sizeof(T); return r; }
+    static HC_HD SV make(void* q) {
+        SV r; r.p = 0u;
+#if defined(__CUDA_ARCH__)
+        if (q) r.p = (unsigned)__cvta_generic_to_local(q);
+#endif
+        return r;
+    }
 };
 
 template <int S>
@@ -178,6 +226,43 @@ HC_HDN void run_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
     }
 }
 
+// ------------------------------------------------------------------ program cursors
+// The thread-per-path kernel (S = 2) always runs from programs staged in shared memory and reads
+// them with ld.shared on a 32-bit address; everything else walks a generic pointer.
+template <class E, bool SHARED>
+struct PCur {
+    const E* p;
+    HC_HD explicit PCur(const E* q) : p(q) {}
+    HC_HD E get(int i) const { return p[i]; }
+    HC_HD void adv(int k) { p += k; }
+};
+#if defined(__CUDA_ARCH__)
+template <>
+struct PCur<FOp, true> {
+    unsigned a;
+    HC_D explicit PCur(const FOp* q) : a((unsigned)__cvta_generic_to_shared(q)) {}
+    HC_D FOp get(int i) const {
+        FOp v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.a), "=r"(v.b), "=r"(v.c), "=r"(v.out) : "r"(a + 16u * (unsigned)i));
+        return v;
+    }
+    HC_D void adv(int k) { a += 16u * (unsigned)k; }
+};
+template <>
+struct PCur<int2, true> {
+    unsigned a;
+    HC_D explicit PCur(const int2* q) : a((unsigned)__cvta_generic_to_shared(q)) {}
+    HC_D int2 get(int i) const {
+        int2 v;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a + 8u * (unsigned)i));
+        return v;
+    }
+    HC_D void adv(int k) { a += 8u * (unsigned)k; }
+};
+#endif
+template <class TV> struct ProgInShared { static constexpr bool value = false; };
+template <> struct ProgInShared<SV<cx, 2>> { static constexpr bool value = true; };
+
 // ------------------------------------------------------------------ segmented interpreter (G == 1)
 // One dispatch per segment instead of one per micro-op: the loop of a segment knows class and
 // signs at compile time (negations fold into the DFMA operand modifiers), reads the slot numbers
@@ -197,30 +282,29 @@ HC_HD cx fop_eval(cx a, cx b, cx c, cx d) {
     if (CLS == MC_DIV) return cdiv(a, b);
     return ciszero(a) ? a : cinv(a);
 }
-template <int CLS, bool N1, bool N2, class TV>
-HC_HD const FOp* run_segment(const FOp* op, int cnt, TV tape) {
+template <int CLS, bool N1, bool N2, class OC, class TV>
+HC_HD void run_segment(OC& op, int cnt, TV tape) {
     constexpr bool useB = CLS == MC_MM || CLS == MC_MA || CLS == MC_M || CLS == MC_DIV;
     constexpr bool useC = CLS == MC_MM || CLS == MC_MA || CLS == MC_AA;
     constexpr int STEP = CLS == MC_MM ? 2 : 1;
     const cx z = mk(0.0);
-    for (; cnt >= 2; cnt -= 2, op += 2 * STEP) {
-        const FOp I0 = op[0], I1 = op[STEP];
+    for (; cnt >= 2; cnt -= 2, op.adv(2 * STEP)) {
+        const FOp I0 = op.get(0), I1 = op.get(STEP);
         const cx a0 = tape[I0.a], a1 = tape[I1.a];
         const cx b0 = useB ? tape[I0.b] : z, b1 = useB ? tape[I1.b] : z;
         const cx c0 = useC ? tape[I0.c] : z, c1 = useC ? tape[I1.c] : z;
-        const cx d0 = CLS == MC_MM ? tape[op[1].a] : z, d1 = CLS == MC_MM ? tape[op[STEP + 1].a] : z;
+        const cx d0 = CLS == MC_MM ? tape[op.get(1).a] : z, d1 = CLS == MC_MM ? tape[op.get(STEP + 1).a] : z;
         const cx r0 = fop_eval<CLS, N1, N2>(a0, b0, c0, d0), r1 = fop_eval<CLS, N1, N2>(a1, b1, c1, d1);
         tape[I0.out] = r0;
         tape[I1.out] = r1;
     }
     if (cnt) {
-        const FOp I0 = op[0];
+        const FOp I0 = op.get(0);
         const cx a0 = tape[I0.a];
-        const cx b0 = useB ? tape[I0.b] : z, c0 = useC ? tape[I0.c] : z, d0 = CLS == MC_MM ? tape[op[1].a] : z;
+        const cx b0 = useB ? tape[I0.b] : z, c0 = useC ? tape[I0.c] : z, d0 = CLS == MC_MM ? tape[op.get(1).a] : z;
         tape[I0.out] = fop_eval<CLS, N1, N2>(a0, b0, c0, d0);
-        op += STEP;
+        op.adv(STEP);
     }
-    return op;
 }
 #define HC_SEG_CASES(RUN)                                                                           \
     case HC_KEY(MC_MM, 0, 0): RUN(MC_MM, false, false); break;                                       \
@@ -238,12 +322,13 @@ HC_HD const FOp* run_segment(const FOp* op, int cnt, TV tape) {
     default: RUN(MC_INVNZ, false, false); break;  // the lowering emits no other (class, sign) pair
 
 template <class TV>
-HC_HDN void run_tape_seg(const DevProgram& P, TV tape) {
-    const FOp* op = P.fops;
-    for (int s = 0; s < P.n_segs; ++s) {
-        const int2 sg = P.segs[s];
+HC_HDN void run_tape_seg(const FOp* fops, const int2* segs, int n_segs, TV tape) {
+    PCur<FOp, ProgInShared<TV>::value> op(fops);
+    PCur<int2, ProgInShared<TV>::value> sc(segs);
+    for (int s = 0; s < n_segs; ++s) {
+        const int2 sg = sc.get(s);
         switch (sg.x) {
-#define HC_RUN_(CLS, N1, N2) op = run_segment<CLS, N1, N2>(op, sg.y, tape)
+#define HC_RUN_(CLS, N1, N2) run_segment<CLS, N1, N2>(op, sg.y, tape)
             HC_SEG_CASES(HC_RUN_)
 #undef HC_RUN_
         }
@@ -343,16 +428,16 @@ HC_HDN void run_taylor_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
 }
 
 // segmented Taylor interpreter (G == 1): class and signs are compile-time per segment
-template <int K, int CLS, bool N1, bool N2, class TV>
-HC_HD const FOp* run_taylor_segment(const FOp* op, int cnt, TV tape) {
+template <int K, int CLS, bool N1, bool N2, class OC, class TV>
+HC_HD void run_taylor_segment(OC& op, int cnt, TV tape) {
     constexpr int STEP = CLS == MC_MM ? 2 : 1;
-    for (; cnt > 0; --cnt, op += STEP) {
-        const FOp I = op[0];
+    for (; cnt > 0; --cnt, op.adv(STEP)) {
+        const FOp I = op.get(0);
         Ser<K> a = ser_load<K>(tape, I.a, N1), r;
         if (CLS == MC_MM) {
             Ser<K> b = ser_load<K>(tape, I.b, false);
             r = t_mul<K>(a, b);
-            Ser<K> c = ser_load<K>(tape, I.c, N2), d = ser_load<K>(tape, op[1].a, false);
+            Ser<K> c = ser_load<K>(tape, I.c, N2), d = ser_load<K>(tape, op.get(1).a, false);
             r = t_muladd<K>(c, d, r);
         } else if (CLS == MC_MA) {
             Ser<K> b = ser_load<K>(tape, I.b, false), c = ser_load<K>(tape, I.c, N2);
@@ -370,15 +455,15 @@ HC_HD const FOp* run_taylor_segment(const FOp* op, int cnt, TV tape) {
 #pragma unroll
         for (int k = 0; k <= K; ++k) tape[I.out * (K + 1) + k] = r.c[k];
     }
-    return op;
 }
 template <int K, class TV>
-HC_HDN void run_taylor_tape_seg(const DevProgram& P, TV tape) {
-    const FOp* op = P.fops;
-    for (int s = 0; s < P.n_segs; ++s) {
-        const int2 sg = P.segs[s];
+HC_HDN void run_taylor_tape_seg(const FOp* fops, const int2* segs, int n_segs, TV tape) {
+    PCur<FOp, ProgInShared<TV>::value> op(fops);
+    PCur<int2, ProgInShared<TV>::value> sc(segs);
+    for (int s = 0; s < n_segs; ++s) {
+        const int2 sg = sc.get(s);
         switch (sg.x) {
-#define HC_RUN_(CLS, N1, N2) op = run_taylor_segment<K, CLS, N1, N2>(op, sg.y, tape)
+#define HC_RUN_(CLS, N1, N2) run_taylor_segment<K, CLS, N1, N2>(op, sg.y, tape)
             HC_SEG_CASES(HC_RUN_)
 #undef HC_RUN_
         }
