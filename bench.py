@@ -129,8 +129,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="cyclic7_polyhedral", choices=WORKLOADS)
-    ap.add_argument("--replicas", type=int, default=160, help="replicas of the config per GPU (weak scaling)")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="paths per step of the CPU baseline / reference arm")
+    ap.add_argument("--replicas", type=int, default=480, help="replicas of the config per GPU (weak scaling)")
+    ap.add_argument("--cpu-sample", type=int, default=131072, help="paths per step of the CPU baseline / reference arm (about 5-10 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -242,7 +242,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wg.description, "paths_per_gpu_per_step": w.N,
                    "parallelism": f"path index range sharded over {world} GPU(s), no collective on the hot path",
-                   "l2": (f"per-lane state slabs {tm.slab_bytes / 2**20:.0f} MiB > 126 MiB L2; inputs are KBs" if tm.lanes == 1 else
+                   "l2": (f"per-lane path state in local memory, {tm.slab_bytes / 2**20:.0f} MiB over all lanes > 126 MiB L2; inputs are KBs" if tm.lanes == 1 else
                           f"path state in shared memory ({tm.slab_bytes} B per path); inputs are KBs"),
                    "engine": "thread-per-path" if tm.lanes == 1 else f"{tm.lanes}-lane group per path",
                    "grid": tm.grid, "block": tm.block, "success_paths": n_ok, "class_counts": counts, "expected": wg.expected},

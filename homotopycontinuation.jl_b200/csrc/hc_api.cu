@@ -368,7 +368,7 @@ Plan make_plan(const HomotopyH& H, long long N) {
         p.group = 1;
         p.block = env_int("HC_B200_BLOCK", 64);
         if (p.block % 32 || p.block < 32 || p.block > 128) throw std::string("HC_B200_BLOCK must be 32, 64, 96 or 128 for the thread-per-path engine");
-        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 256 / p.block);  // 8 warps per SM measured best (profiles/r01_sweep.md)
+        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", (H.dev.n <= 4 ? 512 : 256) / p.block);  // 8 warps per SM (16 for tiny systems) measured best (profiles/r01_sweep.md)
         // lanes: at most a fraction of the paths, so that finished lanes have work to refill with
         long long lanes_cap = (long long)sms * per_sm * p.block;
         long long want_lanes = (N + env_int("HC_B200_PATHS_PER_LANE", 1) - 1) / env_int("HC_B200_PATHS_PER_LANE", 1);

@@ -16,6 +16,8 @@
 namespace hc {
 
 #define HC_PAR(i, N) for (int i = g.lane; i < (N); i += G)
+// load-only loops (reductions): unrolled so that the loads of four trips are in flight together
+#define HC_PARU(i, N) _Pragma("unroll 4") for (int i = g.lane; i < (N); i += G)
 
 enum HKind : int { H_STRAIGHT_LINE = 0, H_PARAMETER = 1, H_COEFFICIENT = 2, H_TORIC = 3 };
 
@@ -137,28 +139,28 @@ struct Path {
     // ================================================================ norms (src/norm.jl)
     HC_HDN double inf_norm(CV x) {
         double d = -1.0;
-        HC_PAR(i, n) d = nmax(d, abs2(x[i]));
+        HC_PARU(i, n) d = nmax(d, abs2(x[i]));
         double r = sqrt(g.rmax(d));
         if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = x[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
         return r;
     }
     HC_HDN double inf_dist(CV x, CV y) {
         double d = -1.0;
-        HC_PAR(i, n) d = nmax(d, abs2(x[i] - y[i]));
+        HC_PARU(i, n) d = nmax(d, abs2(x[i] - y[i]));
         double r = sqrt(g.rmax(d));
         if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = x[i] - y[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
         return r;
     }
     HC_HDN double wnorm(CV x) {
         double d = -1.0;
-        HC_PAR(i, n) d = nmax(d, abs2(x[i] / M.w[i]));
+        HC_PARU(i, n) d = nmax(d, abs2(x[i] / M.w[i]));
         double r = sqrt(g.rmax(d));
         if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = x[i] / M.w[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
         return r;
     }
     HC_HDN double wdist(CV x, CV y) {
         double d = -1.0;
-        HC_PAR(i, n) d = nmax(d, abs2((x[i] - y[i]) / M.w[i]));
+        HC_PARU(i, n) d = nmax(d, abs2((x[i] - y[i]) / M.w[i]));
         double r = sqrt(g.rmax(d));
         if (r == HC_INF) { d = 0; HC_PAR(i, n) { cx z = (x[i] - y[i]) / M.w[i]; d = nmax(d, hypot(z.re, z.im)); } r = g.rmax(d); }
         return r;
@@ -587,6 +589,7 @@ struct Path {
         double m = -HC_INF;
         HC_PAR(i, nn) {
             double di = 0.0;
+#pragma unroll 4
             for (int j = 0; j < nn; ++j) di += cabs(M.A[j * nn + i]) * c[j];
             d[i] = di;
             m = nmax(m, di);
@@ -623,6 +626,7 @@ struct Path {
         const int nn = n;
         HC_PAR(i, nn) {
             cx acc = -b[i];
+#pragma unroll 4
             for (int j = 0; j < nn; ++j) acc = cfma(M.A[j * nn + i], x[j], acc);
             M.wr[i] = acc;
         }
@@ -920,7 +924,16 @@ struct Path {
     }
 
     // ================================================================ Newton corrector
-    HC_HDN void axmy(CV out, CV a, CV b) { HC_PAR(i, n) out[i] = a[i] - b[i]; g.sync(); }  // out = a - b
+    HC_HDN void axmy(CV out, CV a, CV b) {  // out = a - b
+        if (G == 1) {
+            int i = 0;
+            for (; i + 3 < n; i += 4) {
+                cx a0 = a[i], a1 = a[i + 1], a2 = a[i + 2], a3 = a[i + 3], b0 = b[i], b1 = b[i + 1], b2 = b[i + 2], b3 = b[i + 3];
+                out[i] = a0 - b0; out[i + 1] = a1 - b1; out[i + 2] = a2 - b2; out[i + 3] = a3 - b3;
+            }
+            for (; i < n; ++i) out[i] = a[i] - b[i];
+        } else { HC_PAR(i, n) out[i] = a[i] - b[i]; g.sync(); }
+    }
     // extended_prec_refinement_step!  newton_corrector.jl:55-78 (xout may alias xin)
     HC_HDN double ext_refinement_step(CV xout, CV xin, cx t, bool simple_newton_step) {
         eval_f64(M.r, &M.A, xin, t);

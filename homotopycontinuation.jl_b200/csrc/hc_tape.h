@@ -266,7 +266,7 @@ template <> struct ProgInShared<SV<cx, 2>> { static constexpr bool value = true;
 // ------------------------------------------------------------------ segmented interpreter (G == 1)
 // One dispatch per segment instead of one per micro-op: the loop of a segment knows class and
 // signs at compile time (negations fold into the DFMA operand modifiers), reads the slot numbers
-// straight out of the 16-byte FOp and handles two independent ops per trip with all loads issued
+// straight out of the 16-byte FOp and handles four (then two) independent ops per trip with all loads issued
 // before the first store (ops of a level never alias).  Results are bit-identical to eval_mop.
 #define HC_KEY(cls, n1, n2) ((cls) | ((n1) << 3) | ((n2) << 4))
 
@@ -288,7 +288,21 @@ HC_HD void run_segment(OC& op, int cnt, TV tape) {
     constexpr bool useC = CLS == MC_MM || CLS == MC_MA || CLS == MC_AA;
     constexpr int STEP = CLS == MC_MM ? 2 : 1;
     const cx z = mk(0.0);
-    for (; cnt >= 2; cnt -= 2, op.adv(2 * STEP)) {
+    for (; cnt >= 4; cnt -= 4, op.adv(4 * STEP)) {
+        const FOp I0 = op.get(0), I1 = op.get(STEP), I2 = op.get(2 * STEP), I3 = op.get(3 * STEP);
+        const cx a0 = tape[I0.a], a1 = tape[I1.a], a2 = tape[I2.a], a3 = tape[I3.a];
+        const cx b0 = useB ? tape[I0.b] : z, b1 = useB ? tape[I1.b] : z, b2 = useB ? tape[I2.b] : z, b3 = useB ? tape[I3.b] : z;
+        const cx c0 = useC ? tape[I0.c] : z, c1 = useC ? tape[I1.c] : z, c2 = useC ? tape[I2.c] : z, c3 = useC ? tape[I3.c] : z;
+        const cx d0 = CLS == MC_MM ? tape[op.get(1).a] : z, d1 = CLS == MC_MM ? tape[op.get(STEP + 1).a] : z;
+        const cx d2 = CLS == MC_MM ? tape[op.get(2 * STEP + 1).a] : z, d3 = CLS == MC_MM ? tape[op.get(3 * STEP + 1).a] : z;
+        const cx r0 = fop_eval<CLS, N1, N2>(a0, b0, c0, d0), r1 = fop_eval<CLS, N1, N2>(a1, b1, c1, d1);
+        const cx r2 = fop_eval<CLS, N1, N2>(a2, b2, c2, d2), r3 = fop_eval<CLS, N1, N2>(a3, b3, c3, d3);
+        tape[I0.out] = r0;
+        tape[I1.out] = r1;
+        tape[I2.out] = r2;
+        tape[I3.out] = r3;
+    }
+    if (cnt >= 2) {
         const FOp I0 = op.get(0), I1 = op.get(STEP);
         const cx a0 = tape[I0.a], a1 = tape[I1.a];
         const cx b0 = useB ? tape[I0.b] : z, b1 = useB ? tape[I1.b] : z;
@@ -297,6 +311,7 @@ HC_HD void run_segment(OC& op, int cnt, TV tape) {
         const cx r0 = fop_eval<CLS, N1, N2>(a0, b0, c0, d0), r1 = fop_eval<CLS, N1, N2>(a1, b1, c1, d1);
         tape[I0.out] = r0;
         tape[I1.out] = r1;
+        cnt -= 2; op.adv(2 * STEP);
     }
     if (cnt) {
         const FOp I0 = op.get(0);

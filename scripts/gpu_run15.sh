@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+timeout 1200 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 3000 gpurun_out/bench_default.json; tail -3 gpurun_out/bench_default.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 1500 gpurun_out/bench_ref.json
+timeout 900 python bench.py --workload katsura8 --replicas 1184 --steps 3 > gpurun_out/bench_katsura8.json 2> gpurun_out/bench_katsura8.err; tail -c 2500 gpurun_out/bench_katsura8.json

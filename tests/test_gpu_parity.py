@@ -135,3 +135,23 @@ def test_cyclic7_polyhedral_config2(oracle, gpu):  # BASELINE.json configs[1]: 9
     assert (rg.return_code == 1).sum() == 924 and rg.singular.sum() == 0
     assert len(np.unique(np.round(rg.solution, 6), axis=0)) == 924
     assert rg.residual.max() < 1e-10
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 7, 9, 10, 11, 12, 15])
+def test_system_sizes(oracle, gpu, k):
+    """n = k + 1: every register-blocked LU instantiation class (n <= 12), the generic LU of the
+    thread-per-path engine (n = 13) and the lane-group engine (n = 16); 64 paths of katsura(k) each."""
+    out = []
+    for api in (oracle, gpu):
+        td, H = straight_line(api, systems.katsura(k), 0.4 + 1.3j)
+        out.append(H.track_batch(td.start_solutions()[:64], nthreads=8))
+    assert_batches_match(*out)
+    assert abs(int(out[0].accepted_steps.sum()) - int(out[1].accepted_steps.sum())) <= 0.02 * out[0].accepted_steps.sum()
+
+
+def test_group_engine_matches_thread_engine(oracle, gpu, monkeypatch):
+    """Both engines run the same per-path algorithm: force the lane-group engine on a small system."""
+    monkeypatch.setenv("HC_B200_ENGINE", "group")
+    ro, rg = (track_td(api, systems.katsura(6), 0.4 + 1.3j, nthreads=8) for api in (oracle, gpu))
+    assert_batches_match(ro, rg)
+    assert lib.timing().lanes in (8, 32)

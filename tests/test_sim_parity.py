@@ -89,3 +89,15 @@ def test_polyhedral_cyclic5(oracle, sim):
     assert_batches_match(*res)
     assert (res[1].return_code == 1).sum() == 70
     assert len(np.unique(np.round(res[1].solution, 6), axis=0)) == 70
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 6, 10, 11, 12])
+def test_system_sizes(oracle, sim, k):
+    """n = k + 1 = 2 .. 13: the register-blocked LU / solve instantiations (n <= 12) and the generic
+    fallback (n = 13) must reproduce the oracle; 24 paths of katsura(k) each."""
+    out = []
+    for api in (oracle, sim):
+        td, H = straight_line(api, systems.katsura(k), 0.4 + 1.3j)
+        out.append(H.track_batch(td.start_solutions()[:24]))
+    assert_batches_match(*out)
+    assert abs(int(out[0].accepted_steps.sum()) - int(out[1].accepted_steps.sum())) <= 0.02 * out[0].accepted_steps.sum()
