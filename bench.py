@@ -227,6 +227,9 @@ def main():
     if dist is not None:
         dist.all_reduce(ct)
     counts = {k: int(v) for k, v in zip(sorted(counts), ct.tolist())}
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant (only) kernel

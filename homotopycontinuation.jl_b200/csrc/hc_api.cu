@@ -95,7 +95,7 @@ int group_size_for(int n) {
 int engine_for(int n);
 
 // Lower the reference's 24-byte, 1-based Instruction stream (hc_lower.h) and upload it.
-void build_program(ProgramH& H, const hc_program_desc* d) {
+void build_program(ProgramH& H, const hc_program_desc* d, bool is_jac) {
 #ifdef HC_HOST_SIM
     const bool tpp = true;
 #else
@@ -104,7 +104,10 @@ void build_program(ProgramH& H, const hc_program_desc* d) {
     // thread per path: segment scheduling (window of tape-order ops) feeds the segment loops of hc_tape.h;
     // lane groups: rounds of at most `cap` independent ops
     const int cap = tpp ? 0 : env_int("HC_B200_ROUND_CAP", 2 * group_size_for(d->n_vars));
-    const int win = tpp ? env_int("HC_B200_SEG_WINDOW", 32) : 0;
+    // Both programs are segment-scheduled; the evaluation-only program (the one the Taylor interpreter runs
+    // with K + 1 coefficients per slot) has its own knob because its tape size is multiplied by four.
+    // Measured (profiles/r01_sweep.md): window 32 beats tape order by 7-13 % for it as well.
+    const int win = !tpp ? 0 : is_jac ? env_int("HC_B200_SEG_WINDOW", 32) : env_int("HC_B200_SEG_WINDOW_EVAL", 32);
     H.low = lower_program(d, cap, env_int("HC_B200_PRIO_HEIGHT", 1) != 0, false, win);
     const LoweredProgram& L = H.low;
     DevProgram& P = H.dev;
@@ -249,7 +252,7 @@ __device__ __forceinline__ void tpp_loop(LaneT& L, const KArgs& A, const KArgs& 
 // above), element addresses are base + immediate (no per-access stride multiply), and L1 keeps
 // local lines write-back, so the state that a step re-reads stays on the SM.
 template <int SLAB>
-__global__ void __launch_bounds__(128) hc_track_tpl_kernel(const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(256) hc_track_tpl_kernel(const __grid_constant__ KArgs A) {
     __shared__ KArgs sA;
     if (threadIdx.x == 0) sA = A;
     __syncthreads();
@@ -366,9 +369,13 @@ Plan make_plan(const HomotopyH& H, long long N) {
     }
     if (p.engine != 0) {
         p.group = 1;
-        p.block = env_int("HC_B200_BLOCK", 64);
-        if (p.block % 32 || p.block < 32 || p.block > 128) throw std::string("HC_B200_BLOCK must be 32, 64, 96 or 128 for the thread-per-path engine");
-        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", (H.dev.n <= 4 ? 512 : 256) / p.block);  // 8 warps per SM (16 for tiny systems) measured best (profiles/r01_sweep.md)
+        // One CTA per SM: 4 warps (8 for tiny systems).  The lane state is cached in L1, so a single copy of
+        // the staged programs (smallest shared-memory carve-out) and few lanes beat more warps; 255
+        // registers per thread keep the unrolled segment loops and the LU columns out of local memory
+        // (profiles/r01_sweep.md).
+        p.block = env_int("HC_B200_BLOCK", H.dev.n <= 4 ? 256 : 128);
+        if (p.block % 32 || p.block < 32 || p.block > 256) throw std::string("HC_B200_BLOCK must be a multiple of 32 in [32, 256]");
+        int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 1);
         // lanes: at most a fraction of the paths, so that finished lanes have work to refill with
         long long lanes_cap = (long long)sms * per_sm * p.block;
         long long want_lanes = (N + env_int("HC_B200_PATHS_PER_LANE", 1) - 1) / env_int("HC_B200_PATHS_PER_LANE", 1);
@@ -485,6 +492,17 @@ void launch_tpl(const DeviceBatch& D) {
         CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
         if (cur < (size_t)SLAB + 8192) CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)SLAB + 8192));
         attr_set = true;
+    }
+    // the lane state lives in L1 (local memory): ask for the smallest shared-memory carve-out that holds
+    // the staged programs of the CTAs resident on one SM
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = (D.plan.grid + sms - 1) / sms;
+        int pct = env_int("HC_B200_CARVEOUT", (int)((per_sm * (D.plan.smem + 3072) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+        if (pct > 100) pct = 100;
+        CK(cudaFuncSetAttribute(hc_track_tpl_kernel<SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     hc_track_tpl_kernel<SLAB><<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
 }
@@ -633,8 +651,8 @@ void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac) 
             throw std::string("eval and Jacobian tapes disagree on dimensions");
         if (eval->out_dim != eval->n_vars) throw std::string("only square systems are supported");
         S = new SystemH();
-        build_program(S->eval, eval);
-        build_program(S->jac, jac);
+        build_program(S->eval, eval, false);
+        build_program(S->jac, jac, true);
         S->m = eval->out_dim; S->n = eval->n_vars; S->P = eval->n_params;
     } catch (const std::string& e) { delete S; fail(e); return nullptr; }
     return S;
