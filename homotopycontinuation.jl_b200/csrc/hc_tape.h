@@ -268,6 +268,9 @@ template <> struct ProgInShared<SV<cx, 2>> { static constexpr bool value = true;
 // signs at compile time (negations fold into the DFMA operand modifiers), reads the slot numbers
 // straight out of the 16-byte FOp and handles four (then two) independent ops per trip with all loads issued
 // before the first store (ops of a level never alias).  Results are bit-identical to eval_mop.
+#ifndef HC_SEG_UNROLL4
+#define HC_SEG_UNROLL4 0  // measured: the x4 trip costs more in instruction-cache misses than it gains in overlap (-4 %)
+#endif
 #define HC_KEY(cls, n1, n2) ((cls) | ((n1) << 3) | ((n2) << 4))
 
 template <int CLS, bool N1, bool N2>
@@ -288,6 +291,7 @@ HC_HD void run_segment(OC& op, int cnt, TV tape) {
     constexpr bool useC = CLS == MC_MM || CLS == MC_MA || CLS == MC_AA;
     constexpr int STEP = CLS == MC_MM ? 2 : 1;
     const cx z = mk(0.0);
+#if HC_SEG_UNROLL4
     for (; cnt >= 4; cnt -= 4, op.adv(4 * STEP)) {
         const FOp I0 = op.get(0), I1 = op.get(STEP), I2 = op.get(2 * STEP), I3 = op.get(3 * STEP);
         const cx a0 = tape[I0.a], a1 = tape[I1.a], a2 = tape[I2.a], a3 = tape[I3.a];
@@ -303,6 +307,9 @@ HC_HD void run_segment(OC& op, int cnt, TV tape) {
         tape[I3.out] = r3;
     }
     if (cnt >= 2) {
+#else
+    for (; cnt >= 2;) {
+#endif
         const FOp I0 = op.get(0), I1 = op.get(STEP);
         const cx a0 = tape[I0.a], a1 = tape[I1.a];
         const cx b0 = useB ? tape[I0.b] : z, b1 = useB ? tape[I1.b] : z;

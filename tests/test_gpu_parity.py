@@ -155,3 +155,33 @@ def test_group_engine_matches_thread_engine(oracle, gpu, monkeypatch):
     ro, rg = (track_td(api, systems.katsura(6), 0.4 + 1.3j, nthreads=8) for api in (oracle, gpu))
     assert_batches_match(ro, rg)
     assert lib.timing().lanes in (8, 32)
+
+
+def test_tritangents_slice_config3(oracle, gpu):
+    """BASELINE.json configs[2] at test size: the first 4096 total-degree paths of tritangents (n = 12).
+    Nonsingular endpoints and their count must agree; paths that die inside the endgame at t < 1e-9 may
+    end with a different terminated_* code (FMA contraction decides there), so only a bound is asserted."""
+    from hcb200 import workloads
+    w = workloads.tritangents_total_degree().subset(4096)
+    ro, rg = (w.track(api, w.build(api), nthreads=8) for api in (oracle, gpu))
+    ns_o = (ro.return_code == 1) & (ro.singular == 0)
+    ns_g = (rg.return_code == 1) & (rg.singular == 0)
+    assert (ns_o == ns_g).all() and ns_o.sum() > 0
+    assert rel_endpoint_error(rg.solution[ns_g], ro.solution[ns_o]) < 1e-8
+    at_inf = lambda r: int((r.return_code == 2).sum())
+    assert abs(at_inf(ro) - at_inf(rg)) <= 0.005 * w.N
+    assert (ro.return_code != rg.return_code).sum() <= 0.02 * w.N
+
+
+def test_cyclooctane_slice_config4(oracle, gpu):
+    """BASELINE.json configs[3] at test size (n = 17, lane-group engine, singular endpoints at infinity via the
+    endgame + DoubleDouble): the first 2048 total-degree paths of cyclooctane."""
+    from hcb200 import workloads
+    w = workloads.cyclooctane_total_degree().subset(2048)
+    ro, rg = (w.track(api, w.build(api), nthreads=8) for api in (oracle, gpu))
+    ns_o = (ro.return_code == 1) & (ro.singular == 0)
+    ns_g = (rg.return_code == 1) & (rg.singular == 0)
+    assert (ns_o == ns_g).all()
+    if ns_o.any():
+        assert rel_endpoint_error(rg.solution[ns_g], ro.solution[ns_o]) < 1e-8
+    assert (ro.return_code != rg.return_code).sum() <= 0.02 * w.N
