@@ -465,6 +465,7 @@ struct Lane : Path<G, S> {
         g.sync();
         refined_extended_prec = false; factorized = scaled = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
+        B::tol_acc_limit = pow(O->a, (double)((1 << O->min_newton_iters) - 1)) * hfun(O->a);
         n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_tay1 = n_tay2 = n_tay3 = 0; c_fact = c_ldiv = 0;
         toric_acc = toric_rej = 0;
         double om = HC_NAN, mu_ = HC_NAN;

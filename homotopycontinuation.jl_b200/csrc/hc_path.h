@@ -129,6 +129,7 @@ struct Path {
     bool extended_prec, used_extended_prec, refined_extended_prec, keep_extended_prec, use_strict_beta_tau;
     bool factorized, scaled;  // MatrixWorkspace flags
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
+    double tol_acc_limit;  // accuracy-limit threshold of check_terminated (options only; cached per path: pow is 300 instructions)
     double min_step_size, min_rel_step_size;  // mutable copies (polyhedral.jl:474-488, endgame_tracker.jl:270)
     // ---- predictor (src/predictor.jl:72-103)
     int pm_hermite; double trust_region, local_error, cond_H;
@@ -806,6 +807,18 @@ struct Path {
         trust_region = local_error = HC_NAN;
         pm_hermite = 0;
     }
+    // cold parts of pred_update (winding > 1, singular endgame only), out of line to keep the regular step small
+    HC_HDN void pu_splane(cx t) { pprev_s = ps; ps = t_to_s_plane(t, winding); }
+    HC_HDN void pu_hermite(double nrm0, double nrm1) {
+        const int nn = n;
+        CV x1 = M.tx.at(nn);
+        cx mu_ = winding == 2 ? 2.0 * ps : (double)winding * cpowi(ps, winding - 1);
+        HC_PAR(i, nn) { x1[i] = M.xtemp[i]; M.ty1[nn + i] = mu_ * M.xtemp[i]; }
+        g.sync();
+        pm_hermite = 1;
+        trust_region = nrm0 / nrm1;
+        if (local_error != local_error) { double q = nrm1 / nrm0; local_error = q * q * q; }
+    }
     // update!(predictor, H, x, t, J, norm, xhat)  predictor.jl:158-284
     HC_HDN void pred_update(cx t, bool have_xhat) {
         const int nn = n;
@@ -813,7 +826,7 @@ struct Path {
         HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i];
         g.sync();
         pprev_t = pt; pt = t;
-        if (winding > 1) { pprev_s = ps; ps = t_to_s_plane(t, winding); }
+        if (winding > 1) pu_splane(t);
         if (!have_xhat) local_error = HC_NAN;
         else {
             double ds = cabs(t - pprev_t), d2 = ds * ds;
@@ -831,15 +844,7 @@ struct Path {
         cond_H = delta / HC_EPS;
         if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, false, 5, 1e-10);
         double nrm1 = wnorm(M.xtemp);
-        if (winding > 1) {
-            cx mu_ = winding == 2 ? 2.0 * ps : (double)winding * cpowi(ps, winding - 1);
-            HC_PAR(i, nn) { x1[i] = M.xtemp[i]; M.ty1[nn + i] = mu_ * M.xtemp[i]; }
-            g.sync();
-            pm_hermite = 1;
-            trust_region = nrm0 / nrm1;
-            if (local_error != local_error) { double q = nrm1 / nrm0; local_error = q * q * q; }
-            return;
-        }
+        if (winding > 1) { pu_hermite(nrm0, nrm1); return; }
         vcopy(x1, M.xtemp, nn);
         taylor<2>(M.u, M.tx, t);
         HC_PAR(i, nn) M.u[i] = -M.u[i];
@@ -908,19 +913,22 @@ struct Path {
                 }
             }
             g.sync();
-        } else {
-            int mw = winding;
-            cx s0 = t_to_s_plane(pprev_t, mw), s1 = t_to_s_plane(t, mw), sp = t_to_s_plane(t + dt, mw);
-            cx psm, sm;
-            if (mw == 2) { psm = 2.0 * s0; sm = 2.0 * s1; }
-            else { psm = (double)mw * cpowi(s0, mw - 1); sm = (double)mw * cpowi(s1, mw - 1); }
-            HC_PAR(i, nn) {
-                M.pty1[i] = M.ptx1[i]; M.pty1[nn + i] = psm * M.ptx1[nn + i];
-                M.ty1[i] = M.tx[i]; M.ty1[nn + i] = sm * M.tx[nn + i];
-            }
-            g.sync();
-            cubic_hermite(M.xhat, M.pty1, M.pty1.at(nn), s0, M.ty1, M.ty1.at(nn), s1, sp);
+        } else predict_hermite(t, dt);
+    }
+    // cold half of predict (winding > 1 only): kept out of line so that the regular step's code stays small
+    HC_HDN void predict_hermite(cx t, cx dt) {
+        const int nn = n;
+        int mw = winding;
+        cx s0 = t_to_s_plane(pprev_t, mw), s1 = t_to_s_plane(t, mw), sp = t_to_s_plane(t + dt, mw);
+        cx psm, sm;
+        if (mw == 2) { psm = 2.0 * s0; sm = 2.0 * s1; }
+        else { psm = (double)mw * cpowi(s0, mw - 1); sm = (double)mw * cpowi(s1, mw - 1); }
+        HC_PAR(i, nn) {
+            M.pty1[i] = M.ptx1[i]; M.pty1[nn + i] = psm * M.ptx1[nn + i];
+            M.ty1[i] = M.tx[i]; M.ty1[nn + i] = sm * M.tx[nn + i];
         }
+        g.sync();
+        cubic_hermite(M.xhat, M.pty1, M.pty1.at(nn), s0, M.ty1, M.ty1.at(nn), s1, sp);
     }
 
     // ================================================================ Newton corrector
@@ -1065,6 +1073,14 @@ struct Path {
         double ds = nanmin(ds1, ds2);
         return jmin(jmin(ds, O->max_step_size), O->max_initial_step_size);
     }
+    HC_HDN double rejected_stepsize(const NewtonResult& R, double a) {  // tracker.jl:572-586 (cold: general n-th roots)
+        int j = R.iters - 2;
+        int rootn = j >= 0 ? (1 << j) : 0;
+        double Th = rootn == 8 ? sqrt(sqrt(sqrt(R.theta))) : nthroot(R.theta, rootn);
+        double hT = hfun(Th), ha = hfun(0.5 * a);
+        if (Th != Th || R.code == NEWT_SINGULARITY || R.accuracy != R.accuracy || R.iters == 1 || hT < ha) return 0.25 * st_ds();
+        return nthroot((sqrt(1 + 2 * ha) - 1) / (sqrt(1 + 2 * hT) - 1), 4) * st_ds();
+    }
     HC_HDN void update_stepsize(const NewtonResult& R) {  // tracker.jl:541-588
         double a = O->beta_a * O->a;
         double om = clampd(omega + 2 * (omega - omega_prev), omega, 8 * omega);
@@ -1078,24 +1094,12 @@ struct Path {
             if (use_strict_beta_tau && st_dist() < ds) ds *= O->strict_beta_tau;
             ds = jmin(ds, 10 * ds_prev);
             if (last_steps_failed > 0) ds = jmin(ds, ds_prev);
-        } else {
-            int j = R.iters - 2;
-            int rootn = j >= 0 ? (1 << j) : 0;
-            double Th = rootn == 8 ? sqrt(sqrt(sqrt(R.theta))) : nthroot(R.theta, rootn);
-            double hT = hfun(Th), ha = hfun(0.5 * a);
-            if (Th != Th || R.code == NEWT_SINGULARITY || R.accuracy != R.accuracy || R.iters == 1 || hT < ha)
-                ds = 0.25 * st_ds();
-            else
-                ds = nthroot((sqrt(1 + 2 * ha) - 1) / (sqrt(1 + 2 * hT) - 1), 4) * st_ds();
-        }
+        } else ds = rejected_stepsize(R, a);
         st_propose(ds);
     }
     HC_HDN void check_terminated() {  // tracker.jl:591-619
         double tol_acc = HC_INF;
-        if (extended_prec || !O->extended_precision) {
-            double a = O->a;
-            tol_acc = pow(a, (double)((1 << O->min_newton_iters) - 1)) * hfun(a);
-        }
+        if (extended_prec || !O->extended_precision) tol_acc = tol_acc_limit;  // a^(2^min_newton_iters - 1) h(a), set once per path
         cx tp = st_tp(), t = st_t();
         if (st_done()) code = TC_success;
         else if (steps() >= O->max_steps) code = TC_terminated_max_steps;
