@@ -129,6 +129,7 @@ struct Path {
     bool extended_prec, used_extended_prec, refined_extended_prec, keep_extended_prec, use_strict_beta_tau;
     bool factorized, scaled;  // MatrixWorkspace flags
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
+    const DevProgram* tape_prog; int tape_kind; cx tape_t;  // whose inputs (constants, parameters at t) the fp64 tape holds
     double tol_acc_limit;  // accuracy-limit threshold of check_terminated (options only; cached per path: pow is 300 instructions)
     double min_step_size, min_rel_step_size;  // mutable copies (polyhedral.jl:474-488, endgame_tracker.jl:270)
     // ---- predictor (src/predictor.jl:72-103)
@@ -260,11 +261,18 @@ struct Path {
     HC_HDN void load_inputs(const DevProgram& P, CV x, const CV* xlo, cx t, const cx* fixed) {
         T* tag = nullptr;
         CV tape = M.tape;
-        HC_PAR(i, P.C) store_in(tape, i, P.consts[i], mk(0.0), tag);
-        HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? fixed[i] : param_value(i, t), mk(0.0), tag);
-        if (P.t_slot >= 0 && g.lane == 0) store_in(tape, P.t_slot, t, mk(0.0), tag);
+        // Ops never write into the input block, so constants, parameters and t survive an fp64 run: the
+        // Newton iterations of one step (same program, same t) only refresh the variables.  That skips
+        // P parameter evaluations (t^w = exp(w log t) each for a toric homotopy) per iteration.
+        const bool keep = sizeof(T) == sizeof(cx) && tape_prog == &P && tape_kind == kind && tape_t.re == t.re && tape_t.im == t.im;
+        if (!keep) {
+            HC_PAR(i, P.C) store_in(tape, i, P.consts[i], mk(0.0), tag);
+            HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? fixed[i] : param_value(i, t), mk(0.0), tag);
+            if (P.t_slot >= 0 && g.lane == 0) store_in(tape, P.t_slot, t, mk(0.0), tag);
+        }
         HC_PAR(i, P.n) store_in(tape, P.var_off + i, x[i], xlo ? (*xlo)[i] : mk(0.0), tag);
         g.sync();
+        tape_prog = sizeof(T) == sizeof(cx) ? &P : nullptr; tape_kind = kind; tape_t = t;
     }
 
     // thread-per-path engines run the segmented interpreters, lane groups the levelised ones
@@ -341,6 +349,7 @@ struct Path {
     template <int K>
     HC_HDN void taylor_inputs(const DevProgram& P, CV tx, cx t, const cx* fixed) {
         CV tape = M.tape;
+        tape_prog = nullptr;  // the series layout overwrites the fp64 input block
         HC_PAR(i, P.C) {
             tape[i * (K + 1)] = P.consts[i];
 #pragma unroll
