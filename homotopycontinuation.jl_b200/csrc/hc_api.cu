@@ -282,7 +282,7 @@ __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, cons
     L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = 0; L.kind = sA.H.kind;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold);
-    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = nullptr;
+    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr;
     const int n = sA.H.n;
     if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
@@ -779,7 +779,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         L.g.init();
         L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = 0; L.kind = A.H.kind;
         carve(L.M, n, P, A.H.tape_cx, (unsigned char*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15), A.cold);
-        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = nullptr;
+        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr;
         if (dtw) for (int i = 0; i < P; ++i) L.M.tw[i] = dtw[i];
         if (what == 3) for (int i = 0; i < K * n; ++i) L.M.tx[i] = dx[i]; else for (int i = 0; i < n; ++i) L.M.x[i] = dx[i];
         if (what == 0) L.eval_f64(L.M.u, nullptr, L.M.x, tt);

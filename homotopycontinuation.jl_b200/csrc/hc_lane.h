@@ -383,7 +383,7 @@ struct Lane : Path<G, S> {
         smax = 0.0; smin = HC_INF;
         for (int l = 0; l < P; ++l) { double r = raw[l]; if (r != 0.0) { smax = jmax(smax, r); smin = jmin(smin, r); } }
         double lam = use_min ? smin / target : smax / target;
-        B::tape_prog = nullptr;  // new weights: cached toric parameters are stale
+        B::tape_prog = B::tay_prog = nullptr;  // new weights: cached toric parameters are stale
         g.sync();
         HC_PAR(l, P) M.tw[l] = raw[l] / lam;
         g.sync();
@@ -466,7 +466,7 @@ struct Lane : Path<G, S> {
         g.sync();
         refined_extended_prec = false; factorized = scaled = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
-        B::tape_prog = nullptr;
+        B::tape_prog = B::tay_prog = nullptr;
         B::tol_acc_limit = pow(O->a, (double)((1 << O->min_newton_iters) - 1)) * hfun(O->a);
         n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_tay1 = n_tay2 = n_tay3 = 0; c_fact = c_ldiv = 0;
         toric_acc = toric_rej = 0;

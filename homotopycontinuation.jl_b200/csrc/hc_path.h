@@ -130,6 +130,7 @@ struct Path {
     bool factorized, scaled;  // MatrixWorkspace flags
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
     const DevProgram* tape_prog; int tape_kind; cx tape_t;  // whose inputs (constants, parameters at t) the fp64 tape holds
+    const DevProgram* tay_prog; int tay_kind; cx tay_t;     // ... and the series tape
     double tol_acc_limit;  // accuracy-limit threshold of check_terminated (options only; cached per path: pow is 300 instructions)
     double min_step_size, min_rel_step_size;  // mutable copies (polyhedral.jl:474-488, endgame_tracker.jl:270)
     // ---- predictor (src/predictor.jl:72-103)
@@ -273,6 +274,7 @@ struct Path {
         HC_PAR(i, P.n) store_in(tape, P.var_off + i, x[i], xlo ? (*xlo)[i] : mk(0.0), tag);
         g.sync();
         tape_prog = sizeof(T) == sizeof(cx) ? &P : nullptr; tape_kind = kind; tape_t = t;
+        tay_prog = nullptr;
     }
 
     // thread-per-path engines run the segmented interpreters, lane groups the levelised ones
@@ -348,34 +350,41 @@ struct Path {
 
     template <int K>
     HC_HDN void taylor_inputs(const DevProgram& P, CV tx, cx t, const cx* fixed) {
+        constexpr int TS = HC_TS(K);
         CV tape = M.tape;
         tape_prog = nullptr;  // the series layout overwrites the fp64 input block
-        HC_PAR(i, P.C) {
-            tape[i * (K + 1)] = P.consts[i];
+        // constants and the parameter series at t are written with all TS coefficients by the first pass of a
+        // predictor update and serve the later passes (same program, same t): ops never write the input block
+        const bool keep = K <= 3 && tay_prog == &P && tay_kind == kind && tay_t.re == t.re && tay_t.im == t.im;
+        if (!keep) {
+            HC_PAR(i, P.C) {
+                tape[i * TS] = P.consts[i];
 #pragma unroll
-            for (int k = 1; k <= K; ++k) tape[i * (K + 1) + k] = mk(0.0);
-        }
-        HC_PAR(i, P.P) {
-            cx c[5];
-            if (fixed) { c[0] = fixed[i]; c[1] = c[2] = c[3] = c[4] = mk(0.0); }
-            else param_series(i, t, c);
-            const int b = (P.param_off + i) * (K + 1);
+                for (int k = 1; k < TS; ++k) tape[i * TS + k] = mk(0.0);
+            }
+            HC_PAR(i, P.P) {
+                cx c[5];
+                if (fixed) { c[0] = fixed[i]; c[1] = c[2] = c[3] = c[4] = mk(0.0); }
+                else param_series(i, t, c);
+                const int b = (P.param_off + i) * TS;
 #pragma unroll
-            for (int k = 0; k <= K; ++k) tape[b + k] = c[k];
-        }
-        if (P.t_slot >= 0 && g.lane == 0) {
-            const int b = P.t_slot * (K + 1);
-            tape[b] = t; tape[b + 1] = mk(1.0);
+                for (int k = 0; k < TS; ++k) tape[b + k] = c[k];
+            }
+            if (P.t_slot >= 0 && g.lane == 0) {
+                const int b = P.t_slot * TS;
+                tape[b] = t; tape[b + 1] = mk(1.0);
 #pragma unroll
-            for (int k = 2; k <= K; ++k) tape[b + k] = mk(0.0);
+                for (int k = 2; k < TS; ++k) tape[b + k] = mk(0.0);
+            }
         }
         HC_PAR(i, P.n) {  // x series: rows 0..K-1 of tx, coefficient K zero padded
-            const int b = (P.var_off + i) * (K + 1);
+            const int b = (P.var_off + i) * TS;
 #pragma unroll
             for (int k = 0; k < K; ++k) tape[b + k] = tx[k * n + i];
             tape[b + K] = mk(0.0);
         }
         g.sync();
+        tay_prog = &P; tay_kind = kind; tay_t = t;
     }
     // u = K-th Taylor coefficient of lambda -> H(x(lambda), t + lambda); tx rows x^0..x^{K-1}
     template <int K>
@@ -388,20 +397,20 @@ struct Path {
             run_taylor<K>(H->Ge);
             HC_PAR(k, H->Ge.nu) {
                 int2 a = H->Ge.u_assign[k];
-                u[a.x] = H->gamma * (tape[a.y * (K + 1) + K - 1] + t * tape[a.y * (K + 1) + K]);
+                u[a.x] = H->gamma * (tape[a.y * HC_TS(K) + K - 1] + t * tape[a.y * HC_TS(K) + K]);
             }
             g.sync();
             taylor_inputs<K>(H->Fe, tx, t, H->F_params);
             run_taylor<K>(H->Fe);
             HC_PAR(k, H->Fe.nu) {
                 int2 a = H->Fe.u_assign[k];
-                u[a.x] = u[a.x] + ((mk(1.0) - t) * tape[a.y * (K + 1) + K] - tape[a.y * (K + 1) + K - 1]);
+                u[a.x] = u[a.x] + ((mk(1.0) - t) * tape[a.y * HC_TS(K) + K] - tape[a.y * HC_TS(K) + K - 1]);
             }
             g.sync();
         } else {  // parameter / coefficient / toric: parameters are series in lambda
             taylor_inputs<K>(H->Fe, tx, t, nullptr);
             run_taylor<K>(H->Fe);
-            HC_PAR(k, H->Fe.nu) { int2 a = H->Fe.u_assign[k]; u[a.x] = tape[a.y * (K + 1) + K]; }
+            HC_PAR(k, H->Fe.nu) { int2 a = H->Fe.u_assign[k]; u[a.x] = tape[a.y * HC_TS(K) + K]; }
             g.sync();
         }
     }

@@ -358,13 +358,17 @@ HC_HDN void run_tape_seg(const FOp* fops, const int2* segs, int n_segs, TV tape)
 }
 
 // ------------------------------------------------------------------ Taylor micro-ops
+// Slot stride of a series tape: orders 1..3 (the tracker's three predictor passes) share the stride 4, so
+// that the input block written by the first pass (constants, parameter series at t) serves all three.
+#define HC_TS(K) ((K) <= 3 ? 4 : (K) + 1)
+
 template <int K>
 struct Ser { cx c[K + 1]; };
 
 template <int K, class TV> HC_HD Ser<K> ser_load(TV tape, int s, bool neg) {
     Ser<K> r;
 #pragma unroll
-    for (int k = 0; k <= K; ++k) r.c[k] = mneg(tape[s * (K + 1) + k], neg);
+    for (int k = 0; k <= K; ++k) r.c[k] = mneg(tape[s * HC_TS(K) + k], neg);
     return r;
 }
 template <int K> HC_HD Ser<K> t_mul(const Ser<K>& x, const Ser<K>& y) {
@@ -435,7 +439,7 @@ HC_HD void exec_mop_taylor(const MOp I, TV tape) {
         default: r = t_div<K>(t_one<K>(), a); break;  // MC_INV, MC_INVNZ (taylor.jl: inv and inv_not_zero share the rule)
     }
 #pragma unroll
-    for (int k = 0; k <= K; ++k) tape[out * (K + 1) + k] = r.c[k];
+    for (int k = 0; k <= K; ++k) tape[out * HC_TS(K) + k] = r.c[k];
 }
 
 template <int K, int G, class TV>
@@ -475,7 +479,7 @@ HC_HD void run_taylor_segment(OC& op, int cnt, TV tape) {
         else if (CLS == MC_DIV) { Ser<K> b = ser_load<K>(tape, I.b, false); r = t_div<K>(a, b); }
         else r = t_div<K>(t_one<K>(), a);
 #pragma unroll
-        for (int k = 0; k <= K; ++k) tape[I.out * (K + 1) + k] = r.c[k];
+        for (int k = 0; k <= K; ++k) tape[I.out * HC_TS(K) + k] = r.c[k];
     }
 }
 template <int K, class TV>
