@@ -104,11 +104,22 @@ void build_program(ProgramH& H, const hc_program_desc* d, bool is_jac) {
     // thread per path: segment scheduling (window of tape-order ops) feeds the segment loops of hc_tape.h;
     // lane groups: rounds of at most `cap` independent ops
     const int cap = tpp ? 0 : env_int("HC_B200_ROUND_CAP", 2 * group_size_for(d->n_vars));
-    // Both programs are segment-scheduled; the evaluation-only program (the one the Taylor interpreter runs
-    // with K + 1 coefficients per slot) has its own knob because its tape size is multiplied by four.
-    // Measured (profiles/r01_sweep.md): window 32 beats tape order by 7-13 % for it as well.
-    const int win = !tpp ? 0 : is_jac ? env_int("HC_B200_SEG_WINDOW", 32) : env_int("HC_B200_SEG_WINDOW_EVAL", 32);
-    H.low = lower_program(d, cap, env_int("HC_B200_PRIO_HEIGHT", 1) != 0, false, win);
+    // Segment-scheduling window: longer segments (fewer dispatches, more independent ops per trip) cost tape
+    // slots.  Take the largest window whose tape stays within 10 % of the window-32 tape: cyclic-7's Jacobian
+    // goes from 65 to 28 segments for 152 -> 158 slots (+3-6 % paths/s), katsura(8) stays at 32 (a full window
+    // would double its tape).  HC_B200_SEG_WINDOW / _SEG_WINDOW_EVAL pin the window instead.
+    const bool prio = env_int("HC_B200_PRIO_HEIGHT", 1) != 0;
+    const char* pin = getenv(is_jac ? "HC_B200_SEG_WINDOW" : "HC_B200_SEG_WINDOW_EVAL");
+    if (!tpp) H.low = lower_program(d, cap, prio, false, 0);
+    else if (pin) H.low = lower_program(d, 0, prio, false, atoi(pin));
+    else {
+        H.low = lower_program(d, 0, prio, false, 32);
+        const int limit = H.low.W + H.low.W / 10;
+        for (int w : {1000, 128, 64}) {
+            LoweredProgram cand = lower_program(d, 0, prio, false, w);
+            if (cand.W <= limit) { H.low = std::move(cand); break; }
+        }
+    }
     const LoweredProgram& L = H.low;
     DevProgram& P = H.dev;
     P.ops = to_dev(L.ops); P.level_end = to_dev(L.level_end); P.consts = to_dev(L.consts);

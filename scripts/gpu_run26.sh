@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out /tmp/ncu
+export PYTHONUNBUFFERED=1
+timeout 1200 ncu --set full --import-source on --clock-control none -k regex:hc_track -s 1 -c 1 -o /tmp/ncu/c7 -f python bench.py --steps 1 --warmup 1 --replicas 160 --no-cpu-baseline > gpurun_out/ncu_v4_c7.log 2>&1; tail -2 gpurun_out/ncu_v4_c7.log
+ncu -i /tmp/ncu/c7.ncu-rep --page raw --csv > gpurun_out/ncu_v4_c7_raw.csv 2>/dev/null
+ncu -i /tmp/ncu/c7.ncu-rep --page source --csv --print-source cuda,sass > /tmp/ncu/c7_src.csv 2>/dev/null
+python scripts/ncu_by_function.py /tmp/ncu/c7_src.csv | cut -c1-170 > gpurun_out/ncu_v4_c7_by_function.txt
+gzip -c /tmp/ncu/c7_src.csv > gpurun_out/ncu_v4_c7_src.csv.gz
+ls -la gpurun_out | tail -5
