@@ -458,17 +458,9 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     B.starts = (const cx*)D.upload<double>(starts, (size_t)2 * n * N);
     B.t1 = t1 ? mk(t1[0], t1[1]) : mk(1.0); B.t0 = t0 ? mk(t0[0], t0[1]) : mk(0.0);
     B.omega_mu = omega_mu ? D.upload<double>(omega_mu, (size_t)2 * N) : nullptr;
-    auto transpose_params = [&](const double* src) {  // (P x N, path-major) -> [i * N + path]
-        std::vector<double> tmp((size_t)2 * P * N);
-        for (long long k = 0; k < N; ++k)
-            for (int i = 0; i < P; ++i) {
-                tmp[2 * ((size_t)i * N + k)] = src[2 * ((size_t)k * P + i)];
-                tmp[2 * ((size_t)i * N + k) + 1] = src[2 * ((size_t)k * P + i) + 1];
-            }
-        return (const cx*)D.upload<double>(tmp.data(), tmp.size());
-    };
-    D.A.H.path_p = path_p ? transpose_params(path_p) : nullptr;
-    D.A.H.path_q = path_q ? transpose_params(path_q) : nullptr;
+    // per-path parameters stay path-major (P values per path, read once per step and lane)
+    D.A.H.path_p = path_p ? (const cx*)D.upload<double>(path_p, (size_t)2 * P * N) : nullptr;
+    D.A.H.path_q = path_q ? (const cx*)D.upload<double>(path_q, (size_t)2 * P * N) : nullptr;
     if (mode == MODE_POLYHEDRAL) {
         B.cell_index = D.upload<int32_t>(cell_index, (size_t)N);
         B.cell_weights = D.upload<double>(cell_weights, (size_t)ncells * P);

@@ -42,8 +42,8 @@ struct DevHomotopy {
     const cx* F_params;        // straight-line: fixed parameters of F
     const cx* p;               // parameter/coefficient: start (t = 1); toric: system coefficients
     const cx* q;               // parameter/coefficient: target (t = 0)
-    const cx* path_p;          // optional per-path start parameters, [i * N + path]
-    const cx* path_q;          // optional per-path target parameters, [i * N + path]
+    const cx* path_p;          // optional per-path start parameters, [path * P + i] (the caller's layout, no host transposition)
+    const cx* path_q;          // optional per-path target parameters, [path * P + i]
     long long N;
     int tape_cx;               // per-path tape region, in cx units
 };
@@ -214,8 +214,8 @@ struct Path {
     }
 
     // ================================================================ homotopy
-    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)i * H->N + pidx] : H->p[i]; }
-    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)i * H->N + pidx] : H->q[i]; }
+    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)pidx * H->P + i] : H->p[i]; }
+    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)pidx * H->P + i] : H->q[i]; }
 
     // Taylor coefficients c[0..4] of parameter i at t
     HC_HD void param_series(int i, cx t, cx* c) const {
