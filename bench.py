@@ -239,6 +239,13 @@ def main():
     ach_tflops = fl / (np.mean(kernel_ms) * 1e-3) / 1e12
     hbm_peak, hbm_src = load_peaks()
     alg_bytes = flops.path_bytes(w.n) * w.N
+    traffic, traffic_src = None, None
+    try:  # measured DRAM bytes per path of this workload's kernel (one ncu --set full capture, profiles/traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tj:
+            traffic, traffic_src = tj["dram_bytes_per_path"] * w.N, tj["capture"]
+    except (OSError, ValueError, KeyError):
+        pass
     line = {
         "metric": "paths tracked/sec", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -253,7 +260,7 @@ def main():
         "gpu_launches": args.steps,
         "clocks": clocks,
         "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": peak_gflops / 1e3, "unit": "TFLOP/s",
-                     "frac": ach_tflops / (peak_gflops / 1e3), "traffic": None,
+                     "frac": ach_tflops / (peak_gflops / 1e3), "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": "hc_dfma_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                      "flops_per_path": fl / w.N,
                      "hbm": {"algorithmic_gbs": alg_bytes / (np.mean(kernel_ms) * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src}},

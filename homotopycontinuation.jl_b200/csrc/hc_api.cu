@@ -193,6 +193,17 @@ __device__ void stage_program(DevProgram& P, unsigned char*& cur, bool fast = fa
     P.U_assign = stage_array(P.U_assign, P.nU, cur);
 }
 
+// homotopy-level constant arrays: start / target parameters, fixed parameters of F and G
+__device__ void stage_params(DevHomotopy& h, unsigned char*& cur) {
+    if (h.kind == H_STRAIGHT_LINE) {
+        h.G_params = stage_array(h.G_params, h.Ge.P > 0 ? h.Ge.P : 1, cur);
+        h.F_params = stage_array(h.F_params, h.Fe.P > 0 ? h.Fe.P : 1, cur);
+    } else {
+        h.p = stage_array(h.p, h.P > 0 ? h.P : 1, cur);
+        if (h.q) h.q = stage_array(h.q, h.P > 0 ? h.P : 1, cur);
+    }
+}
+
 // Persistent tracker: each group of G lanes owns one shared-memory slab, pulls path indices from
 // the device-side queue (the `next_k` counter of threaded_solve, src/solve.jl:641, 660-667) and
 // writes its PathResult by path index (src/solve.jl:637, 670).
@@ -207,6 +218,7 @@ __global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant_
         stage_program(h.Fe, cur);
         stage_program(h.Fj, cur);
         if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur); stage_program(h.Gj, cur); }
+        stage_params(h, cur);
         __syncthreads();
         if (threadIdx.x == 0) sA.H = h;
         __syncthreads();
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(256) hc_track_tpl_kernel(const __grid_constant
         stage_program(h.Fe, cur, true);
         stage_program(h.Fj, cur, true);
         if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur, true); stage_program(h.Gj, cur, true); }
+        stage_params(h, cur);
         __syncthreads();
         if (threadIdx.x == 0) sA.H = h;
         __syncthreads();
@@ -368,6 +381,7 @@ Plan make_plan(const HomotopyH& H, long long N) {
     auto stage_plan = [&](bool fast) {
         p.stage_bytes = program_stage_bytes(H.F->eval, fast) + program_stage_bytes(H.F->jac, fast);
         if (H.dev.kind == H_STRAIGHT_LINE) p.stage_bytes += program_stage_bytes(H.G->eval, fast) + program_stage_bytes(H.G->jac, fast);
+        p.stage_bytes += 2 * 16 * (size_t)std::max(1, std::max(H.dev.P, H.G ? H.G->P : 0));  // stage_params
         p.stage = (p.stage_bytes <= (size_t)env_int("HC_B200_STAGE_MAX", 96 * 1024)) && env_int("HC_B200_STAGE", 1);
         if (!p.stage) p.stage_bytes = 0;
     };

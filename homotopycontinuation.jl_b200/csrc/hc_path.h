@@ -194,7 +194,7 @@ struct Path {
         if (G == 1) {
             int k = 0;
             for (; k + 3 < cnt; k += 4) {
-                int2 a0 = asg[k], a1 = asg[k + 1], a2 = asg[k + 2], a3 = asg[k + 3];
+                int2 a0 = pld<S>(asg + k), a1 = pld<S>(asg + k + 1), a2 = pld<S>(asg + k + 2), a3 = pld<S>(asg + k + 3);
                 cx v0 = tape[a0.y], v1 = tape[a1.y], v2 = tape[a2.y], v3 = tape[a3.y];
                 if (MODE == 0) { dst[a0.x] = v0; dst[a1.x] = v1; dst[a2.x] = v2; dst[a3.x] = v3; }
                 else if (MODE == 1) { dst[a0.x] = s * v0; dst[a1.x] = s * v1; dst[a2.x] = s * v2; dst[a3.x] = s * v3; }
@@ -204,24 +204,24 @@ struct Path {
                 }
             }
             for (; k < cnt; ++k) {
-                int2 a = asg[k];
+                int2 a = pld<S>(asg + k);
                 if (MODE == 0) dst[a.x] = tape[a.y]; else if (MODE == 1) dst[a.x] = s * tape[a.y]; else dst[a.x] = cfma(s, tape[a.y], dst[a.x]);
             }
         } else HC_PAR(k, cnt) {
-            int2 a = asg[k];
+            int2 a = pld<S>(asg + k);
             if (MODE == 0) dst[a.x] = tape[a.y]; else if (MODE == 1) dst[a.x] = s * tape[a.y]; else dst[a.x] = cfma(s, tape[a.y], dst[a.x]);
         }
     }
 
     // ================================================================ homotopy
-    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)pidx * H->P + i] : H->p[i]; }
-    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)pidx * H->P + i] : H->q[i]; }
+    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)pidx * H->P + i] : pld<S>(H->p + i); }
+    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)pidx * H->P + i] : pld<S>(H->q + i); }
 
     // Taylor coefficients c[0..4] of parameter i at t
     HC_HD void param_series(int i, cx t, cx* c) const {
         c[1] = c[2] = c[3] = c[4] = mk(0.0);
         if (kind == H_TORIC) {  // toric_homotopy.jl:145-177, 220-264 (real t >= 0)
-            cx u = H->p[i];
+            cx u = pld<S>(H->p + i);
             double w = M.tw[i], tr = t.re;
             if (tr == 0.0) {
                 c[0] = mk(0.0);
@@ -245,7 +245,7 @@ struct Path {
     // value of parameter i at t (toric t == 0: weights that are exactly 0 survive, toric_homotopy.jl:160-165)
     HC_HD cx param_value(int i, cx t) const {
         if (kind == H_TORIC) {
-            cx u = H->p[i];
+            cx u = pld<S>(H->p + i);
             double w = M.tw[i];
             if (t.re == 0.0) return w == 0.0 ? u : mk(0.0);
             return u * exp(w * log(t.re));
@@ -267,8 +267,8 @@ struct Path {
         // P parameter evaluations (t^w = exp(w log t) each for a toric homotopy) per iteration.
         const bool keep = sizeof(T) == sizeof(cx) && tape_prog == &P && tape_kind == kind && tape_t.re == t.re && tape_t.im == t.im;
         if (!keep) {
-            HC_PAR(i, P.C) store_in(tape, i, P.consts[i], mk(0.0), tag);
-            HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? fixed[i] : param_value(i, t), mk(0.0), tag);
+            HC_PAR(i, P.C) store_in(tape, i, pld<S>(P.consts + i), mk(0.0), tag);
+            HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? pld<S>(fixed + i) : param_value(i, t), mk(0.0), tag);
             if (P.t_slot >= 0 && g.lane == 0) store_in(tape, P.t_slot, t, mk(0.0), tag);
         }
         HC_PAR(i, P.n) store_in(tape, P.var_off + i, x[i], xlo ? (*xlo)[i] : mk(0.0), tag);
@@ -358,13 +358,13 @@ struct Path {
         const bool keep = K <= 3 && tay_prog == &P && tay_kind == kind && tay_t.re == t.re && tay_t.im == t.im;
         if (!keep) {
             HC_PAR(i, P.C) {
-                tape[i * TS] = P.consts[i];
+                tape[i * TS] = pld<S>(P.consts + i);
 #pragma unroll
                 for (int k = 1; k < TS; ++k) tape[i * TS + k] = mk(0.0);
             }
             HC_PAR(i, P.P) {
                 cx c[5];
-                if (fixed) { c[0] = fixed[i]; c[1] = c[2] = c[3] = c[4] = mk(0.0); }
+                if (fixed) { c[0] = pld<S>(fixed + i); c[1] = c[2] = c[3] = c[4] = mk(0.0); }
                 else param_series(i, t, c);
                 const int b = (P.param_off + i) * TS;
 #pragma unroll
@@ -396,21 +396,21 @@ struct Path {
             taylor_inputs<K>(H->Ge, tx, t, H->G_params);
             run_taylor<K>(H->Ge);
             HC_PAR(k, H->Ge.nu) {
-                int2 a = H->Ge.u_assign[k];
+                int2 a = pld<S>(H->Ge.u_assign + k);
                 u[a.x] = H->gamma * (tape[a.y * HC_TS(K) + K - 1] + t * tape[a.y * HC_TS(K) + K]);
             }
             g.sync();
             taylor_inputs<K>(H->Fe, tx, t, H->F_params);
             run_taylor<K>(H->Fe);
             HC_PAR(k, H->Fe.nu) {
-                int2 a = H->Fe.u_assign[k];
+                int2 a = pld<S>(H->Fe.u_assign + k);
                 u[a.x] = u[a.x] + ((mk(1.0) - t) * tape[a.y * HC_TS(K) + K] - tape[a.y * HC_TS(K) + K - 1]);
             }
             g.sync();
         } else {  // parameter / coefficient / toric: parameters are series in lambda
             taylor_inputs<K>(H->Fe, tx, t, nullptr);
             run_taylor<K>(H->Fe);
-            HC_PAR(k, H->Fe.nu) { int2 a = H->Fe.u_assign[k]; u[a.x] = tape[a.y * HC_TS(K) + K]; }
+            HC_PAR(k, H->Fe.nu) { int2 a = pld<S>(H->Fe.u_assign + k); u[a.x] = tape[a.y * HC_TS(K) + K]; }
             g.sync();
         }
     }

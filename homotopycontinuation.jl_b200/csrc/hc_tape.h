@@ -260,6 +260,28 @@ struct PCur<int2, true> {
     HC_D void adv(int k) { a += 8u * (unsigned)k; }
 };
 #endif
+// Read-only program data (constants, output maps, homotopy parameters).  The thread-per-path kernel (S = 2)
+// always runs with them staged in shared memory: ld.shared on a 32-bit address instead of a generic LD.
+template <int S> HC_HD cx pld(const cx* p) {
+#if defined(__CUDA_ARCH__)
+    if (S == 2) {
+        cx v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        return v;
+    }
+#endif
+    return *p;
+}
+template <int S> HC_HD int2 pld(const int2* p) {
+#if defined(__CUDA_ARCH__)
+    if (S == 2) {
+        int2 v;
+        asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        return v;
+    }
+#endif
+    return *p;
+}
 template <class TV> struct ProgInShared { static constexpr bool value = false; };
 template <> struct ProgInShared<SV<cx, 2>> { static constexpr bool value = true; };
 
