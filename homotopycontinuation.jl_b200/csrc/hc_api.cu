@@ -228,44 +228,52 @@ __global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant_
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem + A.stage_bytes + (size_t)(threadIdx.x / G) * A.slab_bytes,
           A.cold + ((size_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G) * A.cold_bytes);
-    L.phase = PH_IDLE;
+    L.phase = PH_IDLE; L.ev = EV_START; L.stop_pending = false;
     const long long N = sA.B.N;
     while (true) {
-        if (L.phase == PH_IDLE) {
-            long long k = 0;
-            if (L.g.lane == 0) k = (long long)atomicAdd(A.queue, 1ULL);
-            k = L.g.bcast(k, 0);
-            if (k >= N) break;
-            L.start_path(k, sA.B, sA.R);
+        if (L.ev != EV_NONE) {  // a lane group handles its events at once (all its lanes are in the same state)
+            L.event_finish(sA.R);
+            long long k = -1;
+            if (L.ev == EV_START) {
+                if (L.g.lane == 0) k = (long long)atomicAdd(A.queue, 1ULL);
+                k = L.g.bcast(k, 0);
+                if (k >= N) break;
+            }
+            L.event_begin(k, k >= 0, sA.B, sA.R);
         }
-        if (L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
+        if (L.ev == EV_NONE && L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
     }
 }
 
-// Main loop of the thread-per-path engines.  Idle lanes of a warp take new paths from the queue
-// together, so that the start-up code of a path (init_newton!, first predictor update) runs
-// converged instead of stalling the warp once per lane.
+// Main loop of the thread-per-path engine.  Lanes park with an event (path finished, toric stage over, free)
+// and the warp handles the parked lanes together once `refill_min` of them wait or nobody can step, so that
+// the once-per-path work (init_newton!, first predictor update, condition number of the endpoint) runs with
+// many lanes instead of stalling the warp once per lane.
 template <class LaneT>
 __device__ __forceinline__ void tpp_loop(LaneT& L, const KArgs& A, const KArgs& sA) {
-    L.phase = PH_IDLE;
+    L.phase = PH_IDLE; L.ev = EV_START; L.stop_pending = false;
     const long long N = sA.B.N;
     const unsigned lane = threadIdx.x & 31u;
     bool drained = false;  // warp-uniform
     while (true) {
-        const unsigned idle = __ballot_sync(0xffffffffu, L.phase == PH_IDLE);
-        const int n_idle = __popc(idle);
-        if (!drained && (n_idle >= A.refill_min || n_idle == 32)) {
-            long long base = 0;
-            if (lane == 0) base = (long long)atomicAdd(A.queue, (unsigned long long)n_idle);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + n_idle >= N) drained = true;
-            if (L.phase == PH_IDLE) {
-                const long long k = base + __popc(idle & ((1u << lane) - 1u));
-                if (k < N) L.start_path(k, sA.B, sA.R);
+        const unsigned pend = __ballot_sync(0xffffffffu, L.ev != EV_NONE);
+        const unsigned act = __ballot_sync(0xffffffffu, L.ev == EV_NONE && L.phase != PH_IDLE);
+        if (pend == 0u && act == 0u) break;
+        if (__popc(pend) >= A.refill_min || act == 0u) {
+            if (L.ev != EV_NONE) L.event_finish(sA.R);
+            const unsigned want = __ballot_sync(0xffffffffu, L.ev == EV_START);
+            long long k = -1;
+            if (want != 0u && !drained) {
+                const int cnt = __popc(want);
+                long long base = 0;
+                if (lane == 0) base = (long long)atomicAdd(A.queue, (unsigned long long)cnt);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base + cnt >= N) drained = true;
+                if (L.ev == EV_START) k = base + __popc(want & ((1u << lane) - 1u));
             }
+            if (L.ev != EV_NONE) L.event_begin(k, k >= 0 && k < N, sA.B, sA.R);
         }
-        if (drained && __all_sync(0xffffffffu, L.phase == PH_IDLE)) break;
-        if (L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
+        if (L.ev == EV_NONE && L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
     }
 }
 
@@ -560,9 +568,17 @@ double run_batch(DeviceBatch& D) {
     unsigned char* base = (unsigned char*)(((uintptr_t)slab.data() + 15) & ~(uintptr_t)15);
     carve(L.M, D.A.H.n, D.A.H.P, D.A.H.tape_cx, base, D.A.cold);
     for (long long k = 0; k < D.N; ++k) {
-        L.phase = PH_IDLE;
-        L.start_path(k, D.A.B, D.A.R);
-        while (L.phase != PH_IDLE) L.iterate(D.A.B, D.A.R);
+        L.phase = PH_IDLE; L.ev = EV_START; L.stop_pending = false;
+        L.event_begin(k, true, D.A.B, D.A.R);
+        while (true) {
+            if (L.ev != EV_NONE) {
+                L.event_finish(D.A.R);
+                if (L.ev == EV_START) break;  // path done
+                L.event_begin(-1, false, D.A.B, D.A.R);
+                continue;
+            }
+            L.iterate(D.A.B, D.A.R);
+        }
     }
     return 0.0;
 #endif

@@ -38,6 +38,13 @@ HC_HD int convert_code(int c) {  // :119-139
 }
 
 enum Phase : int { PH_IDLE = 0, PH_PLAIN, PH_EG, PH_SING, PH_TORIC_A, PH_TORIC_B };
+// Heavy, once-per-path work (tracker / endgame initialisation, the toric restart, the condition number and
+// residual of a finished path) is not run where it arises: the lane parks with an event, and the kernel
+// handles the events of a warp together (event_finish / event_begin below), each kind of work from ONE call
+// site -- otherwise every lane would run its initialisations alone while the other 31 lanes of the warp wait.
+enum Event : int { EV_NONE = 0, EV_START, EV_TORIC_NEXT, EV_FINISH_EG, EV_FINISH_PLAIN, EV_FINISH_POLY_FAILED };
+enum InitKind : int { IK_NONE = 0, IK_TRACKER, IK_EG, IK_POLY_A, IK_POLY_B };
+struct InitReq { int kind; cx t1, t0; double omega, mu, tau, max_init; bool keep_steps, ext; };
 enum Mode : int { MODE_ENDGAME = 0, MODE_TRACKER = 1, MODE_POLYHEDRAL = 2 };
 
 struct DevResults {  // caller's SoA, path-major (fields of src/path_result.jl:76-98)
@@ -72,6 +79,7 @@ struct Lane : Path<G, S> {
     using B::refine_current_solution; using B::eval_f64; using B::vcopy;
 
     int phase, mode;
+    int ev; bool stop_pending; InitReq req;  // parked event, deferred tracking_stopped!, pending tracker initialisation
     // ---- endgame state (src/endgame_tracker.jl:177-215)
     int eg_code; bool singular_endgame; int eg_winding;  // 0 = nothing
     double eg_accuracy, eg_cond; bool eg_singular;
@@ -165,9 +173,8 @@ struct Lane : Path<G, S> {
         skeel(M.egrs, M.egcs, O->scaling_threshold);
     }
     // init!(endgame_tracker, x, t1; omega, mu, extended_precision)  endgame_tracker.jl:260-294
-    HC_HDN void eg_init(double t1, double omega_, double mu_, bool ext) {
-        min_rel_step_size = 0.0;
-        tracker_init(mk(t1), mk(0.0), omega_, mu_, HC_INF, HC_INF, false, ext);
+    // (first half: min_rel_step_size = 0 and the tracker_init request, see eg_request; this is the rest)
+    HC_HDN void eg_init_post() {
         eg_code = convert_code(code);
         singular_endgame = false; jtz_prev = jtz_cur = false;
         val_init(); eg_winding = 0;
@@ -326,7 +333,7 @@ struct Lane : Path<G, S> {
     // Second half of step!(::EndgameTracker) after a regular tracker step  :362-398
     HC_HDN void eg_post(bool step_success) {
         eg_code = convert_code(code);
-        if (eg_code != EG_tracking) { tracking_stopped(); return; }
+        if (eg_code != EG_tracking) { stop_pending = true; return; }  // tracking_stopped! runs in the event round
         jtz_prev = jtz_cur; jtz_cur = is_jump_to_zero;
         double t = st_t().re;
         if (!(t <= O->endgame_start)) return;
@@ -347,7 +354,7 @@ struct Lane : Path<G, S> {
         singular_steps += 1;
         const double lt = 0.25 * sing_t;
         if (!max_steps) {
-            if (code != TC_success) { eg_code = convert_code(code); tracking_stopped(); return; }
+            if (code != TC_success) { eg_code = convert_code(code); stop_pending = true; return; }
             val_update(lt);
             int mh; double mh_err;
             estimate_winding(mh, mh_err);
@@ -458,13 +465,19 @@ struct Lane : Path<G, S> {
     }
 
     // ================================================================ driver
-    HC_HDN void start_path(long long k, const BatchIn& Bt, const DevResults& R) {
+    HC_HD void eg_request(double t1, double omega_, double mu_) {  // init!(endgame_tracker, ...) first half
+        min_rel_step_size = 0.0;
+        req.kind = IK_EG; req.t1 = mk(t1); req.t0 = mk(0.0); req.omega = omega_; req.mu = mu_; req.tau = HC_INF; req.max_init = HC_INF;
+        req.keep_steps = false; req.ext = false;
+    }
+    // a new path: load the start, reset the per-path state, request the first tracker initialisation
+    HC_HDN void start_pre(long long k, const BatchIn& Bt) {
         pidx = k; mode = Bt.mode;
         const int nn = n;
         g.sync();
         HC_PAR(i, nn) M.x[i] = Bt.starts[k * nn + i];
         g.sync();
-        refined_extended_prec = false; factorized = scaled = false;
+        refined_extended_prec = false; factorized = scaled = false; stop_pending = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
         B::tape_prog = B::tay_prog = nullptr;
         B::tol_acc_limit = pow(O->a, (double)((1 << O->min_newton_iters) - 1)) * hfun(O->a);
@@ -474,14 +487,11 @@ struct Lane : Path<G, S> {
         if (Bt.omega_mu) { om = Bt.omega_mu[2 * k]; mu_ = Bt.omega_mu[2 * k + 1]; }
         if (mode == MODE_TRACKER) {
             kind = H->kind;
-            tracker_init(Bt.t1, Bt.t0, om, mu_, HC_INF, HC_INF, false, false);
-            phase = PH_PLAIN;
-            if (code != TC_tracking) finish_plain(R);
+            req.kind = IK_TRACKER; req.t1 = Bt.t1; req.t0 = Bt.t0; req.omega = om; req.mu = mu_; req.tau = HC_INF; req.max_init = HC_INF;
+            req.keep_steps = false; req.ext = false;
         } else if (mode == MODE_ENDGAME) {
             kind = H->kind;
-            eg_init(Bt.t1.re, om, mu_, false);
-            phase = PH_EG;
-            if (eg_code != EG_tracking) finish_eg(R);
+            eg_request(Bt.t1.re, om, mu_);
         } else {  // polyhedral.jl:414-465
             kind = H_TORIC;
             double smin, smax;
@@ -489,23 +499,14 @@ struct Lane : Path<G, S> {
             set_weights(raw, true, 1.0, smin, smax);
             poly_maxw = smax;
             double tend = smax < 10 ? 1.0 : clampd(pow(0.1, 10 / smax), 0.9, 1 - 1e-6);
-            tracker_init(mk(0.0), mk(tend), 20.0, 1e-12, HC_INF, 0.2, false, false);
-            phase = PH_TORIC_A;
-            if (code != TC_tracking) toric_transition(Bt, R);
+            req.kind = IK_POLY_A; req.t1 = mk(0.0); req.t0 = mk(tend); req.omega = 20.0; req.mu = 1e-12; req.tau = HC_INF; req.max_init = 0.2;
+            req.keep_steps = false; req.ext = false;
         }
     }
-    HC_HDN void toric_done(const DevResults& R) {  // polyhedral.jl:491-529
-        if (code != TC_success) { finish_poly_failed(R); return; }
-        toric_acc = accepted_steps; toric_rej = rejected_steps;
-        c_fact += n_fact; c_ldiv += n_ldiv;
-        kind = H_COEFFICIENT;
-        // omega deliberately not passed (:515-521)
-        eg_init(1.0, HC_NAN, mu, false);
-        phase = PH_EG;
-        if (eg_code != EG_tracking) finish_eg(R);
-    }
-    HC_HDN void toric_transition(const BatchIn& Bt, const DevResults& R) {
-        if (phase == PH_TORIC_A && poly_maxw >= 10 && code == TC_success) {  // :466-489
+    // the toric stage of a polyhedral path ended: re-weighted restart (:466-489) or hand-over to the
+    // coefficient homotopy (:491-529)
+    HC_HDN void toric_pre(const BatchIn& Bt) {
+        if (phase == PH_TORIC_A && poly_maxw >= 10 && code == TC_success) {
             double smin, smax;
             const double* raw = Bt.cell_weights + (size_t)Bt.cell_index[pidx] * H->P;
             double t0 = st_target.re;
@@ -513,25 +514,55 @@ struct Lane : Path<G, S> {
             double t_restart = pow(t0, 1 / smin);
             saved_min_step = min_step_size; min_step_size = 0.0;
             c_fact += n_fact; c_ldiv += n_ldiv;
-            tracker_init(mk(t_restart), mk(1.0), omega, mu, 0.1 * t_restart, HC_INF, true, false);
-            phase = PH_TORIC_B;
-            if (code != TC_tracking) { min_step_size = saved_min_step; toric_done(R); }
+            req.kind = IK_POLY_B; req.t1 = mk(t_restart); req.t0 = mk(1.0); req.omega = omega; req.mu = mu; req.tau = 0.1 * t_restart;
+            req.max_init = HC_INF; req.keep_steps = true; req.ext = false;
             return;
         }
         if (phase == PH_TORIC_B) min_step_size = saved_min_step;
-        toric_done(R);
+        if (code != TC_success) { ev = EV_FINISH_POLY_FAILED; return; }
+        toric_acc = accepted_steps; toric_rej = rejected_steps;
+        c_fact += n_fact; c_ldiv += n_ldiv;
+        kind = H_COEFFICIENT;
+        eg_request(1.0, HC_NAN, mu);  // omega deliberately not passed (:515-521)
     }
-    // One flat iteration of an active group.
-    HC_HD void iterate(const BatchIn& Bt, const DevResults& R) {
+    // Event round, part 1: lanes whose path ended write their PathResult and become free (EV_START).
+    HC_HD void event_finish(const DevResults& R) {
+        if (ev == EV_FINISH_EG) {
+            if (stop_pending) { tracking_stopped(); stop_pending = false; }
+            finish_eg(R);
+            ev = EV_START;
+        } else if (ev == EV_FINISH_PLAIN) { finish_plain(R); ev = EV_START; }
+        else if (ev == EV_FINISH_POLY_FAILED) { finish_poly_failed(R); ev = EV_START; }
+    }
+    // Event round, part 2: free lanes take path k (if any is left), toric lanes decide their next stage; all
+    // requested tracker initialisations then run from one call site.
+    HC_HD void event_begin(long long k, bool have_k, const BatchIn& Bt, const DevResults&) {
+        req.kind = IK_NONE;
+        if (ev == EV_START) {
+            if (have_k) start_pre(k, Bt);
+            else { ev = EV_NONE; phase = PH_IDLE; return; }  // queue drained: this lane is done
+        } else if (ev == EV_TORIC_NEXT) toric_pre(Bt);
+        if (req.kind == IK_NONE) return;  // (EV_FINISH_POLY_FAILED was set: handled in the next round)
+        tracker_init(req.t1, req.t0, req.omega, req.mu, req.tau, req.max_init, req.keep_steps, req.ext);
+        ev = EV_NONE;
+        switch (req.kind) {
+            case IK_TRACKER: phase = PH_PLAIN; if (code != TC_tracking) ev = EV_FINISH_PLAIN; break;
+            case IK_EG: eg_init_post(); phase = PH_EG; if (eg_code != EG_tracking) ev = EV_FINISH_EG; break;
+            case IK_POLY_A: phase = PH_TORIC_A; if (code != TC_tracking) ev = EV_TORIC_NEXT; break;
+            default: phase = PH_TORIC_B; if (code != TC_tracking) ev = EV_TORIC_NEXT; break;  // IK_POLY_B
+        }
+    }
+    // One flat iteration of an active lane (ev == EV_NONE, phase != PH_IDLE).
+    HC_HD void iterate(const BatchIn&, const DevResults&) {
         bool do_step = true;
         if (phase == PH_EG) do_step = eg_pre();
         bool ok = false;
         if (do_step) ok = B::tracker_step();
         switch (phase) {
-            case PH_PLAIN: if (code != TC_tracking) finish_plain(R); break;
-            case PH_TORIC_A: case PH_TORIC_B: if (code != TC_tracking) toric_transition(Bt, R); break;
-            case PH_SING: sing_post(); if (eg_code != EG_tracking) finish_eg(R); break;
-            case PH_EG: if (do_step) eg_post(ok); if (eg_code != EG_tracking) finish_eg(R); break;
+            case PH_PLAIN: if (code != TC_tracking) ev = EV_FINISH_PLAIN; break;
+            case PH_TORIC_A: case PH_TORIC_B: if (code != TC_tracking) ev = EV_TORIC_NEXT; break;
+            case PH_SING: sing_post(); if (eg_code != EG_tracking) ev = EV_FINISH_EG; break;
+            case PH_EG: if (do_step) eg_post(ok); if (eg_code != EG_tracking) ev = EV_FINISH_EG; break;
             default: break;
         }
     }
