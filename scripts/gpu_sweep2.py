@@ -19,7 +19,7 @@ import hcb200  # noqa: E402,F401
 from hcb200 import capi, lib, sharding  # noqa: E402
 
 KEYS = ("HC_B200_ENGINE", "HC_B200_GROUP", "HC_B200_BLOCK", "HC_B200_BLOCKS_PER_SM", "HC_B200_REFILL_MIN", "HC_B200_PATHS_PER_LANE",
-        "HC_B200_TAPE_PAIRS", "HC_B200_STAGE", "HC_B200_TPP_MAX_N", "HC_B200_SMEM_TAPE")
+        "HC_B200_TAPE_PAIRS", "HC_B200_POST_FRAC", "HC_B200_CARVEOUT", "HC_B200_SEG_WINDOW", "HC_B200_SEG_WINDOW_EVAL", "HC_B200_STAGE", "HC_B200_TPP_MAX_N", "HC_B200_SMEM_TAPE")
 
 
 def main():
