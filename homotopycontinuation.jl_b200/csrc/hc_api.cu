@@ -844,6 +844,53 @@ int32_t hc_toric_set_weights(void* Hv, const double* w) {
     return 0;
 }
 
+#ifdef HC_HOST_SIM
+// Test hook (tests/host_sim only): lowers a tape with the given segment window and checks the invariants the
+// segment interpreters rely on.  Returns 0 if they hold, a positive code otherwise; stats = {ops, segments, W}.
+int32_t hc_sim_check_lowering(const hc_program_desc* d, int32_t window, int32_t* stats) {
+    try {
+        const LoweredProgram L = lower_program(d, 0, true, false, window);
+        const int Nin = L.var_off + L.n;
+        std::vector<char> written((size_t)L.W, 0);
+        for (int i = 0; i < Nin; ++i) written[i] = 1;
+        size_t f = 0, op = 0;
+        long long total = 0;
+        for (const int2& sg : L.segs) {
+            const int cls = sg.x & 7;
+            std::vector<uint32_t> outs;
+            for (int k = 0; k < sg.y; ++k, ++op) {
+                if (op >= L.ops.size() || f >= L.fops.size()) return 1;
+                const MOp& m = L.ops[op];
+                const FOp& F = L.fops[f];
+                if ((int)((m.w0 >> 16) & 31) != sg.x) return 2;                       // segment key == op key
+                if (F.out != (m.w0 & 0xffff) || F.a != (m.w1 & 0xffff)) return 3;     // fast format mirrors the packed one
+                const bool useB = cls == MC_MM || cls == MC_MA || cls == MC_M || cls == MC_DIV;
+                const bool useC = cls == MC_MM || cls == MC_MA || cls == MC_AA;
+                std::vector<uint32_t> ins{F.a};
+                if (useB) { if (F.b != (m.w1 >> 16)) return 3; ins.push_back(F.b); }
+                if (useC) { if (F.c != (m.w2 & 0xffff)) return 3; ins.push_back(F.c); }
+                if (cls == MC_MM) { if (L.fops[f + 1].a != (m.w2 >> 16)) return 3; ins.push_back(L.fops[f + 1].a); }
+                for (uint32_t s_ : ins) {
+                    if (s_ >= (uint32_t)L.W || !written[s_]) return 4;                // operands exist before the segment...
+                    for (uint32_t o : outs) if (o == s_) return 5;                    // ...and are not produced inside it
+                }
+                if (F.out < (uint32_t)Nin || F.out >= (uint32_t)L.W) return 6;        // never writes the input block
+                for (uint32_t o : outs) if (o == F.out) return 7;                     // no two ops of a segment share a slot
+                outs.push_back(F.out);
+                f += cls == MC_MM ? 2 : 1;
+            }
+            for (uint32_t o : outs) written[o] = 1;
+            total += sg.y;
+        }
+        if (op != L.ops.size() || f != L.fops.size() || total != (long long)L.ops.size()) return 8;
+        for (const int2& a : L.u_assign) if (a.y < 0 || a.y >= L.W || !written[a.y]) return 9;
+        for (const int2& a : L.U_assign) if (a.y < 0 || a.y >= L.W || !written[a.y]) return 9;
+        if (stats) { stats[0] = (int32_t)L.ops.size(); stats[1] = (int32_t)L.segs.size(); stats[2] = L.W; }
+        return 0;
+    } catch (const std::string& e) { fail(e); return -1; }
+}
+#endif
+
 double hc_dfma_peak(int32_t iters) {
 #ifndef HC_HOST_SIM
     try {

@@ -101,3 +101,27 @@ def test_system_sizes(oracle, sim, k):
         out.append(H.track_batch(td.start_solutions()[:24]))
     assert_batches_match(*out)
     assert abs(int(out[0].accepted_steps.sum()) - int(out[1].accepted_steps.sum())) <= 0.02 * out[0].accepted_steps.sum()
+
+
+@pytest.mark.parametrize("window", [1, 8, 32, 64, 1000])
+def test_segment_scheduler_invariants(sim, window):
+    """The lowering the thread-per-path engine runs (hc_lower.h): every op's operands exist before its segment
+    starts and are not produced inside it, segments are runs of one (class, sign) key, the fast format mirrors
+    the packed one, nothing writes the input block -- for the tapes of all five configs."""
+    import ctypes as C
+    from hcb200 import workloads
+    lib = sim.raw
+    lib.hc_sim_check_lowering.restype = C.c_int32
+    lib.hc_sim_check_lowering.argtypes = [C.POINTER(capi.ProgramDesc), C.c_int32, C.POINTER(C.c_int32)]
+    progs = []
+    for S in (systems.katsura(8), systems.cyclic(7), systems.tritangents(), systems.cyclooctane(), systems.biochem1()):
+        progs += [S.eval_program, S.jac_program]
+    for P in progs:
+        keep = []
+        d = sim._program_desc(P, keep)
+        stats = (C.c_int32 * 3)()
+        rc = lib.hc_sim_check_lowering(C.byref(d), window, stats)
+        assert rc == 0, (rc, window)
+        assert stats[0] >= 1 and 1 <= stats[1] <= stats[0]
+        if window == 1:
+            assert stats[1] == stats[0]          # tape order: one op per segment
