@@ -8,6 +8,7 @@ plain-data structs.  Product code only ever instantiates it on ``libhc_b200.so``
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 
 import numpy as np
@@ -142,6 +143,9 @@ class BatchResults:
             np.zeros((N, n), np.complex128), f(N), f(N, n), np.zeros(N, np.uint8), f(N), f(N),
             np.zeros(N, np.int32), np.zeros(N, np.int32), np.zeros(N, np.int32), np.zeros(N, np.uint8),
             np.zeros((N, 8), np.int64))
+
+    def arrays(self) -> list:
+        return [getattr(self, f.name) for f in dataclasses.fields(self) if isinstance(getattr(self, f.name), np.ndarray)]
 
     def desc(self) -> ResultsDesc:
         u8 = lambda a: a.ctypes.data_as(c_uint8_p)
@@ -293,11 +297,13 @@ class HomotopyHandle:
 
     # ---- batched tracking
     def track_batch(self, starts, options: Options | None = None, mode: int = 0, t1=1.0, t0=0.0,
-                    path_p=None, path_q=None, omega_mu=None, nthreads: int = 1) -> BatchResults:
+                    path_p=None, path_q=None, omega_mu=None, nthreads: int = 1, out: BatchResults | None = None) -> BatchResults:
+        """`out`: result arrays of an earlier call (or BatchResults.allocate) to be overwritten -- what a host
+        that solves repeatedly does with its preallocated, page-locked result vectors."""
         starts = np.ascontiguousarray(np.asarray(starts, dtype=np.complex128).reshape(-1, self.n))
         N = starts.shape[0]
         opts = options if options is not None else self.api.default_options()
-        res = BatchResults.allocate(self.n, N)
+        res = _out_or_new(out, self.n, N)
         d = res.desc()
         t1a, t0a = _cflat([t1]), _cflat([t0])
         pp = _cflat(np.asarray(path_p).reshape(-1), N * self.P) if path_p is not None else None
@@ -311,15 +317,24 @@ class HomotopyHandle:
         return res
 
 
+def _out_or_new(out: "BatchResults | None", n: int, N: int) -> BatchResults:
+    if out is None:
+        return BatchResults.allocate(n, N)
+    if out.n != n or out.N != N:
+        raise ValueError(f"out holds {out.N} paths of dimension {out.n}, the batch has {N} of dimension {n}")
+    return out
+
+
 def polyhedral_track_batch(api: CApi, Htoric: HomotopyHandle, Hcoeff: HomotopyHandle, starts, cell_index,
-                           cell_weights, options: Options | None = None, nthreads: int = 1) -> BatchResults:
+                           cell_weights, options: Options | None = None, nthreads: int = 1,
+                           out: BatchResults | None = None) -> BatchResults:
     n, P = Htoric.n, Htoric.P
     starts = np.ascontiguousarray(np.asarray(starts, dtype=np.complex128).reshape(-1, n))
     N = starts.shape[0]
     ci = np.ascontiguousarray(cell_index, dtype=np.int32)
     cw = np.ascontiguousarray(cell_weights, dtype=np.float64).reshape(-1, P)
     opts = options if options is not None else api.default_options()
-    res = BatchResults.allocate(n, N)
+    res = _out_or_new(out, n, N)
     d = res.desc()
     rc = api._polyhedral_track_batch(Htoric.handle, Hcoeff.handle, C.byref(opts), N, _dp(starts.view(np.float64)),
                                      _ip(ci), _dp(cw), cw.shape[0], C.byref(d), nthreads)

@@ -844,6 +844,28 @@ int32_t hc_toric_set_weights(void* Hv, const double* w) {
     return 0;
 }
 
+int32_t hc_host_register(void* p, int64_t bytes) {
+#ifndef HC_HOST_SIM
+    if (!p || bytes <= 0) return 0;
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+#else
+    (void)p; (void)bytes;
+#endif
+    return 0;
+}
+int32_t hc_host_unregister(void* p) {
+#ifndef HC_HOST_SIM
+    if (!p) return 0;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+#else
+    (void)p;
+#endif
+    return 0;
+}
+
 #ifdef HC_HOST_SIM
 // Test hook (tests/host_sim only): lowers a tape with the given segment window and checks the invariants the
 // segment interpreters rely on.  Returns 0 if they hold, a positive code otherwise; stats = {ops, segments, W}.

@@ -39,6 +39,8 @@ def load(device: int | None = None) -> CApi:
         lib.hc_resident_run.restype, lib.hc_resident_run.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]
         lib.hc_resident_fetch.restype, lib.hc_resident_fetch.argtypes = C.c_int32, [C.c_void_p, C.POINTER(ResultsDesc)]
         lib.hc_resident_destroy.restype, lib.hc_resident_destroy.argtypes = None, [C.c_void_p]
+        lib.hc_host_register.restype, lib.hc_host_register.argtypes = C.c_int32, [C.c_void_p, C.c_int64]
+        lib.hc_host_unregister.restype, lib.hc_host_unregister.argtypes = C.c_int32, [C.c_void_p]
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         rc = lib.hc_init(device)
@@ -46,6 +48,28 @@ def load(device: int | None = None) -> CApi:
             raise RuntimeError("hc_init failed: " + lib.hc_last_error().decode())
         _api = api
     return _api
+
+
+def pin(*arrays) -> list:
+    """Page-locks caller-owned numpy arrays (hc_host_register) so that hc_track_batch's copies are DMA transfers.
+    Returns the arrays that were registered; pass them to unpin() before they are freed."""
+    raw = load().raw
+    done = []
+    for a in arrays:
+        if a is None or a.nbytes == 0:
+            continue
+        if not a.flags.c_contiguous:
+            raise ValueError("only contiguous arrays can be page-locked")
+        if raw.hc_host_register(a.ctypes.data, a.nbytes) != 0:
+            raise RuntimeError("hc_host_register failed: " + raw.hc_last_error().decode())
+        done.append(a)
+    return done
+
+
+def unpin(arrays) -> None:
+    raw = load().raw
+    for a in arrays:
+        raw.hc_host_unregister(a.ctypes.data)
 
 
 def last_error() -> str:

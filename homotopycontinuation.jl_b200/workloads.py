@@ -44,11 +44,12 @@ class Workload:
                         None if self.path_q is None else self.path_q[lo:hi],
                         None if self.cell_index is None else self.cell_index[lo:hi], self.cell_weights, self.costs, {})
 
-    def track(self, api, handles, options=None, nthreads=1):
+    def track(self, api, handles, options=None, nthreads=1, out=None):
         if self.mode == 2:
             return capi.polyhedral_track_batch(api, handles["H"], handles["Hcoeff"], self.starts, self.cell_index,
-                                               self.cell_weights, options, nthreads)
-        return handles["H"].track_batch(self.starts, options=options, mode=self.mode, path_q=self.path_q, nthreads=nthreads)
+                                               self.cell_weights, options, nthreads, out=out)
+        return handles["H"].track_batch(self.starts, options=options, mode=self.mode, path_q=self.path_q, nthreads=nthreads,
+                                        out=out)
 
 
 def katsura8(replicas: int = 1) -> Workload:

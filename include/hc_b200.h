@@ -139,6 +139,12 @@ int32_t hc_evaluate_and_jacobian(void* H, const double* x, const double* t, doub
 int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double* u);
 int32_t hc_toric_set_weights(void* H, const double* w);
 
+/* Page-locks (cudaHostRegister) / releases caller-owned host buffers -- start solutions, parameters, the arrays of
+ * hc_results -- so that the copies of hc_track_batch run as DMA transfers.  Optional; the Julia host would pin
+ * the arrays of its result struct once per solve (reference: results are plain Julia Vectors, src/solve.jl:637). */
+int32_t hc_host_register(void* p, int64_t bytes);
+int32_t hc_host_unregister(void* p);
+
 /* fp64 FMA pipe microbenchmark (roofline denominator): returns achieved GFLOP/s */
 double hc_dfma_peak(int32_t iters);
 

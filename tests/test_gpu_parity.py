@@ -109,6 +109,31 @@ def test_lane_refill_is_deterministic(gpu):
     assert (r.accepted_steps.reshape(R, 256) == r.accepted_steps[:256][None]).all()
 
 
+def test_page_locked_reused_result_buffers(gpu):
+    """hc_host_register'ed inputs and a reused result struct (what bench.py's e2e arm and a Julia host that keeps
+    its Result vectors do) give bit-identical results to freshly allocated pageable buffers; stale contents of
+    the reused arrays are overwritten."""
+    td, H = straight_line(gpu, systems.katsura(6), 0.4 + 1.3j)
+    S = np.ascontiguousarray(np.tile(td.start_solutions(), (8, 1)))
+    ref = H.track_batch(S)
+    out = capi.BatchResults.allocate(H.n, S.shape[0])
+    for a in out.arrays():
+        a.view(np.uint8)[...] = 0xA5
+    pinned = lib.pin(S, *out.arrays())
+    assert len(pinned) == 1 + len(out.arrays())
+    lib.pin(S)  # registering twice is not an error
+    try:
+        for _ in range(2):
+            r = H.track_batch(S, out=out)
+            assert r is out
+            for a, b in zip(ref.arrays(), out.arrays()):
+                assert np.array_equal(a, b, equal_nan=a.dtype.kind in "fc")
+    finally:
+        lib.unpin(pinned)
+    with pytest.raises(ValueError):
+        H.track_batch(S[:5], out=out)
+
+
 def test_parameter_sweep(oracle, gpu):  # BASELINE.json configs[4] at test size
     F = systems.biochem1()
     rng = np.random.default_rng(5)
