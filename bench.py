@@ -216,7 +216,11 @@ def main():
     if w.cell_index is not None:
         w.cell_index = np.ascontiguousarray(w.cell_index, dtype=np.int32)
     out = capi.BatchResults.allocate(w.n, w.N)
-    pinned = [] if os.environ.get("HC_BENCH_PAGEABLE") else lib.pin(w.starts, w.path_q, w.cell_index, *out.arrays())
+    if w.sweep_starts is not None:   # many_solve entry point: k starts + one parameter column per point cross the bus
+        inputs = [w.sweep_starts, w.sweep_q]
+    else:
+        inputs = [w.starts, w.path_q, w.cell_index]
+    pinned = [] if os.environ.get("HC_BENCH_PAGEABLE") else lib.pin(*inputs, *out.arrays())
     for _ in range(2):
         w.track(api, handles, opts, out=out)
     barrier()
@@ -268,6 +272,7 @@ def main():
                    "engine": "thread-per-path" if tm.lanes == 1 else f"{tm.lanes}-lane group per path",
                    "grid": tm.grid, "block": tm.block, "success_paths": n_ok, "class_counts": counts, "expected": wg.expected},
         "e2e": {"value": e2e, "unit": "paths/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(tm.d2h_bytes),
+                "entry_point": "hc_track_sweep" if w.sweep_starts is not None else ("hc_polyhedral_track_batch" if w.mode == 2 else "hc_track_batch"),
                 "host_buffers": "pageable" if not pinned else "page-locked once (hc_host_register), reused every step",
                 "results_identical_to_resident_arm": e2e_same},
         "gpu_launches": args.steps,

@@ -176,9 +176,17 @@ class CApi:
         f("evaluate_and_jacobian", C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p])
         f("taylor", C.c_int32, [C.c_void_p, C.c_int32, c_double_p, c_double_p, c_double_p])
         f("toric_set_weights", C.c_int32, [C.c_void_p, c_double_p])
+        # device-side start generation: entry points of libhc_b200 only (the oracle takes explicit starts)
+        f("track_total_degree", C.c_int32, [C.c_void_p, C.POINTER(Options), c_int32_p, C.c_int64, C.c_int64,
+                                            C.POINTER(ResultsDesc)], optional=True)
+        f("track_sweep", C.c_int32, [C.c_void_p, C.POINTER(Options), C.c_int64, c_double_p, C.c_int64, c_double_p,
+                                     C.POINTER(ResultsDesc)], optional=True)
 
-    def _fn(self, name, restype, argtypes):
-        fn = getattr(self.lib, self.prefix + name)
+    def _fn(self, name, restype, argtypes, optional=False):
+        fn = getattr(self.lib, self.prefix + name, None) if optional else getattr(self.lib, self.prefix + name)
+        if fn is None:
+            setattr(self, "_" + name, None)
+            return
         fn.restype, fn.argtypes = restype, argtypes
         setattr(self, "_" + name, fn)
 
@@ -315,6 +323,55 @@ class HomotopyHandle:
         if rc:
             raise RuntimeError(f"track_batch failed ({rc})")
         return res
+
+
+def _last_error(api: CApi) -> str:
+    try:
+        fn = getattr(api.lib, api.prefix + "last_error")
+        fn.restype = C.c_char_p
+        return fn().decode()
+    except AttributeError:
+        return ""
+
+
+def track_total_degree(H: "HomotopyHandle", degrees, first: int = 0, count: int | None = None,
+                       options: Options | None = None, out: "BatchResults | None" = None) -> "BatchResults":
+    """Paths first .. first + count - 1 of the total-degree start system, start solutions made on the device
+    (hc_track_total_degree; order of TotalDegreeStartSolutionsIterator, reference src/total_degree.jl:235-262)."""
+    api = H.api
+    if api._track_total_degree is None:
+        raise RuntimeError("this library has no device-side start generation")
+    deg = np.ascontiguousarray(degrees, dtype=np.int32)
+    if deg.shape != (H.n,):
+        raise ValueError(f"need {H.n} degrees")
+    total = int(np.prod(deg.astype(object)))
+    N = total - first if count is None else int(count)
+    opts = options if options is not None else api.default_options()
+    res = _out_or_new(out, H.n, N)
+    d = res.desc()
+    rc = api._track_total_degree(H.handle, C.byref(opts), _ip(deg), int(first), N, C.byref(d))
+    if rc:
+        raise RuntimeError(f"track_total_degree failed ({rc}): {_last_error(api)}")
+    return res
+
+
+def track_sweep(H: "HomotopyHandle", starts, target_parameters, options: Options | None = None,
+                out: "BatchResults | None" = None) -> "BatchResults":
+    """The same S start solutions tracked to each of M target parameter vectors (reference many_solve,
+    src/solve.jl:815-881).  Result row j * S + s = start s to parameter point j."""
+    api = H.api
+    if api._track_sweep is None:
+        raise RuntimeError("this library has no sweep entry point")
+    starts = np.ascontiguousarray(np.asarray(starts, dtype=np.complex128).reshape(-1, H.n))
+    q = np.ascontiguousarray(np.asarray(target_parameters, dtype=np.complex128).reshape(-1, H.P))
+    S, M = starts.shape[0], q.shape[0]
+    opts = options if options is not None else api.default_options()
+    res = _out_or_new(out, H.n, S * M)
+    d = res.desc()
+    rc = api._track_sweep(H.handle, C.byref(opts), S, _dp(starts.view(np.float64)), M, _dp(q.view(np.float64)), C.byref(d))
+    if rc:
+        raise RuntimeError(f"track_sweep failed ({rc}): {_last_error(api)}")
+    return res
 
 
 def _out_or_new(out: "BatchResults | None", n: int, N: int) -> BatchResults:

@@ -312,7 +312,7 @@ __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, cons
     sA = A;
     Lane<1, 0> L;
     L.g.init();
-    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = 0; L.kind = sA.H.kind;
+    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = L.prow = 0; L.kind = sA.H.kind;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold);
     L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr;
     const int n = sA.H.n;
@@ -466,9 +466,17 @@ struct DeviceBatch {  // device-resident inputs and outputs of one batch
     }
 };
 
+// How the start solutions (and the rows of the per-path parameters) of a batch are produced.
+struct StartGen {
+    long long start_rows = 0;           // > 0: `starts` holds this many rows, path k starts from row k % start_rows
+    long long param_div = 0;            // > 0: the per-path parameter arrays hold one row per param_div consecutive paths
+    const int32_t* degrees = nullptr;   // total degree: no `starts` at all
+    long long td_first = 0;
+};
+
 void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1,
                  const double* t0, const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
-                 const double* cell_weights, int ncells) {
+                 const double* cell_weights, int ncells, const StartGen& sg = StartGen()) {
     D.H = H; D.mode = mode; D.N = N; D.n = H->dev.n;
     const int n = D.n, P = H->dev.P;
     memset(&D.A, 0, sizeof(D.A));
@@ -477,12 +485,32 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     D.A.O = to_dev_options(o);
     BatchIn& B = D.A.B;
     B.mode = mode; B.N = N;
-    B.starts = (const cx*)D.upload<double>(starts, (size_t)2 * n * N);
+    if (sg.degrees) {
+        // roots of unity per variable, exactly the values the host iterator yields (cis(2 pi j / d), total_degree.jl:258)
+        std::vector<double> roots; std::vector<int> deg(n);
+        double total = 1.0;
+        for (int i = 0; i < n; ++i) {
+            const int d = sg.degrees[i];
+            if (d < 1) throw std::string("total degree start system: degrees must be >= 1");
+            deg[i] = d; total *= d;
+            for (int j = 0; j < d; ++j) { const double a = 2.0 * M_PI * j / d; roots.push_back(cos(a)); roots.push_back(sin(a)); }
+        }
+        if (sg.td_first < 0 || (double)sg.td_first + (double)N > total) throw std::string("total degree start system: path range exceeds prod(degrees)");
+        B.td_roots = (const cx*)D.upload<double>(roots.data(), roots.size());
+        B.td_degrees = D.upload<int>(deg.data(), (size_t)n);
+        B.td_first = sg.td_first;
+    } else {
+        if (!starts) throw std::string("start solutions missing");
+        B.start_mod = sg.start_rows;
+        B.starts = (const cx*)D.upload<double>(starts, (size_t)2 * n * (sg.start_rows > 0 ? sg.start_rows : N));
+    }
+    B.param_div = sg.param_div;
+    const long long prow = sg.param_div > 0 ? (N + sg.param_div - 1) / sg.param_div : N;
     B.t1 = t1 ? mk(t1[0], t1[1]) : mk(1.0); B.t0 = t0 ? mk(t0[0], t0[1]) : mk(0.0);
     B.omega_mu = omega_mu ? D.upload<double>(omega_mu, (size_t)2 * N) : nullptr;
     // per-path parameters stay path-major (P values per path, read once per step and lane)
-    D.A.H.path_p = path_p ? (const cx*)D.upload<double>(path_p, (size_t)2 * P * N) : nullptr;
-    D.A.H.path_q = path_q ? (const cx*)D.upload<double>(path_q, (size_t)2 * P * N) : nullptr;
+    D.A.H.path_p = path_p ? (const cx*)D.upload<double>(path_p, (size_t)2 * P * prow) : nullptr;
+    D.A.H.path_q = path_q ? (const cx*)D.upload<double>(path_q, (size_t)2 * P * prow) : nullptr;
     if (mode == MODE_POLYHEDRAL) {
         B.cell_index = D.upload<int32_t>(cell_index, (size_t)N);
         B.cell_weights = D.upload<double>(cell_weights, (size_t)ncells * P);
@@ -616,13 +644,13 @@ HomotopyH* merged_polyhedral(HomotopyH* toric, HomotopyH* coeff) {
 
 int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1, const double* t0,
                const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
-               const double* cell_weights, int ncells, hc_results* out) {
+               const double* cell_weights, int ncells, hc_results* out, const StartGen& sg = StartGen()) {
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         if (N <= 0) return 0;
         double tA = now_ms();
         DeviceBatch D;
-        setup_batch(D, H, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, cell_index, cell_weights, ncells);
+        setup_batch(D, H, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, cell_index, cell_weights, ncells, sg);
 #ifndef HC_HOST_SIM
         CK(cudaDeviceSynchronize());
 #endif
@@ -746,6 +774,23 @@ int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* 
     } catch (const std::string& e) { return fail(e); }
 }
 
+int32_t hc_track_total_degree(void* H, const hc_options* o, const int32_t* degrees, int64_t first, int64_t N, hc_results* out) {
+    HomotopyH* h = (HomotopyH*)H;
+    if (!degrees) return fail("degrees missing");
+    if (h->dev.kind == H_TORIC) return fail("toric homotopies are tracked through hc_polyhedral_track_batch");
+    StartGen sg; sg.degrees = degrees; sg.td_first = first;
+    return track_impl(h, o, MODE_ENDGAME, N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, out, sg);
+}
+
+int32_t hc_track_sweep(void* H, const hc_options* o, int64_t S, const double* starts, int64_t M, const double* target_params,
+                       hc_results* out) {
+    HomotopyH* h = (HomotopyH*)H;
+    if (h->dev.kind != H_PARAMETER) return fail("hc_track_sweep needs a parameter homotopy");
+    if (S <= 0 || M < 0 || !starts || !target_params) return fail("hc_track_sweep: starts and target parameters are required");
+    StartGen sg; sg.start_rows = S; sg.param_div = S;
+    return track_impl(h, o, MODE_ENDGAME, S * M, starts, nullptr, nullptr, nullptr, target_params, nullptr, nullptr, nullptr, 0, out, sg);
+}
+
 void hc_get_timing(hc_timing* t) { *t = g_timing; }
 
 void* hc_resident_create(void* H, void* Hcoeff, const hc_options* o, int32_t mode, int64_t N, const double* starts, const double* t1,
@@ -810,7 +855,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         std::vector<unsigned char> mem(slab + 16);
         Lane<1, 0> L;
         L.g.init();
-        L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = 0; L.kind = A.H.kind;
+        L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = L.prow = 0; L.kind = A.H.kind;
         carve(L.M, n, P, A.H.tape_cx, (unsigned char*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15), A.cold);
         L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr;
         if (dtw) for (int i = 0; i < P; ++i) L.M.tw[i] = dtw[i];

@@ -59,6 +59,12 @@ struct BatchIn {
     int mode;
     long long N;
     const cx* starts;          // path-major: starts[path * n + i]
+    // start solutions produced on the device instead of streamed in:
+    long long start_mod;       // > 0: path k starts from row k % start_mod of `starts` (many_solve: one start set for every parameter point)
+    long long param_div;       // > 0: path k reads row k / param_div of the per-path parameters
+    const cx* td_roots;        // total degree: roots of unity cis(2 pi j / d_i), j < d_i, variable after variable (host-made table)
+    const int* td_degrees;     // total degree: d_1 .. d_n; path k <-> mixed-radix digits of td_first + k, first index fastest
+    long long td_first;
     cx t1, t0;
     const double* omega_mu;    // optional 2 x N
     const int* cell_index;     // polyhedral: N
@@ -69,7 +75,7 @@ template <int G, int S>
 struct Lane : Path<G, S> {
     using B = Path<G, S>;
     using CV = typename B::CV; using RV = typename B::RV;
-    using B::g; using B::H; using B::O; using B::M; using B::n; using B::pidx; using B::kind;
+    using B::g; using B::H; using B::O; using B::M; using B::n; using B::pidx; using B::prow; using B::kind;
     using B::code; using B::accuracy; using B::omega; using B::mu; using B::tau; using B::winding;
     using B::extended_prec; using B::used_extended_prec; using B::refined_extended_prec; using B::keep_extended_prec;
     using B::accepted_steps; using B::rejected_steps; using B::factorized; using B::scaled;
@@ -475,7 +481,21 @@ struct Lane : Path<G, S> {
         pidx = k; mode = Bt.mode;
         const int nn = n;
         g.sync();
-        HC_PAR(i, nn) M.x[i] = Bt.starts[k * nn + i];
+        prow = Bt.param_div > 0 ? k / Bt.param_div : k;
+        if (Bt.td_roots) {  // TotalDegreeStartSolutionsIterator  total_degree.jl:235-262
+            long long idx = Bt.td_first + k;
+            int off = 0;
+            for (int i = 0; i < nn; ++i) {
+                const int d = Bt.td_degrees[i];
+                const int j = (int)(idx % d);
+                idx /= d;
+                if (i % G == g.lane) M.x[i] = Bt.td_roots[off + j];
+                off += d;
+            }
+        } else {
+            const long long row = Bt.start_mod > 0 ? k % Bt.start_mod : k;
+            HC_PAR(i, nn) M.x[i] = Bt.starts[row * nn + i];
+        }
         g.sync();
         refined_extended_prec = false; factorized = scaled = false; stop_pending = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;

@@ -122,6 +122,7 @@ struct Path {
     PathMem<S> M;
     int n;
     long long pidx;
+    long long prow;  // row of the per-path parameter arrays this path reads (pidx, or pidx / param_div for sweeps)
     int kind;  // current homotopy kind (polyhedral paths switch TORIC -> COEFFICIENT)
     // ---- tracker state (src/tracker.jl:307-338)
     cx st_start, st_target; double st_absd; bool st_forward; double st_s, st_sp;  // SegmentStepper
@@ -214,8 +215,8 @@ struct Path {
     }
 
     // ================================================================ homotopy
-    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)pidx * H->P + i] : pld<S>(H->p + i); }
-    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)pidx * H->P + i] : pld<S>(H->q + i); }
+    HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)prow * H->P + i] : pld<S>(H->p + i); }
+    HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)prow * H->P + i] : pld<S>(H->q + i); }
 
     // Taylor coefficients c[0..4] of parameter i at t
     HC_HD void param_series(int i, cx t, cx* c) const {

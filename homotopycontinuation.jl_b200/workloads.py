@@ -26,6 +26,10 @@ class Workload:
     cell_weights: np.ndarray | None = None
     costs: dict = field(default_factory=dict)
     expected: dict = field(default_factory=dict)
+    # many-parameter sweeps (many_solve): the k start solutions and one target parameter row per POINT; `starts` and
+    # `path_q` above are their per-path replication (path j * k + s = start s to point j)
+    sweep_starts: np.ndarray | None = None
+    sweep_q: np.ndarray | None = None
 
     @property
     def N(self):
@@ -40,11 +44,18 @@ class Workload:
 
     def slice(self, lo: int, hi: int) -> "Workload":
         """Paths lo .. hi-1 (a shard of the batch; cell weights and homotopies are shared)."""
-        return Workload(self.name, self.description, self.n, self.starts[lo:hi], self.mode, self.build,
-                        None if self.path_q is None else self.path_q[lo:hi],
-                        None if self.cell_index is None else self.cell_index[lo:hi], self.cell_weights, self.costs, {})
+        w = Workload(self.name, self.description, self.n, self.starts[lo:hi], self.mode, self.build,
+                     None if self.path_q is None else self.path_q[lo:hi],
+                     None if self.cell_index is None else self.cell_index[lo:hi], self.cell_weights, self.costs, {})
+        if self.sweep_starts is not None:
+            k = len(self.sweep_starts)
+            if lo % k == 0 and hi % k == 0:   # the shard holds whole parameter points
+                w.sweep_starts, w.sweep_q = self.sweep_starts, self.sweep_q[lo // k:hi // k]
+        return w
 
     def track(self, api, handles, options=None, nthreads=1, out=None):
+        if self.sweep_starts is not None and getattr(api, "_track_sweep", None) is not None:
+            return capi.track_sweep(handles["H"], self.sweep_starts, self.sweep_q, options, out=out)
         if self.mode == 2:
             return capi.polyhedral_track_batch(api, handles["H"], handles["Hcoeff"], self.starts, self.cell_index,
                                                self.cell_weights, options, nthreads, out=out)
@@ -184,4 +195,5 @@ def biochem_sweep_from_starts(starts: np.ndarray, p1: np.ndarray, points: int, s
     def build(api):
         return {"H": api.homotopy(capi.H_PARAMETER, api.system(F), p=p1, q=q[0])}
     return Workload("biochem_sweep", f"bio-chemical network 1 parameter sweep, {points} parameter points x {k} start solutions",
-                    3, S, 0, build, path_q=Q, costs=flops.homotopy_costs(F))
+                    3, S, 0, build, path_q=Q, costs=flops.homotopy_costs(F),
+                    sweep_starts=np.ascontiguousarray(starts, dtype=np.complex128), sweep_q=np.ascontiguousarray(q, dtype=np.complex128))

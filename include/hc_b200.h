@@ -121,6 +121,20 @@ int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, co
 int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* o, int64_t N, const double* starts,
                                   const int32_t* cell_index, const double* cell_weights, int32_t ncells,
                                   hc_results* out, int32_t reserved);
+
+/* Start solutions produced on the device: nothing but the degrees crosses the bus.
+ * Tracks the paths first .. first + N - 1 of the total-degree start system of H = StraightLineHomotopy(G, F):
+ * path k starts from x_i = cis(2 pi j_i / d_i), (j_1, ..., j_n) = mixed-radix digits of k, first index fastest --
+ * the order of TotalDegreeStartSolutionsIterator (reference src/total_degree.jl:235-262; replaces
+ * collect(starts), src/solve.jl:543).  `first` lets every GPU take an index range without a start matrix. */
+int32_t hc_track_total_degree(void* H, const hc_options* o, const int32_t* degrees, int64_t first, int64_t N,
+                              hc_results* out);
+/* Many-parameter solve (reference many_solve, src/solve.jl:815-881: the same S start solutions tracked to each
+ * of M target parameter vectors): starts is n x S, target_params P x M (column per point).  Path j * S + s =
+ * start s to parameter point j; `out` holds S * M paths in that order.  Only the S starts and one parameter
+ * column per POINT are copied to the device. */
+int32_t hc_track_sweep(void* H, const hc_options* o, int64_t S, const double* starts, int64_t M,
+                       const double* target_params, hc_results* out);
 void hc_get_timing(hc_timing* t);
 
 /* Device-resident variant for throughput measurement: inputs are uploaded once, results stay on

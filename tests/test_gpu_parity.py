@@ -134,6 +134,49 @@ def test_page_locked_reused_result_buffers(gpu):
         H.track_batch(S[:5], out=out)
 
 
+def _same(a, b):
+    for x, y in zip(a.arrays(), b.arrays()):
+        assert np.array_equal(x, y, equal_nan=x.dtype.kind in "fc")
+
+
+def test_total_degree_starts_made_on_the_device(oracle, gpu):
+    """hc_track_total_degree: start solutions from the path index on the device == the streamed-in
+    values of TotalDegreeStartSolutionsIterator (src/total_degree.jl:235-262), whole range and a shard's sub-range."""
+    td, H = straight_line(gpu, systems.katsura(8), 0.4 + 1.3j)
+    S = td.start_solutions()
+    ref = H.track_batch(S)
+    _same(ref, capi.track_total_degree(H, td.degrees))
+    _same(H.track_batch(S[100:200]), capi.track_total_degree(H, td.degrees, first=100, count=100))
+    _, Ho = straight_line(oracle, systems.katsura(8), 0.4 + 1.3j)
+    assert_batches_match(Ho.track_batch(S), capi.track_total_degree(H, td.degrees))
+    # lane-group engine (n > 14): every lane of a group derives the digits itself
+    F = systems.katsura(15)
+    td, H = straight_line(gpu, F, 0.4 + 1.3j)
+    S = td.start_solutions()[:96]
+    _same(H.track_batch(S), capi.track_total_degree(H, td.degrees, first=0, count=96))
+    with pytest.raises(RuntimeError, match="exceeds"):
+        capi.track_total_degree(H, td.degrees, first=2 ** 15 - 1, count=2)
+
+
+def test_sweep_entry_point(oracle, gpu):  # many_solve, src/solve.jl:815-881
+    F = systems.biochem1()
+    rng = np.random.default_rng(11)
+    p1 = rng.normal(size=10) + 1j * rng.normal(size=10)
+    td, H0 = straight_line(gpu, F, 0.4 + 1.3j, p1)
+    r0 = H0.track_batch(td.start_solutions())
+    starts = r0.solution[(r0.return_code == 1) & (r0.singular == 0)]
+    k, M = len(starts), 300
+    q = (systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * rng.normal(size=(M, 10)))).astype(np.complex128)
+    H = gpu.homotopy(capi.H_PARAMETER, gpu.system(F), p=p1, q=q[0])
+    S = np.repeat(starts[None], M, axis=0).reshape(-1, 3)
+    Q = np.repeat(q[:, None, :], k, axis=1).reshape(-1, 10)
+    got = capi.track_sweep(H, starts, q)
+    _same(H.track_batch(S, path_q=Q), got)
+    Ho = oracle.homotopy(capi.H_PARAMETER, oracle.system(F), p=p1, q=q[0])
+    assert_batches_match(Ho.track_batch(S, path_q=Q), got)
+    assert lib.timing().h2d_bytes < 16 * (3 * k + 10 * M) + 4096   # only S starts and one column per point cross the bus
+
+
 def test_parameter_sweep(oracle, gpu):  # BASELINE.json configs[4] at test size
     F = systems.biochem1()
     rng = np.random.default_rng(5)

@@ -73,6 +73,57 @@ def test_parameter_sweep_per_path_targets(oracle, sim):
     assert np.allclose(one.solution, res[1].solution[blk], rtol=1e-12, atol=1e-14)
 
 
+def _same(a, b):
+    for x, y in zip(a.arrays(), b.arrays()):
+        assert np.array_equal(x, y, equal_nan=x.dtype.kind in "fc")
+
+
+def test_total_degree_starts_made_by_the_tracker(oracle, sim):
+    """hc_track_total_degree: index -> start solution inside the tracker gives bit-identical results
+    to the streamed-in iterator values, for the whole range and for an index sub-range (a multi-GPU shard)."""
+    td, H = straight_line(sim, systems.katsura(4), 0.4 + 1.3j)
+    S = td.start_solutions()
+    ref = H.track_batch(S)
+    got = capi.track_total_degree(H, td.degrees)
+    assert got.N == len(S) == 16
+    _same(ref, got)
+    part = capi.track_total_degree(H, td.degrees, first=5, count=7)
+    _same(H.track_batch(S[5:12]), part)
+    # mixed degrees: the first index runs fastest (Iterators.product order, total_degree.jl:241)
+    F = make_system(lambda v, p: [v[0] ** 3 - 2 * v[1] + 1, v[0] * v[1] + v[1] ** 2 - 3, v[2] - v[0] - 1], 3)
+    td, H = straight_line(sim, F, 0.3 - 0.9j)
+    assert list(td.degrees) == [3, 2, 1]
+    _same(H.track_batch(td.start_solutions()), capi.track_total_degree(H, td.degrees))
+    _, Ho = straight_line(oracle, F, 0.3 - 0.9j)
+    assert_batches_match(Ho.track_batch(td.start_solutions()), capi.track_total_degree(H, td.degrees))
+    with pytest.raises(RuntimeError, match="exceeds"):
+        capi.track_total_degree(H, td.degrees, first=4, count=3)
+    with pytest.raises(RuntimeError):
+        capi.track_total_degree(Ho, td.degrees)   # the oracle has no such entry point
+
+
+def test_sweep_entry_point_matches_replicated_batch(oracle, sim):
+    """hc_track_sweep (many_solve, src/solve.jl:815-881): S starts x M parameter points with one parameter column per
+    point == hc_track_batch with starts and parameters replicated per path."""
+    F = systems.biochem1()
+    rng = np.random.default_rng(11)
+    p1 = rng.normal(size=10) + 1j * rng.normal(size=10)
+    td, H0 = straight_line(oracle, F, 0.4 + 1.3j, p1)
+    r0 = H0.track_batch(td.start_solutions())
+    starts = r0.solution[(r0.return_code == 1)]
+    k, M = len(starts), 5
+    q = (systems.BIOCHEM1_PVALS[None, :] * np.exp(0.5 * rng.normal(size=(M, 10)))).astype(np.complex128)
+    H = sim.homotopy(capi.H_PARAMETER, sim.system(F), p=p1, q=q[0])
+    S = np.repeat(starts[None], M, axis=0).reshape(-1, 3)
+    Q = np.repeat(q[:, None, :], k, axis=1).reshape(-1, 10)
+    _same(H.track_batch(S, path_q=Q), capi.track_sweep(H, starts, q))
+    Ho = oracle.homotopy(capi.H_PARAMETER, oracle.system(F), p=p1, q=q[0])
+    assert_batches_match(Ho.track_batch(S, path_q=Q), capi.track_sweep(H, starts, q))
+    _, Hs = straight_line(sim, F, 0.4 + 1.3j, p1)   # a straight-line homotopy is not a sweep target
+    with pytest.raises(RuntimeError, match="parameter homotopy"):
+        capi.track_sweep(Hs, starts, q)
+
+
 def test_polyhedral_cyclic5(oracle, sim):
     """PolyhedralTracker two-stage track (reference src/polyhedral.jl:414-530): 70 mixed-volume paths, 70 solutions
     (reference test/polyhedral_test.jl:38-46)."""
