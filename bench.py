@@ -272,6 +272,8 @@ def main():
                    "engine": "thread-per-path" if tm.lanes == 1 else f"{tm.lanes}-lane group per path",
                    "grid": tm.grid, "block": tm.block, "success_paths": n_ok, "class_counts": counts, "expected": wg.expected},
         "e2e": {"value": e2e, "unit": "paths/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(tm.d2h_bytes),
+                "last_call_ms": {"setup_and_h2d": round(tm.h2d_ms, 2), "kernel": round(tm.kernel_ms, 2), "d2h": round(tm.d2h_ms, 2),
+                                 "whole_step_mean": round(1e3 * float(te[0]) / args.steps, 2)},
                 "entry_point": "hc_track_sweep" if w.sweep_starts is not None else ("hc_polyhedral_track_batch" if w.mode == 2 else "hc_track_batch"),
                 "host_buffers": "pageable" if not pinned else "page-locked once (hc_host_register), reused every step",
                 "results_identical_to_resident_arm": e2e_same},

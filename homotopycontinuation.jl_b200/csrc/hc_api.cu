@@ -43,8 +43,17 @@ int fail(const std::string& msg) { g_err = msg; return -1; }
         cudaError_t e_ = (call);                                                                    \
         if (e_ != cudaSuccess) throw std::string(#call) + ": " + cudaGetErrorString(e_);            \
     } while (0)
-void* dev_alloc(size_t bytes) { void* p = nullptr; CK(cudaMalloc(&p, bytes ? bytes : 16)); return p; }
-void dev_free(void* p) { if (p) cudaFree(p); }
+// Device memory comes from the stream-ordered pool of the device (cudaMallocAsync on the legacy default stream, the
+// stream every copy and kernel of this library runs on).  hc_init sets the pool's release threshold to "never", so the
+// ~30 buffers of a batch are recycled by the next call instead of being unmapped and mapped again (cudaFree of a
+// 100 MB buffer synchronises the device and costs milliseconds).  HC_B200_POOL=0 falls back to cudaMalloc / cudaFree.
+bool g_pool = true;
+void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (g_pool) CK(cudaMallocAsync(&p, bytes ? bytes : 16, 0)); else CK(cudaMalloc(&p, bytes ? bytes : 16));
+    return p;
+}
+void dev_free(void* p) { if (p) { if (g_pool) cudaFreeAsync(p, 0); else cudaFree(p); } }
 void h2d(void* d, const void* h, size_t bytes) { if (bytes) CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); }
 void d2h(void* h, const void* d, size_t bytes) { if (bytes) CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); }
 void dev_zero(void* d, size_t bytes) { if (bytes) CK(cudaMemset(d, 0, bytes)); }
@@ -648,21 +657,26 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         if (N <= 0) return 0;
-        double tA = now_ms();
-        DeviceBatch D;
-        setup_batch(D, H, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, cell_index, cell_weights, ncells, sg);
+        double tA = now_ms(), tB, tC, tD, kms;
+        {
+            DeviceBatch D;
+            setup_batch(D, H, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, cell_index, cell_weights, ncells, sg);
 #ifndef HC_HOST_SIM
-        CK(cudaDeviceSynchronize());
+            CK(cudaDeviceSynchronize());
 #endif
-        double tB = now_ms();
-        double kms = run_batch(D);
-        double tC = now_ms();
-        fetch_results(D, out);
-        double tD = now_ms();
-        g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
-        g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
-        g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.group;
-        g_timing.slab_bytes = D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.slab + D.plan.cold) : (int64_t)D.plan.slab;
+            tB = now_ms();
+            kms = run_batch(D);
+            tC = now_ms();
+            fetch_results(D, out);
+            tD = now_ms();
+            g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
+            g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
+            g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.group;
+            g_timing.slab_bytes = D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.slab + D.plan.cold) : (int64_t)D.plan.slab;
+        }
+        if (env_int("HC_B200_VERBOSE", 0) >= 2)
+            fprintf(stderr, "[hc_b200] batch of %lld paths: setup+h2d %.2f ms, launch..done %.2f ms (kernel %.2f ms by events), d2h %.2f ms, release %.2f ms\n",
+                    N, tB - tA, tC - tB, kms, tD - tC, now_ms() - tD);
     } catch (const std::string& e) { return fail(e); }
     return 0;
 }
@@ -683,6 +697,13 @@ int32_t hc_init(int32_t device) {
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
     cudaDeviceSetLimit(cudaLimitStackSize, (size_t)env_int("HC_B200_STACK", 8192));
+    g_pool = env_int("HC_B200_POOL", 1) != 0;
+    if (g_pool) {
+        cudaMemPool_t mp;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) != cudaSuccess ||
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) { cudaGetLastError(); g_pool = false; }
+    }
 #else
     (void)device;
 #endif

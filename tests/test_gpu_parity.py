@@ -171,10 +171,10 @@ def test_sweep_entry_point(oracle, gpu):  # many_solve, src/solve.jl:815-881
     S = np.repeat(starts[None], M, axis=0).reshape(-1, 3)
     Q = np.repeat(q[:, None, :], k, axis=1).reshape(-1, 10)
     got = capi.track_sweep(H, starts, q)
+    assert lib.timing().h2d_bytes < 16 * (3 * k + 10 * M) + 4096   # only S starts and one column per point cross the bus
     _same(H.track_batch(S, path_q=Q), got)
     Ho = oracle.homotopy(capi.H_PARAMETER, oracle.system(F), p=p1, q=q[0])
     assert_batches_match(Ho.track_batch(S, path_q=Q), got)
-    assert lib.timing().h2d_bytes < 16 * (3 * k + 10 * M) + 4096   # only S starts and one column per point cross the bus
 
 
 def test_parameter_sweep(oracle, gpu):  # BASELINE.json configs[4] at test size
