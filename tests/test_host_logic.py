@@ -89,3 +89,13 @@ def test_mixed_cells_give_the_mixed_volume():
             assert rest.size == 0 or rest.min() > cell.beta[i] + 1e-9
     w = ps.cell_weights()
     assert w.shape == (len(ps.cells), len(ps.start_coeffs)) and (w >= 0).all()
+
+
+def test_mixed_volume_of_the_only_torus_example():
+    """reference test/polyhedral_test.jl:23-36: 92 paths with the origins added (only_torus = false)."""
+    from hcb200 import polyhedral as ph
+    from hcb200.modelkit import make_system
+    F = make_system(lambda v, p: [v[0] ** 3 * v[2] ** 15 + v[0] * v[1] * v[2] + v[1] ** 3 + v[2] ** 12,
+                                  v[0] ** 2 * v[2] ** 9 + v[0] * v[1] ** 2 + v[1] * v[2] ** 3,
+                                  v[0] ** 2 * v[1] * v[2] ** 5 + v[0] * v[2] ** 8 + v[1] ** 2], 3)
+    assert ph.polyhedral(F).n_paths() == 92

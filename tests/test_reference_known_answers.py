@@ -89,3 +89,52 @@ def test_invalid_startvalue_singular_jacobian(api, db):  # test/tracker_test.jl:
     H = api.homotopy(capi.H_PARAMETER, api.system(F), p=[b0], q=[b0 + db])
     r = H.track_batch([start], mode=1)
     assert capi.TRACKER_CODES[r.return_code[0]] == "terminated_invalid_startvalue_singular_jacobian"
+
+
+# ---- polyhedral start systems (mixed cells from hcb200.polyhedral with explicit seeds, SURVEY.md 8c "RNG")
+def track_polyhedral(api, F):
+    from hcb200 import polyhedral as ph
+    ps = ph.polyhedral(F)
+    S, ci = ps.start_solutions()
+    h = api.system(ps.F)
+    Ht = api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs)
+    Hc = api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)
+    return ps, capi.polyhedral_track_batch(api, Ht, Hc, S, ci, ps.cell_weights())
+
+
+def test_polyhedral_affine_and_torus_solutions(api):  # test/polyhedral_test.jl:2-9 (only_torus = false)
+    from hcb200.modelkit import make_system
+    f = make_system(lambda v, p: [2 * v[1] + 3 * v[1] ** 2 - v[0] * v[1] ** 3, v[0] + 4 * v[0] ** 2 - 2 * v[0] ** 3 * v[1]], 2)
+    ps, r = track_polyhedral(api, f)
+    assert ps.n_paths() == 8
+    assert int((r.return_code == 1).sum()) == 6
+
+
+def test_polyhedral_affine_square(api):  # test/solve_test.jl:94-101
+    from helpers import system_2x2
+    ps, r = track_polyhedral(api, system_2x2())
+    assert int((r.return_code == 1).sum()) == 2
+    assert sorted(capi.ENDGAME_CODES[c] for c in r.return_code) == ["at_infinity", "at_infinity", "success", "success"]
+
+
+def test_many_parameters_solver(api):  # test/solve_test.jl:437-537: circle x line, 100 parameter points, 2 solutions each
+    from hcb200.modelkit import make_system
+    F = make_system(lambda v, p: [v[0] ** 2 + v[1] ** 2 - 1, p[0] * v[0] + p[1] * v[1] + p[2]], 2, 3)
+    rng = np.random.default_rng(2024)
+    p0 = (rng.normal(size=3) + 1j * rng.normal(size=3)) / np.sqrt(2)
+    td, H0 = straight_line(api, F, GAMMA, p0)
+    r0 = H0.track_batch(td.start_solutions())
+    S0 = r0.solution[r0.return_code == 1]
+    assert len(S0) == 2
+    params = rng.random((100, 3)).astype(np.complex128)
+    H = api.homotopy(capi.H_PARAMETER, api.system(F), p=p0, q=params[0])
+    if getattr(api, "_track_sweep", None) is not None:
+        r = capi.track_sweep(H, S0, params)                                     # many_solve entry point
+    else:
+        r = H.track_batch(np.tile(S0, (100, 1)), path_q=np.repeat(params, 2, axis=0))
+    assert (r.return_code == 1).all() and not r.singular.any()
+    sol = r.solution.reshape(100, 2, 2)
+    assert (np.abs(sol[:, 0] - sol[:, 1]).max(axis=1) > 1e-8).all()              # 2 distinct solutions per point
+    x, y = r.solution[:, 0], r.solution[:, 1]
+    q = np.repeat(params, 2, axis=0)
+    assert np.abs(x ** 2 + y ** 2 - 1).max() < 1e-10 and np.abs(q[:, 0] * x + q[:, 1] * y + q[:, 2]).max() < 1e-10
