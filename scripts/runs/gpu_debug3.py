@@ -1,6 +1,6 @@
 """Debug: 2x2 endgame golden case and katsura(3) on the selected engine, printed next to the oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
 import numpy as np
 import hcb200, pyoracle
