@@ -218,8 +218,16 @@ struct Path {
     HC_HD cx param_p(int i) const { return H->path_p ? H->path_p[(size_t)prow * H->P + i] : pld<S>(H->p + i); }
     HC_HD cx param_q(int i) const { return H->path_q ? H->path_q[(size_t)prow * H->P + i] : pld<S>(H->q + i); }
 
+    // log t and 1 / t of a toric homotopy: the same for every parameter (t^w = exp(w log t)), so the loops over the
+    // parameters compute them once instead of once per parameter
+    struct ToricT { double lt, ti; };
+    HC_HD ToricT toric_t(cx t) const {
+        ToricT r; r.lt = 0.0; r.ti = 0.0;
+        if (kind == H_TORIC && t.re != 0.0) { r.lt = log(t.re); r.ti = 1.0 / t.re; }
+        return r;
+    }
     // Taylor coefficients c[0..4] of parameter i at t
-    HC_HD void param_series(int i, cx t, cx* c) const {
+    HC_HD void param_series(int i, cx t, const ToricT& tt, cx* c) const {
         c[1] = c[2] = c[3] = c[4] = mk(0.0);
         if (kind == H_TORIC) {  // toric_homotopy.jl:145-177, 220-264 (real t >= 0)
             cx u = pld<S>(H->p + i);
@@ -229,7 +237,7 @@ struct Path {
                 if (w < 1e-12) c[0] = u;
                 else if (fabs(w - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(w), 1.0)) c[1] = u;
             } else {
-                double tw = exp(w * log(tr)), ti = 1.0 / tr;
+                double tw = exp(w * tt.lt), ti = tt.ti;
                 c[0] = u * tw;
                 double tw1 = w * tw * ti; c[1] = u * tw1;
                 double tw2 = 0.5 * (w - 1) * tw1 * ti; c[2] = u * tw2;
@@ -244,12 +252,12 @@ struct Path {
         }
     }
     // value of parameter i at t (toric t == 0: weights that are exactly 0 survive, toric_homotopy.jl:160-165)
-    HC_HD cx param_value(int i, cx t) const {
+    HC_HD cx param_value(int i, cx t, const ToricT& tt) const {
         if (kind == H_TORIC) {
             cx u = pld<S>(H->p + i);
             double w = M.tw[i];
             if (t.re == 0.0) return w == 0.0 ? u : mk(0.0);
-            return u * exp(w * log(t.re));
+            return u * exp(w * tt.lt);
         }
         cx p = param_p(i), q = param_q(i);
         if (t.im == 0.0) return t.re * p + (1.0 - t.re) * q;
@@ -269,7 +277,8 @@ struct Path {
         const bool keep = sizeof(T) == sizeof(cx) && tape_prog == &P && tape_kind == kind && tape_t.re == t.re && tape_t.im == t.im;
         if (!keep) {
             HC_PAR(i, P.C) store_in(tape, i, pld<S>(P.consts + i), mk(0.0), tag);
-            HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? pld<S>(fixed + i) : param_value(i, t), mk(0.0), tag);
+            const ToricT tt = toric_t(t);
+            HC_PAR(i, P.P) store_in(tape, P.param_off + i, fixed ? pld<S>(fixed + i) : param_value(i, t, tt), mk(0.0), tag);
             if (P.t_slot >= 0 && g.lane == 0) store_in(tape, P.t_slot, t, mk(0.0), tag);
         }
         HC_PAR(i, P.n) store_in(tape, P.var_off + i, x[i], xlo ? (*xlo)[i] : mk(0.0), tag);
@@ -363,10 +372,11 @@ struct Path {
 #pragma unroll
                 for (int k = 1; k < TS; ++k) tape[i * TS + k] = mk(0.0);
             }
+            const ToricT tt = toric_t(t);
             HC_PAR(i, P.P) {
                 cx c[5];
                 if (fixed) { c[0] = pld<S>(fixed + i); c[1] = c[2] = c[3] = c[4] = mk(0.0); }
-                else param_series(i, t, c);
+                else param_series(i, t, tt, c);
                 const int b = (P.param_off + i) * TS;
 #pragma unroll
                 for (int k = 0; k < TS; ++k) tape[b + k] = c[k];
