@@ -21,6 +21,18 @@ def test_header_declares_the_boundary():
         assert s in syms
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/hc_b200.h compiles as C99 (no C++ or torch types in the signatures) and a
+    C translation unit can fill the structs and reference every entry point."""
+    import subprocess
+    src = tmp_path / "use.c"
+    calls = "\n".join(f"    (void)&{s};" for s in declared_symbols())
+    src.write_text('#include "hc_b200.h"\nint main(void) {\n    hc_options o; hc_results r; hc_program_desc p; hc_homotopy_desc h; hc_timing t;\n'
+                   '    (void)o; (void)r; (void)p; (void)h; (void)t;\n' + calls + "\n    return 0;\n}\n")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-Wno-comment", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                   check=True)
+
+
 def test_library_exports_every_declared_symbol():
     import __graft_entry__ as ge
     ge.build()
