@@ -222,7 +222,13 @@ def main():
         inputs = [w.sweep_starts, w.sweep_q]
     else:
         inputs = [w.starts, w.path_q, w.cell_index]
-    pinned = [] if os.environ.get("HC_BENCH_PAGEABLE") else lib.pin(*inputs, *out.arrays())
+    pinned, pin_note = [], "pageable"
+    if not os.environ.get("HC_BENCH_PAGEABLE"):
+        try:
+            pinned = lib.pin(*inputs, *out.arrays())
+            pin_note = "page-locked once (hc_host_register), reused every step"
+        except RuntimeError as e:   # e.g. a locked-memory limit on the box: measure with pageable buffers and say so
+            pin_note = f"pageable ({e})"
     for _ in range(2):
         w.track(api, handles, opts, out=out)
     barrier()
@@ -277,7 +283,7 @@ def main():
                 "last_call_ms": {"setup_and_h2d": round(tm.h2d_ms, 2), "kernel": round(tm.kernel_ms, 2), "d2h": round(tm.d2h_ms, 2),
                                  "whole_step_mean": round(1e3 * float(te[0]) / args.steps, 2)},
                 "entry_point": "hc_track_sweep" if w.sweep_starts is not None else ("hc_polyhedral_track_batch" if w.mode == 2 else "hc_track_batch"),
-                "host_buffers": "pageable" if not pinned else "page-locked once (hc_host_register), reused every step",
+                "host_buffers": pin_note,
                 "results_identical_to_resident_arm": e2e_same},
         "gpu_launches": args.steps,
         "clocks": clocks,

@@ -61,7 +61,10 @@ def pin(*arrays) -> list:
         if not a.flags.c_contiguous:
             raise ValueError("only contiguous arrays can be page-locked")
         if raw.hc_host_register(a.ctypes.data, a.nbytes) != 0:
-            raise RuntimeError("hc_host_register failed: " + raw.hc_last_error().decode())
+            msg = raw.hc_last_error().decode()
+            for b in done:   # all or nothing
+                raw.hc_host_unregister(b.ctypes.data)
+            raise RuntimeError("hc_host_register failed: " + msg)
         done.append(a)
     return done
 
