@@ -176,3 +176,86 @@ def test_segment_scheduler_invariants(sim, window):
         assert stats[0] >= 1 and 1 <= stats[1] <= stats[0]
         if window == 1:
             assert stats[1] == stats[0]          # tape order: one op per segment
+
+
+def _random_system(rng, n, degs):
+    """Sparse random polynomial system with complex coefficients: per equation one monomial of full degree, a few
+    lower ones and a constant."""
+    seed = int(rng.integers(1 << 30))
+
+    def build(v, p):
+        r = np.random.default_rng(seed)
+
+        def monomial(deg):
+            ex = r.multinomial(deg, np.ones(n) / n)
+            m = complex(r.normal(), r.normal() if r.random() < 0.5 else 0.0)
+            for k in range(n):
+                if ex[k]:
+                    m = m * v[k] ** int(ex[k])
+            return m
+        eqs = []
+        for i in range(n):
+            d = int(degs[i])
+            e = monomial(d) + complex(r.normal(), r.normal())
+            for _ in range(int(r.integers(2, 6))):
+                e = e + monomial(int(r.integers(0, d + 1)))
+            eqs.append(e)
+        return eqs
+    return make_system(build, n)
+
+
+def test_random_systems_fuzz(oracle, sim):
+    """80 random systems (n = 1..4, degrees 1..3, 500+ total-degree paths incl. diverging ones): the device code agrees
+    with the oracle on every return code, singular flag and winding number and on the endpoints to 1e-8."""
+    rng = np.random.default_rng(1)
+    paths = 0
+    for _ in range(80):
+        n = int(rng.integers(1, 5))
+        degs = rng.integers(1, 4, size=n)
+        F = _random_system(rng, n, degs)
+        gamma = np.exp(2j * np.pi * rng.random())
+        tdo, Ho = straight_line(oracle, F, gamma)
+        _, Hs = straight_line(sim, F, gamma)
+        S = tdo.start_solutions()
+        ro, rs = Ho.track_batch(S), Hs.track_batch(S)
+        assert_batches_match(ro, rs)
+        ok = ro.return_code == 1
+        assert (np.abs(ro.accepted_steps - rs.accepted_steps)[ok] <= np.maximum(3, 0.1 * ro.accepted_steps[ok])).all()
+        paths += len(S)
+    assert paths > 500
+
+
+def _track_polyhedral(api, ps):
+    S, ci = ps.start_solutions()
+    h = api.system(ps.F)
+    Ht = api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs)
+    Hc = api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)
+    return capi.polyhedral_track_batch(api, Ht, Hc, S, ci, ps.cell_weights())
+
+
+def test_polyhedral_fuzz_and_agreement_with_total_degree(oracle, sim):
+    """Random sparse systems (n = 2, 3): (1) the polyhedral driver of the device code agrees with the oracle path by
+    path; (2) size-independent property: the polyhedral homotopy (mixed-volume many paths) and the total-degree homotopy
+    (Bezout many paths) end in the same set of finite solutions."""
+    from hcb200 import polyhedral as ph
+    rng = np.random.default_rng(11)
+    systems_seen = 0
+    for _ in range(30):
+        n = int(rng.integers(2, 4))
+        F = _random_system(rng, n, rng.integers(1, 4, size=n))
+        ps = ph.polyhedral(F)
+        if ps.n_paths() == 0:
+            continue
+        rp = _track_polyhedral(sim, ps)
+        assert_batches_match(_track_polyhedral(oracle, ps), rp)
+        td, H = straight_line(sim, F, np.exp(2j * np.pi * rng.random()))
+        rt = H.track_batch(td.start_solutions())
+        A, B = rp.solution[rp.return_code == 1], rt.solution[rt.return_code == 1]
+        assert len(A) == len(B), (len(A), len(B), ps.n_paths(), td.n_paths())
+        if len(A):
+            d = np.abs(A[:, None, :] - B[None, :, :]).max(axis=2)
+            scale = np.maximum(1.0, np.abs(B).max(axis=1))[None, :]
+            assert ((d / scale).min(axis=1) < 1e-8).all()          # every polyhedral endpoint is a total-degree endpoint
+            assert len(set((d / scale).argmin(axis=1))) == len(A)  # and they are all different
+        systems_seen += 1
+    assert systems_seen >= 20
