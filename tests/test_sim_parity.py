@@ -259,3 +259,51 @@ def test_polyhedral_fuzz_and_agreement_with_total_degree(oracle, sim):
             assert len(set((d / scale).argmin(axis=1))) == len(A)  # and they are all different
         systems_seen += 1
     assert systems_seen >= 20
+
+
+def test_parameter_homotopy_round_trip_fuzz(oracle, sim):
+    """Random parameter homotopies F(x; p), p0 -> q -> p0 with the plain Tracker (mode 1): the device code matches the
+    oracle and the round trip returns to the start solutions (the property reference steiner_higher_prec.jl:145-152 checks)."""
+    rng = np.random.default_rng(5)
+    done = 0
+    for _ in range(25):
+        n = int(rng.integers(1, 4))
+        degs = rng.integers(1, 4, size=n)
+        P = n + 1
+        seed = int(rng.integers(1 << 30))
+
+        def build(v, p, n=n, degs=degs, seed=seed):
+            r = np.random.default_rng(seed)
+            eqs = []
+            for i in range(n):
+                ex = r.multinomial(int(degs[i]), np.ones(n) / n)
+                m = complex(r.normal(), r.normal())
+                for k in range(n):
+                    if ex[k]:
+                        m = m * v[k] ** int(ex[k])
+                lin = sum(complex(r.normal(), r.normal()) * v[k] for k in range(n))
+                eqs.append(m + p[i] * lin + p[n] * p[i] + complex(r.normal(), r.normal()))   # parameters enter bilinearly
+            return eqs
+        F = make_system(build, n, P)
+        p0 = rng.normal(size=P) + 1j * rng.normal(size=P)
+        q = rng.normal(size=P) + 1j * rng.normal(size=P)
+        td, H0 = straight_line(oracle, F, np.exp(2j * np.pi * rng.random()), p0)
+        r0 = H0.track_batch(td.start_solutions())
+        S = r0.solution[(r0.return_code == 1) & (r0.singular == 0)]
+        if len(S) == 0:
+            continue
+        res = []
+        for api in (oracle, sim):
+            H = api.homotopy(capi.H_PARAMETER, api.system(F), p=p0, q=q)
+            fwd = H.track_batch(S, mode=1)
+            okf = fwd.return_code == 1
+            back = H.track_batch(fwd.solution[okf], mode=1, t1=0.0, t0=1.0)
+            res.append((fwd, back, okf))
+        (fo, bo, oko), (fs, bs, oks) = res
+        assert (fo.return_code == fs.return_code).all() and (bo.return_code == bs.return_code).all()
+        if oko.any():
+            assert np.abs(fo.solution[oko] - fs.solution[oko]).max() <= 1e-8 * max(1.0, np.abs(fo.solution[oko]).max())
+            okb = bs.return_code == 1
+            assert np.abs(bs.solution[okb] - S[oks][okb]).max() <= 1e-8 * max(1.0, np.abs(S).max())
+        done += 1
+    assert done >= 15
