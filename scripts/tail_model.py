@@ -70,6 +70,16 @@ def main():
         print(f"slowest 5 % of the paths {f} x faster (second engine): {queue_time(c2):.2f} s")
     for f in (2, 4):
         print(f"every step {f} x faster: {queue_time(cost / f):.2f} s")
+    # two-phase run with the existing kernels (hcb200/two_phase.py): phase 1 = thread-per-path engine with max_steps
+    # capped, phase 2 = paths that hit the cap, from scratch, one warp per path on the lane-group engine
+    # (148 SMs x 8 warps; 0.42 ms per step measured at n = 17 in the tail, assumed 0.3 ms here at n = 12)
+    t_group, slots = 0.3e-3, 148 * 8
+    for cap in (150, 300, 600, 1000):
+        w1 = np.where(ext, ddw, 1.0)
+        p1 = queue_time(np.minimum(steps, cap) * t_step * w1)
+        d = steps > cap
+        p2 = queue_time(steps[d] * t_group * np.where(ext[d], ddw, 1.0), lanes=slots) if d.any() else 0.0
+        print(f"two-phase, cap {cap:4d} steps: {int(d.sum()):5d} paths deferred, phase 1 {p1:.2f} s + phase 2 {p2:.2f} s = {p1 + p2:.2f} s")
 
 
 if __name__ == "__main__":
