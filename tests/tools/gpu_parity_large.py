@@ -1,7 +1,7 @@
 """Class-count parity of the CUDA tracker against the CPU oracle on a large slice of a workload
-(run on the GPU box): python scripts/gpu_parity_large.py tritangents 16384"""
+(run on the GPU box): python tests/tools/gpu_parity_large.py tritangents 16384"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np
 sys.argv, argv = sys.argv[:1], sys.argv[1:]

@@ -8,13 +8,13 @@ fp64 steps: an endgame that runs into max_endgame_steps); DDW is fitted so that 
 full run (4.74 s, profiles/r01s5_bench_tritangents.json).  The model then says what path ordering or a faster
 engine for the slow paths would buy.
 
-usage: python scripts/tail_model.py [paths]"""
+usage: python tests/tools/tail_model.py [paths]"""
 import heapq
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np  # noqa: E402
 import hcb200  # noqa: E402,F401
