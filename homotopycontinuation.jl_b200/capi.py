@@ -176,6 +176,7 @@ class CApi:
         f("evaluate_and_jacobian", C.c_int32, [C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p])
         f("taylor", C.c_int32, [C.c_void_p, C.c_int32, c_double_p, c_double_p, c_double_p])
         f("toric_set_weights", C.c_int32, [C.c_void_p, c_double_p])
+        f("homotopy_set_parameters", C.c_int32, [C.c_void_p, c_double_p, c_double_p], optional=True)
         # device-side start generation: entry points of libhc_b200 only (the oracle takes explicit starts)
         f("track_total_degree", C.c_int32, [C.c_void_p, C.POINTER(Options), c_int32_p, C.c_int64, C.c_int64,
                                             C.POINTER(ResultsDesc)], optional=True)
@@ -266,6 +267,16 @@ class HomotopyHandle:
             self.api._homotopy_destroy(self.handle)
         except Exception:
             pass
+
+    def set_parameters(self, p=None, q=None):
+        """start_parameters! / target_parameters! / parameters! (reference src/endgame_tracker.jl:831-840)."""
+        if self.api._homotopy_set_parameters is None:
+            raise RuntimeError("this library cannot change the parameters of a homotopy")
+        pa = _cflat(p, self.P) if p is not None else None
+        qa = _cflat(q, self.P) if q is not None else None
+        rc = self.api._homotopy_set_parameters(self.handle, _dp(pa) if pa is not None else None, _dp(qa) if qa is not None else None)
+        if rc:
+            raise RuntimeError(f"homotopy_set_parameters failed ({rc}): {_last_error(self.api)}")
 
     # ---- operator API hooks (test hooks of the C ABI)
     def evaluate(self, x, t):

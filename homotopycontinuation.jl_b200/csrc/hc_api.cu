@@ -778,6 +778,20 @@ void* hc_homotopy_create(const hc_homotopy_desc* d) {
 }
 void hc_homotopy_destroy(void* h) { delete (HomotopyH*)h; }
 
+int32_t hc_homotopy_set_parameters(void* Hv, const double* p, const double* q) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try {
+        HomotopyH* H = (HomotopyH*)Hv;
+        if (!H) throw std::string("null homotopy handle");
+        if (H->dev.kind == H_STRAIGHT_LINE) throw std::string("a straight-line homotopy has no start / target parameters");
+        if (q && H->dev.kind == H_TORIC) throw std::string("a toric homotopy has no target parameters");
+        const size_t bytes = (size_t)H->dev.P * 16;
+        if (p) h2d((void*)H->dev.p, p, bytes);
+        if (q) h2d((void*)H->dev.q, q, bytes);
+    } catch (const std::string& e) { return fail(e); }
+    return 0;
+}
+
 int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, const double* starts, const double* t1,
                        const double* t0, const double* path_p, const double* path_q, const double* omega_mu, hc_results* out,
                        int32_t) {

@@ -114,6 +114,10 @@ void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac);
 void hc_system_destroy(void* s);
 void* hc_homotopy_create(const hc_homotopy_desc* d);
 void hc_homotopy_destroy(void* h);
+/* start_parameters!(T, p), target_parameters!(T, q), parameters!(T, p, q) of a parameter / coefficient homotopy
+ * (reference src/endgame_tracker.jl:831-840, src/homotopies/parameter_homotopy.jl:47-64): P complex values each,
+ * NULL = keep.  Takes effect for the next batch call. */
+int32_t hc_homotopy_set_parameters(void* H, const double* p, const double* q);
 
 int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, const double* starts,
                        const double* t1, const double* t0, const double* path_p, const double* path_q,

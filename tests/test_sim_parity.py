@@ -307,3 +307,26 @@ def test_parameter_homotopy_round_trip_fuzz(oracle, sim):
             assert np.abs(bs.solution[okb] - S[oks][okb]).max() <= 1e-8 * max(1.0, np.abs(S).max())
         done += 1
     assert done >= 15
+
+
+def test_change_parameters(oracle, sim):
+    """reference test/tracker_test.jl:81-91 ("Change parameters"): start_parameters! / target_parameters! on an
+    existing tracker (hc_homotopy_set_parameters) == a homotopy created with those parameters."""
+    F = make_system(lambda v, p: [v[0] ** 2 - p[0], v[0] * v[1] - p[0] + p[1]], 2, 2)
+    H = sim.homotopy(capi.H_PARAMETER, sim.system(F), p=[2.2, 3.2], q=[2.2, 3.2])
+    H.set_parameters(p=[1, 0])
+    H.set_parameters(q=[2, 4])
+    r = H.track_batch([[1.0, 1.0]], mode=1)
+    assert capi.TRACKER_CODES[r.return_code[0]] == "success"
+    assert np.allclose(r.solution[0], [np.sqrt(2), -np.sqrt(2)])
+    ref = sim.homotopy(capi.H_PARAMETER, sim.system(F), p=[1, 0], q=[2, 4]).track_batch([[1.0, 1.0]], mode=1)
+    _same(ref, r)
+    H.set_parameters(p=[2, 4], q=[1, 0])      # parameters!(T, p, q): the way back
+    back = H.track_batch([r.solution[0]], mode=1)
+    assert np.allclose(back.solution[0], [1, 1])
+    td, Hs = straight_line(sim, systems.katsura(3), 0.4 + 1.3j)
+    with pytest.raises(RuntimeError, match="straight-line"):
+        Hs.set_parameters(p=[])
+    Ho = oracle.homotopy(capi.H_PARAMETER, oracle.system(F), p=[1, 0], q=[2, 4])
+    with pytest.raises(RuntimeError):
+        Ho.set_parameters(p=[1, 0])           # the oracle has no such entry point
