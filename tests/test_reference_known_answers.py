@@ -138,3 +138,51 @@ def test_many_parameters_solver(api):  # test/solve_test.jl:437-537: circle x li
     x, y = r.solution[:, 0], r.solution[:, 1]
     q = np.repeat(params, 2, axis=0)
     assert np.abs(x ** 2 + y ** 2 - 1).max() < 1e-10 and np.abs(q[:, 0] * x + q[:, 1] * y + q[:, 2]).max() < 1e-10
+
+
+# ---- reference test/homotopies_test.jl: evaluate!, evaluate_and_jacobian!, taylor! K = 1..4 at a random complex t against
+#      the symbolic homotopy (here: 60-digit arithmetic on the expression DAG), rtol 1e-12
+@pytest.fixture(params=["oracle", "sim"])
+def cpu_api(request):
+    return request.getfixturevalue(request.param)
+
+
+def _check_against_symbolic(H, h, n, rng):
+    import mpmath as mp
+    mp.mp.prec = 220
+    x = rng.normal(size=n) + 1j * rng.normal(size=n)
+    t = complex(rng.normal(), rng.normal())
+    mx, mt = [mp.mpc(v) for v in x], mp.mpc(t)
+    ref_u = np.array([complex(v) for v in h(mx, mt)])
+    u, U = H.evaluate_and_jacobian(x, t)
+    assert np.abs(H.evaluate(x, t) - ref_u).max() <= 1e-12 * np.abs(ref_u).max()
+    assert np.abs(u - ref_u).max() <= 1e-12 * np.abs(ref_u).max()
+    ref_U = np.array([[complex(mp.diff(lambda z: h(mx[:j] + [z] + mx[j + 1:], mt)[i], mx[j])) for j in range(n)] for i in range(n)])
+    assert np.abs(U.reshape(n, n, order="F") - ref_U).max() <= 1e-11 * np.abs(ref_U).max()
+    X = rng.normal(size=(4, n)) + 1j * rng.normal(size=(4, n))
+    for K in (1, 2, 3, 4):
+        def g(l, i):
+            xl = [sum(mp.mpc(X[k][j]) * l ** k for k in range(K)) for j in range(n)]
+            return h(xl, mt + l)[i]
+        ref = np.array([complex(mp.taylor(lambda l: g(l, i), 0, K)[K]) for i in range(n)])
+        got = H.taylor(K, X[:K], t)
+        assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max(), K
+
+
+def test_parameter_homotopy_operators(cpu_api):  # test/homotopies_test.jl:59-78
+    from hcb200.modelkit import make_system
+    f = lambda v, p: [(2 * v[0] ** 2 + p[1] ** 2 * v[1] ** 3 + 2 * p[0] * v[0] * v[1]) ** 3, (p[0] + p[2]) ** 4 * v[0] + v[1] ** 2]
+    F = make_system(f, 2, 3)
+    p, q = np.array([5.2, -1.3, 9.3]), np.array([2.6, 3.3, 2.3])
+    H = cpu_api.homotopy(capi.H_PARAMETER, cpu_api.system(F), p=p, q=q)
+    _check_against_symbolic(H, lambda x, t: f(x, [t * a + (1 - t) * b for a, b in zip(p, q)]), 2, np.random.default_rng(3))
+
+
+def test_straight_line_homotopy_operators(cpu_api):  # test/homotopies_test.jl:80-93: H = t F + (1 - t) G (gamma = 1)
+    from hcb200.modelkit import make_system
+    a, b, c = 0.31, 0.77, 0.52
+    f = lambda v, p: [(2 * v[0] ** 2 + b ** 2 * v[1] ** 3 + 2 * a * v[0] * v[1]) ** 3, (a + c) ** 4 * v[0] + v[1] ** 2]
+    g = lambda v, p: [(2 * v[1] ** 2 + b ** 2 * v[0] ** 3 + 2 * a * v[0] * v[1]) ** 2, (a - c) ** 3 * v[1] + v[0] ** 2]
+    start, target = cpu_api.system(make_system(f, 2)), cpu_api.system(make_system(g, 2))
+    H = cpu_api.homotopy(capi.H_STRAIGHT_LINE, target, start, gamma=1.0, G_params=[], F_params=[])
+    _check_against_symbolic(H, lambda x, t: [t * u + (1 - t) * w for u, w in zip(f(x, None), g(x, None))], 2, np.random.default_rng(4))
