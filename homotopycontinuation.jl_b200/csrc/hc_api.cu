@@ -19,12 +19,20 @@
 #include <string>
 #include <vector>
 
-#include "hc_lane.h"
+#include "hc_kernel.h"
 #include "hc_lower.h"
+#include "hc_jit.h"
 
 #ifndef HC_HOST_SIM
 #include <cuda_runtime.h>
 #endif
+
+// The tracker kernels live in hc_kern.cu (one translation unit per instantiation, so that they compile in parallel);
+// this file only needs their entry points.
+namespace hc {
+const void* hc_kernel_tpl(int slab);    // hc_track_tpl_kernel<slab>, slab = 12288 | 24576 | 49152
+const void* hc_kernel_group(int G);     // hc_track_kernel<G>, G = 8 | 32
+}
 
 using namespace hc;
 
@@ -48,15 +56,20 @@ int fail(const std::string& msg) { g_err = msg; return -1; }
 // ~30 buffers of a batch are recycled by the next call instead of being unmapped and mapped again (cudaFree of a
 // 100 MB buffer synchronises the device and costs milliseconds).  HC_B200_POOL=0 falls back to cudaMalloc / cudaFree.
 bool g_pool = true;
+// HC_B200_NO_DEVICE=1: handles are built in host memory so that hc_jit_prepare can generate and compile the specialised
+// kernel of a system on a machine without a GPU (NVRTC targets sm_100a offline; the driver's build check and the
+// "not gpu" tests use this).  Every compute entry point fails in this mode.
+bool nodev() { static const bool v = getenv("HC_B200_NO_DEVICE") && atoi(getenv("HC_B200_NO_DEVICE")) != 0; return v; }
 void* dev_alloc(size_t bytes) {
     void* p = nullptr;
+    if (nodev()) return calloc(bytes ? bytes : 16, 1);
     if (g_pool) CK(cudaMallocAsync(&p, bytes ? bytes : 16, 0)); else CK(cudaMalloc(&p, bytes ? bytes : 16));
     return p;
 }
-void dev_free(void* p) { if (p) { if (g_pool) cudaFreeAsync(p, 0); else cudaFree(p); } }
-void h2d(void* d, const void* h, size_t bytes) { if (bytes) CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); }
-void d2h(void* h, const void* d, size_t bytes) { if (bytes) CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); }
-void dev_zero(void* d, size_t bytes) { if (bytes) CK(cudaMemset(d, 0, bytes)); }
+void dev_free(void* p) { if (p) { if (nodev()) free(p); else if (g_pool) cudaFreeAsync(p, 0); else cudaFree(p); } }
+void h2d(void* d, const void* h, size_t bytes) { if (bytes) { if (nodev()) memcpy(d, h, bytes); else CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); } }
+void d2h(void* h, const void* d, size_t bytes) { if (bytes) { if (nodev()) memcpy(h, d, bytes); else CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); } }
+void dev_zero(void* d, size_t bytes) { if (bytes) { if (nodev()) memset(d, 0, bytes); else CK(cudaMemset(d, 0, bytes)); } }
 #else
 void* dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 16, 1); }
 void dev_free(void* p) { free(p); }
@@ -76,6 +89,7 @@ T* to_dev(const std::vector<T>& v) {
 struct ProgramH {
     DevProgram dev;  // pointers into device memory
     LoweredProgram low;
+    jit::ProgCopy ref;  // the reference tape as handed over (input of the code generator, hc_jitgen.h)
     std::vector<void*> owned;
     ~ProgramH() { for (void* p : owned) dev_free(p); }
 };
@@ -88,6 +102,7 @@ struct HomotopyH {
     SystemH* F = nullptr; SystemH* G = nullptr;
     std::vector<void*> owned;
     std::vector<double> tw_hook;  // weights set through hc_toric_set_weights (test hook)
+    std::shared_ptr<jit::Module> jit_mod[2];  // specialised kernels: [0] as created, [1] driven by the polyhedral tracker
     ~HomotopyH() { for (void* p : owned) dev_free(p); }
 };
 
@@ -105,6 +120,7 @@ int engine_for(int n);
 
 // Lower the reference's 24-byte, 1-based Instruction stream (hc_lower.h) and upload it.
 void build_program(ProgramH& H, const hc_program_desc* d, bool is_jac) {
+    H.ref.assign(d);
 #ifdef HC_HOST_SIM
     const bool tpp = true;
 #else
@@ -159,162 +175,8 @@ DevOptions to_dev_options(const hc_options* o) {
     return D;
 }
 
-// ------------------------------------------------------------------ kernels
-struct KArgs {
-    DevHomotopy H;
-    DevOptions O;
-    BatchIn B;
-    DevResults R;
-    unsigned long long* queue;
-    int stage;            // 1: copy the programs into shared memory
-    int slab_bytes;       // per-path shared-memory slab
-    int cold_bytes;       // per-group scratch in global memory
-    unsigned char* cold;
-    int refill_min;       // thread-per-path engine: idle lanes of a warp refill together once this many wait
-    int stage_bytes;      // staged programs (0 when !stage)
-};
-
+// ------------------------------------------------------------------ kernels (KArgs, staging, tpp_loop: hc_kernel.h)
 #ifndef HC_HOST_SIM
-extern __shared__ __align__(16) unsigned char hc_smem[];
-
-template <class T>
-__device__ const T* stage_array(const T* src, int count, unsigned char*& cur) {
-    size_t bytes = ((size_t)count * sizeof(T) + 15) & ~(size_t)15;
-    T* dst = reinterpret_cast<T*>(cur);
-    const int words = (int)(bytes / 4);
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    const int valid = (int)(((size_t)count * sizeof(T)) / 4);
-    for (int i = threadIdx.x; i < words; i += blockDim.x) d[i] = i < valid ? s[i] : 0u;
-    cur += bytes;
-    return dst;
-}
-// fast = thread-per-path kernels: they interpret fops + segs; the packed ops (only read by the
-// DoubleDouble interpreter) stay in global memory
-__device__ void stage_program(DevProgram& P, unsigned char*& cur, bool fast = false) {
-    if (fast) {
-        P.fops = stage_array(P.fops, P.n_fops, cur);
-        P.segs = stage_array(P.segs, P.n_segs, cur);
-    } else P.ops = stage_array(P.ops, P.n_ops, cur);
-    P.level_end = stage_array(P.level_end, P.n_levels, cur);
-    P.consts = stage_array(P.consts, P.C, cur);
-    P.u_assign = stage_array(P.u_assign, P.nu, cur);
-    P.U_assign = stage_array(P.U_assign, P.nU, cur);
-}
-
-// homotopy-level constant arrays: start / target parameters, fixed parameters of F and G
-__device__ void stage_params(DevHomotopy& h, unsigned char*& cur) {
-    if (h.kind == H_STRAIGHT_LINE) {
-        h.G_params = stage_array(h.G_params, h.Ge.P > 0 ? h.Ge.P : 1, cur);
-        h.F_params = stage_array(h.F_params, h.Fe.P > 0 ? h.Fe.P : 1, cur);
-    } else {
-        h.p = stage_array(h.p, h.P > 0 ? h.P : 1, cur);
-        if (h.q) h.q = stage_array(h.q, h.P > 0 ? h.P : 1, cur);
-    }
-}
-
-// Persistent tracker: each group of G lanes owns one shared-memory slab, pulls path indices from
-// the device-side queue (the `next_k` counter of threaded_solve, src/solve.jl:641, 660-667) and
-// writes its PathResult by path index (src/solve.jl:637, 670).
-template <int G>
-__global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant__ KArgs A) {
-    __shared__ KArgs sA;
-    if (threadIdx.x == 0) sA = A;
-    __syncthreads();
-    if (A.stage) {
-        DevHomotopy h = A.H;  // every thread computes the same pointers
-        unsigned char* cur = hc_smem;
-        stage_program(h.Fe, cur);
-        stage_program(h.Fj, cur);
-        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur); stage_program(h.Gj, cur); }
-        stage_params(h, cur);
-        __syncthreads();
-        if (threadIdx.x == 0) sA.H = h;
-        __syncthreads();
-    }
-    Lane<G, 0> L;
-    L.g.init();
-    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem + A.stage_bytes + (size_t)(threadIdx.x / G) * A.slab_bytes,
-          A.cold + ((size_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G) * A.cold_bytes);
-    L.phase = PH_IDLE; L.ev = EV_START; L.stop_pending = false;
-    const long long N = sA.B.N;
-    while (true) {
-        if (L.ev != EV_NONE) {  // a lane group handles its events at once (all its lanes are in the same state)
-            L.event_finish(sA.R);
-            long long k = -1;
-            if (L.ev == EV_START) {
-                if (L.g.lane == 0) k = (long long)atomicAdd(A.queue, 1ULL);
-                k = L.g.bcast(k, 0);
-                if (k >= N) break;
-            }
-            L.event_begin(k, k >= 0, sA.B, sA.R);
-        }
-        if (L.ev == EV_NONE && L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
-    }
-}
-
-// Main loop of the thread-per-path engine.  Lanes park with an event (path finished, toric stage over, free)
-// and the warp handles the parked lanes together once `refill_min` of them wait or nobody can step, so that
-// the once-per-path work (init_newton!, first predictor update, condition number of the endpoint) runs with
-// many lanes instead of stalling the warp once per lane.
-template <class LaneT>
-__device__ __forceinline__ void tpp_loop(LaneT& L, const KArgs& A, const KArgs& sA) {
-    L.phase = PH_IDLE; L.ev = EV_START; L.stop_pending = false;
-    const long long N = sA.B.N;
-    const unsigned lane = threadIdx.x & 31u;
-    bool drained = false;  // warp-uniform
-    while (true) {
-        const unsigned pend = __ballot_sync(0xffffffffu, L.ev != EV_NONE);
-        const unsigned act = __ballot_sync(0xffffffffu, L.ev == EV_NONE && L.phase != PH_IDLE);
-        if (pend == 0u && act == 0u) break;
-        if (__popc(pend) >= A.refill_min || act == 0u) {
-            if (L.ev != EV_NONE) L.event_finish(sA.R);
-            const unsigned want = __ballot_sync(0xffffffffu, L.ev == EV_START);
-            long long k = -1;
-            if (want != 0u && !drained) {
-                const int cnt = __popc(want);
-                long long base = 0;
-                if (lane == 0) base = (long long)atomicAdd(A.queue, (unsigned long long)cnt);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base + cnt >= N) drained = true;
-                if (L.ev == EV_START) k = base + __popc(want & ((1u << lane) - 1u));
-            }
-            if (L.ev != EV_NONE) L.event_begin(k, k >= 0 && k < N, sA.B, sA.R);
-        }
-        if (L.ev == EV_NONE && L.phase != PH_IDLE) L.iterate(sA.B, sA.R);
-    }
-}
-
-// Thread-per-path engine (n <= 14): every lane tracks its own path, the programs sit in shared memory,
-// the lane state in LOCAL memory: the hardware interleaves the lanes of
-// a warp (a warp access to element i is one contiguous 512 B segment, as in the explicit slabs
-// above), element addresses are base + immediate (no per-access stride multiply), and L1 keeps
-// local lines write-back, so the state that a step re-reads stays on the SM.
-template <int SLAB>
-__global__ void __launch_bounds__(256) hc_track_tpl_kernel(const __grid_constant__ KArgs A) {
-    __shared__ KArgs sA;
-    if (threadIdx.x == 0) sA = A;
-    __syncthreads();
-    if (A.stage) {
-        DevHomotopy h = A.H;
-        unsigned char* cur = hc_smem;
-        stage_program(h.Fe, cur, true);
-        stage_program(h.Fj, cur, true);
-        if (h.kind == H_STRAIGHT_LINE) { stage_program(h.Ge, cur, true); stage_program(h.Gj, cur, true); }
-        stage_params(h, cur);
-        __syncthreads();
-        if (threadIdx.x == 0) sA.H = h;
-        __syncthreads();
-    }
-    __align__(16) unsigned char slab[SLAB];
-    Lane<1, 2> L;
-    L.g.init();
-    L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, slab, slab + A.slab_bytes);
-    tpp_loop(L, A, sA);
-}
-
 // single-path operator-API hooks (one thread: valid for levelised and for sequential programs)
 __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, const cx* xlo, cx t, const double* tw, cx* u, cx* U) {
     __shared__ KArgs sA;
@@ -355,12 +217,46 @@ __global__ void hc_dfma_kernel(double* out, int iters) {
 
 // ------------------------------------------------------------------ launch planning
 struct Plan {
-    int engine;  // 0 = lane group per path (state in shared memory), 1 = thread per path (state in local memory)
+    int engine;  // 0 = lane group per path (state in shared memory), 1 = thread per path (state in local memory),
+                 // 2 = thread per path, kernel specialised for the system at run time (hc_jit.h)
     int grid, block, group, paths_per_block;
     size_t smem, slab, cold, stage_bytes;
     int stage;
     long long lanes;
+    std::shared_ptr<jit::Module> jit;
+    int jit_tape_cx;
 };
+
+// ------------------------------------------------------------------ specialised kernels: policy + module
+// HC_B200_JIT = 0: never; 1: always; auto (default): batches of at least HC_B200_JIT_MIN_PATHS paths -- compiling a
+// system costs seconds, which only a large batch repays (the reference's `compile = :mixed` makes the same trade).
+bool jit_wanted(const HomotopyH& H, long long N) {
+    const char* e = getenv("HC_B200_JIT");
+    if (e && !strcmp(e, "0")) return false;
+    if (H.dev.n > env_int("HC_B200_JIT_MAX_N", 24)) return false;
+    if (e && !strcmp(e, "1")) return true;
+#ifdef HC_HOST_SIM
+    return false;
+#else
+    if (getenv("HC_B200_ENGINE")) return false;  // an engine was pinned explicitly
+    return N >= env_int("HC_B200_JIT_MIN_PATHS", 8192);
+#endif
+}
+int jit_tape_cx(const HomotopyH& H) {  // tape of the DoubleDouble interpreter (2 cx per slot)
+    int We = H.F->eval.dev.W;
+    if (H.G && H.G->eval.dev.W > We) We = H.G->eval.dev.W;
+    return std::max(2 * We, 3 * H.dev.P);  // ... which also holds the parameter series of a predictor update (jit_fill_pser)
+}
+std::shared_ptr<jit::Module> jit_module(HomotopyH& H, bool poly, bool load = true) {
+    if (H.jit_mod[poly] && load) return H.jit_mod[poly];
+    jit::GenInput in;
+    in.kind = H.dev.kind; in.poly = poly; in.n = H.dev.n;
+    in.Fe = &H.F->eval.ref; in.Fj = &H.F->jac.ref;
+    if (H.G) { in.Ge = &H.G->eval.ref; in.Gj = &H.G->jac.ref; }
+    std::shared_ptr<jit::Module> M = jit::build_module(in, H.dev.P, jit_tape_cx(H), env_int("HC_B200_JIT_BLOCK", 256), load, env_int("HC_B200_JIT_SYNC", 1));
+    if (load) H.jit_mod[poly] = M;
+    return M;
+}
 
 size_t program_stage_bytes(const ProgramH& P, bool fast) {
     auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
@@ -384,10 +280,40 @@ int engine_for(int n) {
     return n <= env_int("HC_B200_TPP_MAX_N", 14) ? 1 : 0;
 }
 
-Plan make_plan(const HomotopyH& H, long long N) {
+Plan make_plan(HomotopyH& H, long long N, int mode) {
     Plan p;
-    memset(&p, 0, sizeof(p));
+    p.engine = 0; p.grid = p.block = p.group = p.paths_per_block = 0; p.smem = p.slab = p.cold = p.stage_bytes = 0; p.stage = 0; p.lanes = 0;
+    p.jit_tape_cx = 0;
     PathMem<0> dummy;
+    if (jit_wanted(H, N)) {
+        auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+        p.jit = jit_module(H, mode == MODE_POLYHEDRAL);
+        p.engine = 2; p.group = 1; p.stage = 1;
+        p.jit_tape_cx = jit_tape_cx(H);
+        p.slab = p.jit->hot; p.cold = p.jit->cold;
+        auto sb = [&](const ProgramH& P) {
+            return r16((size_t)P.dev.n_levels * sizeof(int)) + r16((size_t)P.dev.C * sizeof(cx)) + r16((size_t)P.dev.nu * sizeof(int2));
+        };
+        p.stage_bytes = sb(H.F->eval) + (H.dev.kind == H_STRAIGHT_LINE ? sb(H.G->eval) : 0) +
+                        2 * 16 * (size_t)std::max(1, std::max(H.dev.P, H.G ? H.G->P : 0));
+        p.block = p.jit->block;
+        int sms = 148;
+#ifndef HC_HOST_SIM
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#endif
+        const int per_sm = env_int("HC_B200_BLOCKS_PER_SM", 1);
+        long long want_lanes = N;
+        const long long lanes_cap = (long long)sms * per_sm * p.block;
+        if (want_lanes > lanes_cap) want_lanes = lanes_cap;
+        long long want = (want_lanes + p.block - 1) / p.block;
+        p.grid = (int)(want < 1 ? 1 : want);
+        p.paths_per_block = p.block;
+        p.smem = p.stage_bytes;
+        p.lanes = (long long)p.grid * p.block;
+        return p;
+    }
     SlabSizes ss = carve(dummy, H.dev.n, H.dev.P, H.dev.tape_cx, nullptr, nullptr);
     p.slab = ss.hot; p.cold = ss.cold;
 #ifndef HC_HOST_SIM
@@ -533,27 +459,30 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     R.mu = D.alloc<double>(N); R.accepted_steps = D.alloc<int>(N); R.rejected_steps = D.alloc<int>(N);
     R.steps_eg = D.alloc<int>(N); R.extended_precision_used = D.alloc<unsigned char>(N);
     R.counters = D.alloc<long long>((size_t)8 * N);
-    D.plan = make_plan(*H, N);
+    D.plan = make_plan(*H, N, mode);
     const Plan& pl = D.plan;
     D.A.queue = D.alloc<unsigned long long>(1);
     D.A.stage = pl.stage;
     D.A.slab_bytes = (int)pl.slab;
     D.A.cold_bytes = (int)pl.cold;
     if (pl.engine == 1) D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
-    else D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
+    else if (pl.engine == 0) D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
     D.A.stage_bytes = (int)pl.stage_bytes;
+    if (pl.engine == 2) { D.A.H.tape_cx = pl.jit_tape_cx; D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8); }
+    D.A.sync_cta = env_int("HC_B200_SYNC_CTA", 0);
 }
 
 #ifndef HC_HOST_SIM
-template <int SLAB>
-void launch_tpl(const DeviceBatch& D) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CK(cudaFuncSetAttribute(hc_track_tpl_kernel<SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+void launch_tpl(const DeviceBatch& D, int SLAB) {
+    const void* kern = hc_kernel_tpl(SLAB);
+    static bool attr_set[3] = {false, false, false};
+    bool& done = attr_set[SLAB == 12288 ? 0 : (SLAB == 24576 ? 1 : 2)];
+    if (!done) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         size_t cur = 0;
         CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
         if (cur < (size_t)SLAB + 8192) CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)SLAB + 8192));
-        attr_set = true;
+        done = true;
     }
     // the lane state lives in L1 (local memory): ask for the smallest shared-memory carve-out that holds
     // the staged programs of the CTAs resident on one SM
@@ -564,15 +493,40 @@ void launch_tpl(const DeviceBatch& D) {
         const int per_sm = (D.plan.grid + sms - 1) / sms;
         int pct = env_int("HC_B200_CARVEOUT", (int)((per_sm * (D.plan.smem + 3072) * 100 + 228 * 1024 - 1) / (228 * 1024)));
         if (pct > 100) pct = 100;
-        CK(cudaFuncSetAttribute(hc_track_tpl_kernel<SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    hc_track_tpl_kernel<SLAB><<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
+    void* args[] = {(void*)&D.A};
+    CK(cudaLaunchKernel(kern, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, 0));
 }
-template <int G>
-void launch_track(const DeviceBatch& D) {
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(hc_track_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
-    hc_track_kernel<G><<<D.plan.grid, D.plan.block, D.plan.smem, 0>>>(D.A);
+void launch_track(const DeviceBatch& D, int G) {
+    const void* kern = hc_kernel_group(G);
+    static bool attr_set[2] = {false, false};
+    bool& done = attr_set[G == 8 ? 0 : 1];
+    if (!done) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); done = true; }
+    void* args[] = {(void*)&D.A};
+    CK(cudaLaunchKernel(kern, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, 0));
+}
+#endif
+
+#ifndef HC_HOST_SIM
+void launch_jit(const DeviceBatch& D) {
+    jit::Module& M = *D.plan.jit;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!M.attr_set) {
+        CK(cudaFuncSetAttribute((const void*)M.track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+        size_t cur = 0;
+        CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        if (cur < M.slab + 8192) CK(cudaDeviceSetLimit(cudaLimitStackSize, M.slab + 8192));
+        M.attr_set = true;
+    }
+    const int per_sm = (D.plan.grid + sms - 1) / sms;
+    int pct = env_int("HC_B200_CARVEOUT", (int)((per_sm * (D.plan.smem + 3072) * 100 + 228 * 1024 - 1) / (228 * 1024)));
+    if (pct > 100) pct = 100;
+    CK(cudaFuncSetAttribute((const void*)M.track, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    void* args[] = {(void*)&D.A};
+    CK(cudaLaunchKernel((const void*)M.track, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, 0));
 }
 #endif
 
@@ -583,13 +537,11 @@ double run_batch(DeviceBatch& D) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, 0));
-    if (D.plan.engine == 1) {
+    if (D.plan.engine == 2) launch_jit(D);
+    else if (D.plan.engine == 1) {
         const size_t need = D.plan.slab + D.plan.cold;
-        if (need <= 12 * 1024) launch_tpl<12 * 1024>(D);
-        else if (need <= 24 * 1024) launch_tpl<24 * 1024>(D);
-        else launch_tpl<48 * 1024>(D);
-    } else if (D.plan.group == 32) launch_track<32>(D);
-    else launch_track<8>(D);
+        launch_tpl(D, need <= 12 * 1024 ? 12 * 1024 : (need <= 24 * 1024 ? 24 * 1024 : 48 * 1024));
+    } else launch_track(D, D.plan.group == 32 ? 32 : 8);
     CK(cudaEventRecord(e1, 0));
     CK(cudaGetLastError());
     CK(cudaEventSynchronize(e1));
@@ -598,25 +550,18 @@ double run_batch(DeviceBatch& D) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return ms;
 #else
+    if (D.plan.engine == 2) {
+        std::vector<unsigned char> hot(D.plan.slab + 16), cold(D.plan.cold + 16);
+        D.plan.jit->track(&D.A, (unsigned char*)(((uintptr_t)hot.data() + 15) & ~(uintptr_t)15), (unsigned char*)(((uintptr_t)cold.data() + 15) & ~(uintptr_t)15));
+        return 0.0;
+    }
     std::vector<unsigned char> slab(D.plan.slab + 16);
     Lane<1, 0> L;
     L.g.init();
     L.H = &D.A.H; L.O = &D.A.O; L.n = D.A.H.n;
     unsigned char* base = (unsigned char*)(((uintptr_t)slab.data() + 15) & ~(uintptr_t)15);
     carve(L.M, D.A.H.n, D.A.H.P, D.A.H.tape_cx, base, D.A.cold);
-    for (long long k = 0; k < D.N; ++k) {
-        L.phase = PH_IDLE; L.ev = EV_START; L.stop_pending = false;
-        L.event_begin(k, true, D.A.B, D.A.R);
-        while (true) {
-            if (L.ev != EV_NONE) {
-                L.event_finish(D.A.R);
-                if (L.ev == EV_START) break;  // path done
-                L.event_begin(-1, false, D.A.B, D.A.R);
-                continue;
-            }
-            L.iterate(D.A.B, D.A.R);
-        }
-    }
+    sim_loop(L, D.A);
     return 0.0;
 #endif
 }
@@ -657,6 +602,9 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         if (N <= 0) return 0;
+#ifndef HC_HOST_SIM
+        if (nodev()) throw std::string("HC_B200_NO_DEVICE is set: this process can only build kernels, not track (there is no CPU fallback)");
+#endif
         double tA = now_ms(), tB, tC, tD, kms;
         {
             DeviceBatch D;
@@ -879,6 +827,30 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         cx* du = (cx*)A_((size_t)n * 16);
         cx* dU = (cx*)A_((size_t)n * n * 16);
         cx tt = mk(t[0], t[1]);
+        // HC_B200_JIT=1: the operator API runs on the generated code of the specialised kernels (what the tracker
+        // executes there); evaluate_dd and order-4 series only exist in the interpreter
+        const char* jenv = getenv("HC_B200_JIT");
+        if (jenv && !strcmp(jenv, "1") && what != 1 && !(what == 3 && K > 3) && jit_wanted(*H, 1)) {
+            std::shared_ptr<jit::Module> M = jit_module(*H, false);
+            A.H.tape_cx = jit_tape_cx(*H);
+            unsigned char* jcold = (unsigned char*)A_(M->cold);
+            A.cold = jcold;
+#ifndef HC_HOST_SIM
+            if (M->hot > kSmemMax) throw std::string("system too large for one shared-memory slab");
+            CK(cudaFuncSetAttribute((const void*)M->hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+            void* args[] = {(void*)&A, (void*)&what, (void*)&K, (void*)&dx, (void*)&tt, (void*)&dtw, (void*)&du, (void*)&dU};
+            CK(cudaLaunchKernel((const void*)M->hook, dim3(1), dim3(1), args, M->hot, 0));
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+#else
+            std::vector<unsigned char> hot(M->hot + 16);
+            M->hook(&A, (unsigned char*)(((uintptr_t)hot.data() + 15) & ~(uintptr_t)15), jcold, what, K, dx, tt, dtw, du, dU);
+#endif
+            d2h(u, du, (size_t)n * 16);
+            if (U) d2h(U, dU, (size_t)n * n * 16);
+            for (void* p : owned) dev_free(p);
+            return 0;
+        }
 #ifndef HC_HOST_SIM
         if (slab > kSmemMax) throw std::string("system too large for one shared-memory slab");
         static bool attr_set = false;
@@ -921,6 +893,17 @@ int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double*
 int32_t hc_toric_set_weights(void* Hv, const double* w) {
     HomotopyH* H = (HomotopyH*)Hv;
     H->tw_hook.assign(w, w + H->dev.P);
+    return 0;
+}
+
+int32_t hc_jit_prepare(void* Hv, int32_t polyhedral, double* info) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try {
+        HomotopyH* H = (HomotopyH*)Hv;
+        if (!H) throw std::string("null homotopy handle");
+        std::shared_ptr<jit::Module> M = jit_module(*H, polyhedral != 0, false);
+        if (info) { info[0] = (double)M->cubin_bytes; info[1] = M->compile_ms; info[2] = (double)M->hot; info[3] = (double)M->cold; info[4] = M->from_cache ? 1.0 : 0.0; }
+    } catch (const std::string& e) { return fail(e); }
     return 0;
 }
 

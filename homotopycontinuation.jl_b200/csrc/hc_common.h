@@ -7,8 +7,14 @@
 //   src/model_kit/operations.jl:184-248                                     op_* kernels
 //   Julia Base.FastMath.div_fast / inv_fast                                 unscaled complex division
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (the per-system specialised kernels of hc_jit.h) has no host headers: the math functions are built in
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t; typedef unsigned long size_t;
+#else
 #include <cmath>
 #include <cstdint>
+#endif
 
 #if defined(__CUDACC__)
 #define HC_HD __host__ __device__ __forceinline__

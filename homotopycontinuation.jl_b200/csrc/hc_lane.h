@@ -101,7 +101,7 @@ struct Lane : Path<G, S> {
     int c_fact, c_ldiv;
 
     // ================================================================ valuation
-    HC_HD void val_init() { HC_PAR(i, 12 * n) M.val[i] = 0.0; g.sync(); logt2 = logt1 = HC_NAN; }
+    HC_HD void val_init() { HC_COLD_N  HC_PAR(i, 12 * n) M.val[i] = 0.0; g.sync(); logt2 = logt1 = HC_NAN; }
     HC_HD static double fdiff(double v, double s, double v2, double s2, double v1, double s1) {
         double D1 = s - s1, D2 = s - s2, D12 = s1 - s2;
         return (D2 * v1) / (D12 * D1) - ((D12 + D2) * v2) / (D12 * D2) - (D12 * v) / (D1 * D2);
@@ -113,6 +113,7 @@ struct Lane : Path<G, S> {
         nu = t * l; nu1 = t * l1 + l;
     }
     HC_HDN void val_update(double t) {  // valuation.jl:82-124
+        HC_COLD_N
         const int nn = n;
         const double logt = log(t);
         const bool diff = winding > 1 && logt2 == logt2;
@@ -143,10 +144,12 @@ struct Lane : Path<G, S> {
         logt1 = logt2; logt2 = logt;
     }
     HC_HD double eps_inf(int i) {
+        HC_COLD_N
         double vx = M.val[i], vt = M.val[n + i];
         return jmax(jmax(fabs(1.0 - vt / vx), fabs(M.val[2 * n + i] / vx)), fabs(M.val[3 * n + i] / vt));
     }
     HC_HD bool val_is_finite() {  // valuation.jl:175-205
+        HC_COLD_N
         const double ftol = O->val_finite_tol, delta = 1.0 / O->max_winding_number;
         const bool zero_is_finite = !O->zero_is_at_infinity;
         bool ok = true;
@@ -161,6 +164,7 @@ struct Lane : Path<G, S> {
         return g.rall(ok);
     }
     HC_HD void estimate_winding(int& m, double& min_err) {  // valuation.jl:207-228
+        HC_COLD_N
         m = 1; min_err = HC_INF;
         for (int k = 1; k <= O->max_winding_number; ++k) {
             double err = 0.0;
@@ -174,6 +178,7 @@ struct Lane : Path<G, S> {
     // ================================================================ endgame
     HC_HD double eg_jac_cond() { return jac_cond(&M.egrs, &M.egcs); }
     HC_HD void eg_scaling_update() {  // col_scaling .= weights(norm); row_scaling!(...)
+        HC_COLD_N
         HC_PAR(i, n) M.egcs[i] = M.w[i];
         g.sync();
         skeel(M.egrs, M.egcs, O->scaling_threshold);
@@ -181,6 +186,7 @@ struct Lane : Path<G, S> {
     // init!(endgame_tracker, x, t1; omega, mu, extended_precision)  endgame_tracker.jl:260-294
     // (first half: min_rel_step_size = 0 and the tracker_init request, see eg_request; this is the rest)
     HC_HDN void eg_init_post() {
+        HC_COLD_N
         eg_code = convert_code(code);
         singular_endgame = false; jtz_prev = jtz_cur = false;
         val_init(); eg_winding = 0;
@@ -191,6 +197,7 @@ struct Lane : Path<G, S> {
         last_t = HC_NAN;
     }
     HC_HDN void tracking_stopped() {  // :695-721
+        HC_COLD_N
         eg_accuracy = accuracy;
         if (eg_code == EG_success && eg_accuracy > 1e-14) refine_current_solution(1e-14, O->refine_steps);
         vcopy(M.sol, M.x, n);
@@ -213,6 +220,7 @@ struct Lane : Path<G, S> {
         return false;
     }
     HC_HDN bool check_at_infinity() {  // :424-499
+        HC_COLD_N
         if (!O->at_infinity_check) return false;
         const double ftol = O->val_finite_tol;
         const bool zero_is_finite = !O->zero_is_at_infinity;
@@ -261,6 +269,7 @@ struct Lane : Path<G, S> {
         return false;
     }
     HC_HDN void add_sample(double t) {  // :630-662
+        HC_COLD_N
         const int nn = n;
         const int mw = eg_winding;
         double s = nthroot(t, mw), mu_ = mw;
@@ -281,6 +290,7 @@ struct Lane : Path<G, S> {
         if (slot == 0) { stime[0] = s; scond[0] = kappa; } else if (slot == 1) { stime[1] = s; scond[1] = kappa; } else { stime[2] = s; scond[2] = kappa; }
     }
     HC_HDN double predict_endpoint() {  // :664-693
+        HC_COLD_N
         const int nn = n;
         if (singular_steps < 2) return HC_INF;
         CV S0 = M.samp.at(sidx0 * 2 * nn), S1 = M.samp.at(sidx1 * 2 * nn), S2 = M.samp.at(sidx2 * 2 * nn);
@@ -294,6 +304,7 @@ struct Lane : Path<G, S> {
         return err;
     }
     HC_HDN void switch_to_singular() {  // :501-524
+        HC_COLD_N
         singular_endgame = true;
         double t = st_t().re;
         bool allone = true;
@@ -315,6 +326,7 @@ struct Lane : Path<G, S> {
     }
     // First half of step!(::EndgameTracker): returns false when the path ended without a tracker step.
     HC_HDN bool eg_pre() {  // :329-358
+        HC_COLD_N
         if (steps_eg >= O->max_endgame_steps) { eg_code = EG_terminated_max_steps; return false; }
         if (B::ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) {
             bool nonan = true;
@@ -352,6 +364,7 @@ struct Lane : Path<G, S> {
     }
     // After each tracker step of the singular endgame's inner loop  :541-628
     HC_HDN void sing_post() {
+        HC_COLD_N
         bool max_steps = false;
         if ((steps_eg += 1) >= O->max_endgame_steps) { eg_code = EG_terminated_max_steps; max_steps = true; }
         else if (B::ext_steps() - ext_steps_eg_start > O->max_endgame_extended_steps) { eg_code = EG_terminated_max_extended_steps; max_steps = true; }
@@ -396,7 +409,7 @@ struct Lane : Path<G, S> {
         smax = 0.0; smin = HC_INF;
         for (int l = 0; l < P; ++l) { double r = raw[l]; if (r != 0.0) { smax = jmax(smax, r); smin = jmin(smin, r); } }
         double lam = use_min ? smin / target : smax / target;
-        B::tape_prog = B::tay_prog = nullptr;  // new weights: cached toric parameters are stale
+        B::tape_prog = B::tay_prog = nullptr; B::pv_kind = B::ps_kind = -1;  // new weights: cached toric parameters are stale
         g.sync();
         HC_PAR(l, P) M.tw[l] = raw[l] / lam;
         g.sync();
@@ -405,6 +418,7 @@ struct Lane : Path<G, S> {
 
     // ================================================================ results
     HC_HDN void write_result(const DevResults& R, int rc, bool success_at_zero) {
+        HC_COLD_N
         const long long k = pidx;
         const int nn = n;
         CV sol = success_at_zero ? M.sol : M.x;
@@ -424,6 +438,7 @@ struct Lane : Path<G, S> {
         }
     }
     HC_HDN void finish_eg(const DevResults& R) {  // PathResult(::EndgameTracker)  :847-888
+        HC_COLD_N
         const long long k = pidx;
         const int nn = n;
         const bool ok = eg_code == EG_success;
@@ -442,6 +457,7 @@ struct Lane : Path<G, S> {
         phase = PH_IDLE;
     }
     HC_HDN void finish_plain(const DevResults& R) {  // TrackerResult  tracker.jl:998-1012
+        HC_COLD_N
         const long long k = pidx;
         const int nn = n;
         vcopy(M.lastp, M.x, nn);
@@ -457,6 +473,7 @@ struct Lane : Path<G, S> {
         phase = PH_IDLE;
     }
     HC_HDN void finish_poly_failed(const DevResults& R) {  // polyhedral.jl:491-513
+        HC_COLD_N
         const long long k = pidx;
         const int nn = n;
         vcopy(M.lastp, M.x, nn);
@@ -478,6 +495,7 @@ struct Lane : Path<G, S> {
     }
     // a new path: load the start, reset the per-path state, request the first tracker initialisation
     HC_HDN void start_pre(long long k, const BatchIn& Bt) {
+        HC_COLD_N
         pidx = k; mode = Bt.mode;
         const int nn = n;
         g.sync();
@@ -499,7 +517,10 @@ struct Lane : Path<G, S> {
         g.sync();
         refined_extended_prec = false; factorized = scaled = false; stop_pending = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
-        B::tape_prog = B::tay_prog = nullptr;
+        B::tape_prog = B::tay_prog = nullptr; B::pv_kind = B::ps_kind = -1;
+#if defined(HC_JIT_GEN)
+        B::jit_bind_params();
+#endif
         B::tol_acc_limit = pow(O->a, (double)((1 << O->min_newton_iters) - 1)) * hfun(O->a);
         n_fact = n_ldiv = n_evaljac = n_eval = n_evaldd = n_tay1 = n_tay2 = n_tay3 = 0; c_fact = c_ldiv = 0;
         toric_acc = toric_rej = 0;
@@ -573,11 +594,13 @@ struct Lane : Path<G, S> {
         }
     }
     // One flat iteration of an active lane (ev == EV_NONE, phase != PH_IDLE).
-    HC_HD void iterate(const BatchIn&, const DevResults&) {
-        bool do_step = true;
-        if (phase == PH_EG) do_step = eg_pre();
-        bool ok = false;
-        if (do_step) ok = B::tracker_step();
+    // SYNC = true (lockstep kernels): called by every thread of the CTA each round, `act` = this lane is active.
+    template <bool SYNC>
+    HC_HD void iterate_t(bool act) {
+        bool do_step = act;
+        if (act && phase == PH_EG) do_step = eg_pre();
+        const bool ok = B::template tracker_step_t<SYNC>(do_step);
+        if (!act) return;
         switch (phase) {
             case PH_PLAIN: if (code != TC_tracking) ev = EV_FINISH_PLAIN; break;
             case PH_TORIC_A: case PH_TORIC_B: if (code != TC_tracking) ev = EV_TORIC_NEXT; break;
@@ -586,6 +609,7 @@ struct Lane : Path<G, S> {
             default: break;
         }
     }
+    HC_HD void iterate(const BatchIn&, const DevResults&) { iterate_t<false>(true); }
 };
 
 }  // namespace hc

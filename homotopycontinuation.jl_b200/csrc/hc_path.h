@@ -19,6 +19,17 @@ namespace hc {
 // load-only loops (reductions): unrolled so that the loads of four trips are in flight together
 #define HC_PARU(i, N) _Pragma("unroll 4") for (int i = g.lane; i < (N); i += G)
 
+// CTA-wide barriers of the lockstep (SYNC) instantiations of the tracker step: every thread of the CTA passes each of
+// them once per round whether or not its lane has work, so that the warps walk the same code together (a 32 KB
+// instruction cache per SM cannot feed warps that stream different straight-line code).
+#if defined(__CUDA_ARCH__)
+HC_D bool cta_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+HC_D void cta_sync() { __syncthreads(); }
+#else
+HC_HD bool cta_any(bool p) { return p; }
+HC_HD void cta_sync() {}
+#endif
+
 enum HKind : int { H_STRAIGHT_LINE = 0, H_PARAMETER = 1, H_COEFFICIENT = 2, H_TORIC = 3 };
 
 struct DevOptions {  // same field order as hc_options (include/hc_b200.h)
@@ -54,8 +65,10 @@ struct PathMem {
     using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
     CV x, xhat, xbar, tx, ptx1, ty1, pty1, xtemp, u, dx, r, A, LU, wr, wdx, work;
     CV sol, lastp, pred, ppred, samp, tape;
+    CV pv;   // specialised kernels: values of the homotopy parameters at the cached t (jit_refresh_params)
     DV<S> rbd;
     RV w, rs, rwork, egrs, egcs, ais, ait, aia, aic, val, tw;
+    RV ptw;  // specialised kernels, toric stage: t^w_i at the cached t
     IV ipiv, perm;
 };
 
@@ -65,7 +78,7 @@ struct PathMem {
 // accumulators) in a per-group scratch area in global memory.  With null bases it only counts.
 struct SlabSizes { size_t hot, cold; };
 template <int S>
-HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold) {
+HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold, bool jit = false) {
     static_assert(S == 0 || S == 2, "flat layouts only");
     size_t off = 0;
     unsigned char* base = hot;
@@ -74,8 +87,11 @@ HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* h
     M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n);
     M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
     M.wr = C(n); M.wdx = C(n); M.work = C(n);
-    M.tape = C((size_t)tape_cx);
+    // specialised kernels keep no fp64 / Taylor tape (slots are registers of the generated code): the parameter
+    // values take its place in the hot slab, the tape of the DoubleDouble interpreter moves to the cold part
+    if (jit) M.pv = C(P > 0 ? P : 1); else { M.tape = C((size_t)tape_cx); M.pv = M.tape; }
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.tw = R(P > 0 ? P : 1);
+    if (jit) M.ptw = R(P > 0 ? P : 1); else M.ptw = M.tw;
     M.ipiv = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
     M.perm = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
     SlabSizes s;
@@ -84,6 +100,7 @@ HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* h
     M.ptx1 = C(2 * n); M.ty1 = C(2 * n); M.pty1 = C(2 * n);
     M.sol = C(n); M.lastp = C(n); M.pred = C(n); M.ppred = C(n); M.samp = C(6 * n);
     M.rbd.v = C(2 * n);
+    if (jit) M.tape = C((size_t)tape_cx);
     M.egrs = R(n); M.egcs = R(n); M.ais = R(n); M.ait = R(n); M.aia = R(n); M.aic = R(n); M.val = R(12 * n);
     s.cold = (off + 15) & ~(size_t)15;
     return s;
@@ -103,7 +120,7 @@ struct NewtonResult { int code; double accuracy; int iters; double omega, theta,
 
 HC_HD double hfun(double a) { return 2 * a * (sqrt(4 * a * a + 1) - 2 * a); }  // tracker.jl:517
 
-HC_HD cx t_to_s_plane(cx t, int m) {  // predictor.jl:338-351
+static HC_HDN cx t_to_s_plane(cx t, int m) {  // predictor.jl:338-351 (cold: winding > 1 only)
     double r = cabs(t);
     if (t.im == 0.0 && t.re > 0) return mk(nthroot(r, m));
     double th = atan2(t.im, t.re);
@@ -120,7 +137,11 @@ struct Path {
     const DevHomotopy* H;
     const DevOptions* O;
     PathMem<S> M;
+#if defined(HC_JIT_N)
+    static constexpr int n = HC_JIT_N;  // specialised kernel: every loop over the variables has a constant trip count
+#else
     int n;
+#endif
     long long pidx;
     long long prow;  // row of the per-path parameter arrays this path reads (pidx, or pidx / param_div for sweeps)
     int kind;  // current homotopy kind (polyhedral paths switch TORIC -> COEFFICIENT)
@@ -132,6 +153,9 @@ struct Path {
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
     const DevProgram* tape_prog; int tape_kind; cx tape_t;  // whose inputs (constants, parameters at t) the fp64 tape holds
     const DevProgram* tay_prog; int tay_kind; cx tay_t;     // ... and the series tape
+    int pv_kind; cx pv_t;  // specialised kernels: homotopy kind and t the cached parameter values M.pv belong to (-1 = none)
+    int ps_kind; cx ps_t;  // ... and the cached parameter series in M.tape
+    const cx *jp, *jq;     // ... this path's start / target parameters
     double tol_acc_limit;  // accuracy-limit threshold of check_terminated (options only; cached per path: pow is 300 instructions)
     double min_step_size, min_rel_step_size;  // mutable copies (polyhedral.jl:474-488, endgame_tracker.jl:270)
     // ---- predictor (src/predictor.jl:72-103)
@@ -139,6 +163,12 @@ struct Path {
     cx pt, pprev_t, ps, pprev_s; int winding;
     // ---- counters (src/linear_algebra.jl:809-826 + flop accounting of SURVEY.md 8(d))
     int n_fact, n_ldiv, n_evaljac, n_eval, n_evaldd, n_tay1, n_tay2, n_tay3;
+
+    // Specialised kernels know n at compile time, which unrolls every loop over the variables.  That is what the
+    // regular predictor-corrector step wants; the once-per-path and endgame-only code shadows it with the run-time
+    // value so that its loops stay rolled (instruction footprint: the step should fit the instruction cache).
+    HC_HD int nrt() const { return H->n; }
+#define HC_COLD_N const int n = this->nrt(); (void)n;
 
     // ================================================================ norms (src/norm.jl)
     HC_HDN double inf_norm(CV x) {
@@ -284,7 +314,7 @@ struct Path {
         HC_PAR(i, P.n) store_in(tape, P.var_off + i, x[i], xlo ? (*xlo)[i] : mk(0.0), tag);
         g.sync();
         tape_prog = sizeof(T) == sizeof(cx) ? &P : nullptr; tape_kind = kind; tape_t = t;
-        tay_prog = nullptr;
+        tay_prog = nullptr; ps_kind = -1;
     }
 
     // thread-per-path engines run the segmented interpreters, lane groups the levelised ones
@@ -295,6 +325,64 @@ struct Path {
         if (G == 1) run_taylor_tape_seg<K>(P.fops, P.segs, P.n_segs, M.tape); else run_taylor_tape<K, G>(P, M.tape, g);
     }
     // u (and optionally the column-major Jacobian U) of H(x, t)
+#if defined(HC_JIT_GEN)
+    // ---- per-system generated code (hc_jitgen.h): straight-line evaluate / evaluate_and_jacobian / taylor with the
+    // tape slots in registers.  The parameters of a parameter / coefficient / toric homotopy are evaluated once per
+    // t into M.pv (the Newton iterations of a step and the predictor update after it share t).
+    HC_HDN void jit_refresh_params(cx t) {
+        if (pv_kind == kind && pv_t.re == t.re && pv_t.im == t.im) return;
+        const int P = H->P;
+        const ToricT tt = toric_t(t);
+        if (kind == H_TORIC) {
+            for (int i = 0; i < P; ++i) {
+                const double w = M.tw[i];
+                const double tw = t.re == 0.0 ? (w == 0.0 ? 1.0 : 0.0) : exp(w * tt.lt);
+                M.ptw[i] = tw;
+                M.pv[i] = pld<S>(H->p + i) * tw;
+            }
+        } else for (int i = 0; i < P; ++i) M.pv[i] = param_value(i, t, tt);
+        pv_kind = kind; pv_t = t;
+    }
+    // Taylor coefficients 1..3 of every parameter at t for homotopies whose parameters are full series (toric stage;
+    // the polyhedral driver runs the same code in its coefficient stage, where c2 = c3 = 0): written once per
+    // predictor update into the tape region of the DoubleDouble interpreter, which is idle then (M.tape[3 i + k - 1]);
+    // same formulas as param_series.  A rolled loop: 44 inlined copies of it were a quarter of the kernel's code.
+    HC_HDN void jit_fill_pser(cx t) {
+        if (ps_kind == kind && ps_t.re == t.re && ps_t.im == t.im) return;
+        const int P = H->P;
+        const ToricT tt = toric_t(t);
+        for (int i = 0; i < P; ++i) {
+            cx c1 = mk(0.0), c2 = mk(0.0), c3 = mk(0.0);
+            if (kind == H_TORIC) {
+                const cx u = pld<S>(H->p + i);
+                const double w = M.tw[i];
+                if (t.re == 0.0) {
+                    if (!(w < 1e-12) && fabs(w - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(w), 1.0)) c1 = u;
+                } else {
+                    const double tw = M.ptw[i], ti = tt.ti;
+                    const double tw1 = w * tw * ti; c1 = u * tw1;
+                    const double tw2 = 0.5 * (w - 1) * tw1 * ti; c2 = u * tw2;
+                    const double tw3 = (w - 2) * tw2 * ti / 3; c3 = u * tw3;
+                }
+            } else c1 = jp[i] - jq[i];
+            M.tape[3 * i] = c1; M.tape[3 * i + 1] = c2; M.tape[3 * i + 2] = c3;
+        }
+        ps_kind = kind; ps_t = t;
+    }
+    // this path's start / target parameter arrays behind generic pointers (per-path rows in global memory or the
+    // homotopy's own staged in shared memory): the generated code reads them without a branch per access
+    HC_HD void jit_bind_params() {
+        jp = H->path_p ? H->path_p + (size_t)prow * H->P : H->p;
+        jq = H->path_q ? H->path_q + (size_t)prow * H->P : H->q;
+    }
+#include HC_JIT_GEN
+    HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
+        if (U) n_evaljac++; else n_eval++;
+        if (kind != H_STRAIGHT_LINE) jit_refresh_params(t);
+        if (U) jit_evaljac(u, *U, x, t); else jit_eval(u, x, t);
+        g.sync();
+    }
+#else
     HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
         const int nn = n;
         const bool jac = U != nullptr;
@@ -328,6 +416,7 @@ struct Path {
             g.sync();
         }
     }
+#endif  // HC_JIT_GEN
     // DoubleDouble re-evaluation of the residual, rounded to fp64 on store
     // (newton_corrector.jl:104-105; straight_line_homotopy.jl:81-94: combine in DD)
     HC_HDN void eval_dd(CV u, CV x, const CV* xlo, cx t) {
@@ -401,6 +490,12 @@ struct Path {
     template <int K>
     HC_HDN void taylor(CV u, CV tx, cx t) {
         if (K == 1) n_tay1++; else if (K == 2) n_tay2++; else n_tay3++;
+#if defined(HC_JIT_GEN)
+        static_assert(K <= 3, "specialised kernels generate the orders the tracker uses");
+        if (kind != H_STRAIGHT_LINE) jit_refresh_params(t);
+        if (K == 1) jit_taylor1(u, tx, t); else if (K == 2) jit_taylor2(u, tx, t); else jit_taylor3(u, tx, t);
+        g.sync();
+#else
         CV tape = M.tape;
         HC_PAR(i, n) u[i] = mk(0.0);
         if (kind == H_STRAIGHT_LINE) {  // straight_line_homotopy.jl:130-154
@@ -424,6 +519,7 @@ struct Path {
             HC_PAR(k, H->Fe.nu) { int2 a = pld<S>(H->Fe.u_assign + k); u[a.x] = tape[a.y * HC_TS(K) + K]; }
             g.sync();
         }
+#endif
     }
 
     // ================================================================ linear algebra
@@ -513,7 +609,10 @@ struct Path {
         int rowof[N];  // original row that currently sits in position i
 #pragma unroll
         for (int i = 0; i < N; ++i) rowof[i] = i;
-#pragma unroll
+        // The loop over the columns stays rolled (j is uniform over the warp, so the `k < j` / `i >= j` guards below are
+        // branches or predicates, not divergence): the instruction footprint is O(N^2) instead of O(N^3) -- a fully
+        // unrolled N = 9 instance was 46 KB of SASS, more than the instruction cache of an SM holds.
+#pragma unroll 1
         for (int j = 0; j < N; ++j) {
             cx col[N];
 #pragma unroll
@@ -523,27 +622,32 @@ struct Path {
                 for (int i = 0; i < N; ++i) col[i] = col[i] * M.rs[rowof[i]];
             }
 #pragma unroll
-            for (int k = 0; k < j; ++k) {
+            for (int k = 0; k < N - 1; ++k) {
+                if (k >= j) break;
 #pragma unroll
                 for (int i = k + 1; i < N; ++i) col[i] = cfnma(LU[k * N + i], col[k], col[i]);
             }
             double amax = -1.0; int kp = j;
 #pragma unroll
-            for (int i = j; i < N; ++i) { double v = abs2(col[i]); if (v > amax) { amax = v; kp = i; } }
+            for (int i = 0; i < N; ++i) { const double v = abs2(col[i]); if (i >= j && v > amax) { amax = v; kp = i; } }
             M.ipiv[j] = kp;
+            cx pinv = mk(1.0);
             if (amax > 0.0) {
-                if (kp != j) {
-                    const cx cj = col[j]; cx ck = cj;
-                    const int rj = rowof[j]; int rk = rj;
+                if (kp != j) {  // swap positions j and kp: the column in registers, the finished columns in memory
+                    cx cj = col[0], ck = col[0];
+                    int rj = rowof[0], rk = rowof[0];
 #pragma unroll
-                    for (int i = j + 1; i < N; ++i) if (i == kp) { ck = col[i]; col[i] = cj; rk = rowof[i]; rowof[i] = rj; }
-                    col[j] = ck; rowof[j] = rk;
+                    for (int i = 0; i < N; ++i) { if (i == j) { cj = col[i]; rj = rowof[i]; } if (i == kp) { ck = col[i]; rk = rowof[i]; } }
 #pragma unroll
+                    for (int i = 0; i < N; ++i) { if (i == j) { col[i] = ck; rowof[i] = rk; } else if (i == kp) { col[i] = cj; rowof[i] = rj; } }
                     for (int k = 0; k < j; ++k) { cx t0 = LU[k * N + j], t1 = LU[k * N + kp]; LU[k * N + j] = t1; LU[k * N + kp] = t0; }
                 }
-                const cx pinv = cinv(col[j]);
+                cx pj = col[0];
 #pragma unroll
-                for (int i = j + 1; i < N; ++i) col[i] = col[i] * pinv;
+                for (int i = 0; i < N; ++i) if (i == j) pj = col[i];
+                pinv = cinv(pj);
+#pragma unroll
+                for (int i = 0; i < N; ++i) if (i > j) col[i] = col[i] * pinv;
             }
 #pragma unroll
             for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
@@ -575,12 +679,16 @@ struct Path {
         for (int i = 0; i < N; ++i) x[i] = xr[i];
     }
 #define HC_REG_LU_MAX 12
+#if defined(HC_JIT_N)
+#define HC_REG_LU_DISPATCH(CALL) CALL((((HC_JIT_N) >= 2 && (HC_JIT_N) <= HC_REG_LU_MAX) ? (HC_JIT_N) : 2));
+#else
 #define HC_REG_LU_DISPATCH(CALL)                                                                    \
     switch (n) {                                                                                    \
         case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; \
         case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; case 9: CALL(9); break; \
         case 10: CALL(10); break; case 11: CALL(11); break; default: CALL(12); break;               \
     }
+#endif
     HC_HD bool use_reg_lu() const { return G == 1 && S != 1 && n >= 2 && n <= HC_REG_LU_MAX; }
     HC_HD void factorize(bool scale) {
         if (use_reg_lu()) {
@@ -590,6 +698,7 @@ struct Path {
         } else { lu_prepare(scale); lu_factor(); }
     }
     HC_HDN void lu_solve_adj(CV x) {  // :318-354 (in place)
+        HC_COLD_N
         const int nn = n;
         CV A = M.LU;
         for (int j = 0; j < nn; ++j) {  // U^H z = x: column j of U gives a dot product
@@ -615,6 +724,7 @@ struct Path {
     }
     // skeel_row_scaling!(d, A, c; threshold)  :432-459
     HC_HDN void skeel(RV d, RV c, double threshold) {
+        HC_COLD_N
         const int nn = n;
         double m = -HC_INF;
         HC_PAR(i, nn) {
@@ -669,6 +779,7 @@ struct Path {
     }
     // one sweep of mixed precision refinement (:528-544): residual A x - b accumulated in DD
     HC_HDN double refine_mixed(CV x, CV b, bool weighted) {
+        HC_COLD_N
         const int nn = n;
         HC_PAR(i, nn) {
             cdd acc = tocdd(-b[i]);
@@ -701,6 +812,7 @@ struct Path {
     }
     // Hager/Higham estimator of |diag(d_r)^-1 A^-1 diag(d_l)^-1|_inf  :585-682
     HC_HDN double inverse_inf_norm_est(const RV* dl, const RV* dr) {
+        HC_COLD_N
         const int nn = n;
         if (!factorized) factorize(false);
         CV y = M.work; RV x = M.rwork;
@@ -752,6 +864,7 @@ struct Path {
         return nanmin(gamma, HC_INF);
     }
     HC_HDN double a_inf_norm(const RV* dl, const RV* dr) {  // :684-707
+        HC_COLD_N
         const int nn = n;
         double nrm = -HC_INF;
         HC_PAR(i, nn) {
@@ -763,6 +876,7 @@ struct Path {
         return g.rmax(nrm);
     }
     HC_HDN double jac_cond(const RV* dl, const RV* dr) {  // :745-774
+        HC_COLD_N
         if (n == 1) {
             cx a0 = M.A[0]; double a = hypot(a0.re, a0.im);
             if (dl) a *= (*dl)[0];
@@ -781,6 +895,7 @@ struct Path {
 
     // ================================================================ norm weights (norm.jl:101-136)
     HC_HDN void norm_init(CV x) {
+        HC_COLD_N
         const double pn = inf_norm(x);
         HC_PAR(i, n) {
             double wi = cabs(x[i]);
@@ -839,6 +954,7 @@ struct Path {
     // cold parts of pred_update (winding > 1, singular endgame only), out of line to keep the regular step small
     HC_HDN void pu_splane(cx t) { pprev_s = ps; ps = t_to_s_plane(t, winding); }
     HC_HDN void pu_hermite(double nrm0, double nrm1) {
+        HC_COLD_N
         const int nn = n;
         CV x1 = M.tx.at(nn);
         cx mu_ = winding == 2 ? 2.0 * ps : (double)winding * cpowi(ps, winding - 1);
@@ -849,46 +965,57 @@ struct Path {
         if (local_error != local_error) { double q = nrm1 / nrm0; local_error = q * q * q; }
     }
     // update!(predictor, H, x, t, J, norm, xhat)  predictor.jl:158-284
-    HC_HDN void pred_update(cx t, bool have_xhat) {
+    // SYNC = true (lockstep kernels): called by every thread of the CTA once per round; lanes without an accepted
+    // step (`act` false) only keep the barriers company.  The warps re-align before each of the three Taylor passes.
+    template <bool SYNC>
+    HC_HDN void pred_update_t(bool act, cx t, bool have_xhat) {
         const int nn = n;
         CV x0 = M.tx, x1 = M.tx.at(nn), x2 = M.tx.at(2 * nn), x3 = M.tx.at(3 * nn);
-        HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i];
-        g.sync();
-        pprev_t = pt; pt = t;
-        if (winding > 1) pu_splane(t);
-        if (!have_xhat) local_error = HC_NAN;
-        else {
-            double ds = cabs(t - pprev_t), d2 = ds * ds;
-            local_error = wdist(M.xhat, M.x) / (d2 * d2);
+        double nrm0 = 0, nrm1 = 0, nrm2 = 0, nrm3 = 0, delta = 0;
+        if (SYNC) cta_sync();
+        if (act) {
+            HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i];
+            g.sync();
+            pprev_t = pt; pt = t;
+            if (winding > 1) pu_splane(t);
+            if (!have_xhat) local_error = HC_NAN;
+            else {
+                double ds = cabs(t - pprev_t), d2 = ds * ds;
+                local_error = wdist(M.xhat, M.x) / (d2 * d2);
+            }
+            HC_PAR(i, nn) { x0[i] = M.x[i]; if (winding > 1) M.ty1[i] = M.x[i]; }
+            g.sync();
+            nrm0 = wnorm(M.x);
+
+            taylor<1>(M.u, M.tx, t);
+            HC_PAR(i, nn) M.u[i] = -M.u[i];
+            g.sync();
+            ldiv(M.xtemp, M.u, false);
+            delta = refine_fixed(M.xtemp, M.u, true);
+            cond_H = delta / HC_EPS;
+            if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, false, 5, 1e-10);
+            nrm1 = wnorm(M.xtemp);
+            if (winding > 1) { pu_hermite(nrm0, nrm1); act = false; }
         }
-        HC_PAR(i, nn) { x0[i] = M.x[i]; if (winding > 1) M.ty1[i] = M.x[i]; }
-        g.sync();
-        double nrm0 = wnorm(M.x);
-
-        taylor<1>(M.u, M.tx, t);
-        HC_PAR(i, nn) M.u[i] = -M.u[i];
-        g.sync();
-        ldiv(M.xtemp, M.u, false);
-        double delta = refine_fixed(M.xtemp, M.u, true);
-        cond_H = delta / HC_EPS;
-        if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, false, 5, 1e-10);
-        double nrm1 = wnorm(M.xtemp);
-        if (winding > 1) { pu_hermite(nrm0, nrm1); return; }
-        vcopy(x1, M.xtemp, nn);
-        taylor<2>(M.u, M.tx, t);
-        HC_PAR(i, nn) M.u[i] = -M.u[i];
-        g.sync();
-        ldiv(M.xtemp, M.u, false);
-        if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, true, 4, 1e-10);
-        double nrm2 = wnorm(M.xtemp);
-        vcopy(x2, M.xtemp, nn);
-
+        if (SYNC) cta_sync();
+        if (act) {
+            vcopy(x1, M.xtemp, nn);
+            taylor<2>(M.u, M.tx, t);
+            HC_PAR(i, nn) M.u[i] = -M.u[i];
+            g.sync();
+            ldiv(M.xtemp, M.u, false);
+            if (delta > 1e-10) iterative_refinement(M.xtemp, M.u, true, 4, 1e-10);
+            nrm2 = wnorm(M.xtemp);
+            vcopy(x2, M.xtemp, nn);
+        }
+        if (SYNC) cta_sync();
+        if (!act) return;
         taylor<3>(M.u, M.tx, t);
         HC_PAR(i, nn) M.u[i] = -M.u[i];
         g.sync();
         ldiv(M.xtemp, M.u, false);
         if (delta > 1e-4) iterative_refinement(M.xtemp, M.u, true, 3, 1e-4);
-        double nrm3 = wnorm(M.xtemp);
+        nrm3 = wnorm(M.xtemp);
         vcopy(x3, M.xtemp, nn);
 
         double tau_ = HC_INF;
@@ -913,7 +1040,9 @@ struct Path {
         trust_region = tau_;
         if (local_error != local_error) { double q = 1.0 / tau_; local_error = (q * q) * (q * q); }
     }
+    HC_HD void pred_update(cx t, bool have_xhat) { pred_update_t<false>(true, t, have_xhat); }
     HC_HDN void cubic_hermite(CV xh, CV v0, CV d0, cx t0, CV v1, CV d1, cx t1, cx t) {  // predictor.jl:354-371
+        HC_COLD_N
         const int nn = n;
         if (t0.im == 0 && t1.im == 0 && t.im == 0) {
             double T = t.re, T0 = t0.re, T1 = t1.re;
@@ -946,6 +1075,7 @@ struct Path {
     }
     // cold half of predict (winding > 1 only): kept out of line so that the regular step's code stays small
     HC_HDN void predict_hermite(cx t, cx dt) {
+        HC_COLD_N
         const int nn = n;
         int mw = winding;
         cx s0 = t_to_s_plane(pprev_t, mw), s1 = t_to_s_plane(t, mw), sp = t_to_s_plane(t + dt, mw);
@@ -990,69 +1120,88 @@ struct Path {
     // are folded into ONE loop with a single evaluate/factorize/solve call site (`final` marks the
     // convergence pass), so that lanes of a warp that are in different Newton iterations still
     // execute the expensive primitives together.
-    HC_HDN NewtonResult newton(CV x0, cx t, double mu_, double omega_, bool ext, bool accurate_mu, bool first_correction) {
+    // SYNC = true (lockstep kernels): every thread of the CTA calls this once per round, `act` says whether its lane
+    // has a corrector to run; the trip count is CTA-uniform (lanes that are done idle through the remaining trips) and
+    // the warps re-align before the evaluation and before the factorization of every trip.
+    struct NewtonState { double ndxi, ndxim1, abar, mu; bool final; int i; };
+    // the part of a trip after evaluate + solve; true = the iteration ended and R is complete
+    HC_HD bool newton_decide(NewtonResult& R, NewtonState& s, double nd, CV xi, cx t, bool ext, bool accurate_mu, bool first_correction, double h_a) {
+        if (!s.final) {
+            s.ndxi = nd;
+            if (s.ndxi != s.ndxi) { R.code = NEWT_SINGULARITY; R.accuracy = s.ndxi; R.iters = s.i + 1; return true; }
+            axmy(xi, xi, M.dx);
+            if (s.i == 0) R.norm_dx0 = s.ndxi;
+            if (s.i == 1) R.omega = 2 * s.ndxi / (s.ndxim1 * s.ndxim1);
+            if (s.i >= 1) R.theta = s.ndxi / s.ndxim1;
+            if ((s.i >= 1 && R.theta > s.abar) || (s.i == 0 && !first_correction && 0.125 * R.norm_dx0 * R.omega > h_a)) {
+                R.code = NEWT_TERMINATED; R.accuracy = s.ndxi; R.iters = s.i + 1; return true;
+            }
+            if (R.omega * s.ndxi * s.ndxi < 2 * s.mu * sqrt(1 - 2 * h_a)) { s.final = true; return false; }
+            if (s.i == 10) { R.code = NEWT_MAX_ITERS; R.accuracy = s.mu; R.iters = 11; return true; }
+            s.ndxim1 = s.ndxi;
+            if (s.i >= 1) s.abar *= s.abar;
+            ++s.i;
+            return false;
+        }
+        axmy(xi, xi, M.dx);
+        double ndxip1 = nd;
+        if (ndxip1 != ndxip1) { R.code = NEWT_SINGULARITY; R.accuracy = ndxip1; R.iters = s.i + 1; return true; }
+        if (ndxip1 > sqrt(s.ndxi)) {
+            R.theta = ndxip1 / s.ndxi; R.code = NEWT_TERMINATED; R.accuracy = ndxip1; R.iters = s.i + 2; return true;
+        }
+        if (ndxip1 > 2 * s.mu && ext) {
+            eval_dd(M.r, xi, nullptr, t);
+            ldiv(M.dx, M.r, false);
+            s.ndxi = ndxip1;
+            s.mu = ndxip1 = wnorm(M.dx);
+        } else if (ndxip1 > 2 * s.mu || accurate_mu) {
+            eval_f64(M.r, nullptr, xi, t);
+            ldiv(M.dx, M.r, false);
+            s.mu = wnorm(M.dx);
+        } else s.mu = ndxip1;
+        if (s.i == 0) {
+            double ob = 2 * s.ndxi / (ndxip1 * ndxip1);
+            if (ob < R.omega) R.omega = ob; else R.omega *= 0.25;
+        }
+        R.code = NEWT_CONVERGED; R.accuracy = s.mu; R.iters = s.i + 2; return true;
+    }
+    template <bool SYNC>
+    HC_HDN NewtonResult newton_t(bool act, CV x0, cx t, double mu_, double omega_, bool ext, bool accurate_mu, bool first_correction) {
         const int nn = n;
         const double a = O->a, h_a = hfun(a);
         CV xi = M.xbar;
-        if (xi.p != x0.p) vcopy(xi, x0, nn);
-        NewtonResult R; R.mu_low = R.theta = R.norm_dx0 = HC_NAN; R.omega = omega_;
-        double ndxi = HC_NAN, ndxim1 = HC_NAN, abar = a;
-        bool final = false;
-        int i = 0;
+        if (act && xi.p != x0.p) vcopy(xi, x0, nn);
+        NewtonResult R; R.mu_low = R.theta = R.norm_dx0 = HC_NAN; R.omega = omega_; R.code = NEWT_TERMINATED; R.accuracy = HC_NAN; R.iters = 0;
+        NewtonState s; s.ndxi = s.ndxim1 = HC_NAN; s.abar = a; s.mu = mu_; s.final = false; s.i = 0;
+        bool live = act;
         while (true) {
-            eval_f64(M.r, &M.A, xi, t);
-            if (ext && !final) eval_dd(M.r, xi, nullptr, t);
-            updated();
-            if (ext && final) {
-                ldiv(M.dx, M.r, false);
-                R.mu_low = wnorm(M.dx);
-                eval_dd(M.r, xi, nullptr, t);
+            if (SYNC) { if (!cta_any(live)) break; } else if (!live) break;
+            if (live) {
+                eval_f64(M.r, &M.A, xi, t);
+                if (ext && !s.final) eval_dd(M.r, xi, nullptr, t);
+                updated();
             }
-            ldiv(M.dx, M.r, !final);
-            if (ext) iterative_refinement(M.dx, M.r, true, 3, abar * abar);
-            const double nd = wnorm(M.dx);
-            if (!final) {
-                ndxi = nd;
-                if (ndxi != ndxi) { R.code = NEWT_SINGULARITY; R.accuracy = ndxi; R.iters = i + 1; return R; }
-                axmy(xi, xi, M.dx);
-                if (i == 0) R.norm_dx0 = ndxi;
-                if (i == 1) R.omega = 2 * ndxi / (ndxim1 * ndxim1);
-                if (i >= 1) R.theta = ndxi / ndxim1;
-                if ((i >= 1 && R.theta > abar) || (i == 0 && !first_correction && 0.125 * R.norm_dx0 * R.omega > h_a)) {
-                    R.code = NEWT_TERMINATED; R.accuracy = ndxi; R.iters = i + 1; return R;
+            if (SYNC) cta_sync();
+            if (live) {
+                if (ext && s.final) {
+                    ldiv(M.dx, M.r, false);
+                    R.mu_low = wnorm(M.dx);
+                    eval_dd(M.r, xi, nullptr, t);
                 }
-                if (R.omega * ndxi * ndxi < 2 * mu_ * sqrt(1 - 2 * h_a)) { final = true; continue; }
-                if (i == 10) { R.code = NEWT_MAX_ITERS; R.accuracy = mu_; R.iters = 11; return R; }
-                ndxim1 = ndxi;
-                if (i >= 1) abar *= abar;
-                ++i;
-                continue;
+                ldiv(M.dx, M.r, !s.final);
+                if (ext) iterative_refinement(M.dx, M.r, true, 3, s.abar * s.abar);
+                const double nd = wnorm(M.dx);
+                if (newton_decide(R, s, nd, xi, t, ext, accurate_mu, first_correction, h_a)) live = false;
             }
-            axmy(xi, xi, M.dx);
-            double ndxip1 = nd;
-            if (ndxip1 != ndxip1) { R.code = NEWT_SINGULARITY; R.accuracy = ndxip1; R.iters = i + 1; return R; }
-            if (ndxip1 > sqrt(ndxi)) {
-                R.theta = ndxip1 / ndxi; R.code = NEWT_TERMINATED; R.accuracy = ndxip1; R.iters = i + 2; return R;
-            }
-            if (ndxip1 > 2 * mu_ && ext) {
-                eval_dd(M.r, xi, nullptr, t);
-                ldiv(M.dx, M.r, false);
-                ndxi = ndxip1;
-                mu_ = ndxip1 = wnorm(M.dx);
-            } else if (ndxip1 > 2 * mu_ || accurate_mu) {
-                eval_f64(M.r, nullptr, xi, t);
-                ldiv(M.dx, M.r, false);
-                mu_ = wnorm(M.dx);
-            } else mu_ = ndxip1;
-            if (i == 0) {
-                double ob = 2 * ndxi / (ndxip1 * ndxip1);
-                if (ob < R.omega) R.omega = ob; else R.omega *= 0.25;
-            }
-            R.code = NEWT_CONVERGED; R.accuracy = mu_; R.iters = i + 2; return R;
         }
+        return R;
+    }
+    HC_HD NewtonResult newton(CV x0, cx t, double mu_, double omega_, bool ext, bool accurate_mu, bool first_correction) {
+        return newton_t<false>(true, x0, t, mu_, omega_, ext, accurate_mu, first_correction);
     }
     // init_newton!  newton_corrector.jl:207-286
     HC_HDN bool init_newton(cx t, bool ext, double& omega_out, double& mu_out) {
+        HC_COLD_N
         const int nn = n;
         const double a = O->a, a7 = a * a * a * a * a * a * a;
         eval_f64(M.r, &M.A, M.x, t);
@@ -1141,6 +1290,7 @@ struct Path {
     // rank(J; rtol = 1e-14) < n ?  (tracker.jl:711-737).  One-sided Jacobi on the columns of LU (scratch);
     // only reached for invalid start values, so lane 0 does it alone.
     HC_HDN bool jacobian_rank_deficient() {
+        HC_COLD_N
         const int nn = n;
         int deficient = 0;
         if (g.lane == 0) {
@@ -1250,14 +1400,20 @@ struct Path {
         }
         return m_;
     }
-    // step!(tracker)  tracker.jl:851-926; returns true iff the step was accepted
-    HC_HDN bool tracker_step() {
+    // step!(tracker)  tracker.jl:851-926; returns true iff the step was accepted.
+    // SYNC = true (lockstep kernels): every thread of the CTA calls this once per round, `act` = this lane steps.
+    template <bool SYNC>
+    HC_HDN bool tracker_step_t(bool act) {
         const int nn = n;
-        cx t = st_t(), dt = st_dt(), tp = st_tp();
-        predict(t, dt);
-        norm_update(M.xhat);
-        NewtonResult R = newton(M.xhat, tp, mu, omega, extended_prec, false, accepted_steps == 0);
-        if (R.code == NEWT_CONVERGED) {
+        cx t = mk(0.0), dt = mk(0.0), tp = mk(0.0);
+        if (act) {
+            t = st_t(); dt = st_dt(); tp = st_tp();
+            predict(t, dt);
+            norm_update(M.xhat);
+        }
+        NewtonResult R = newton_t<SYNC>(act, M.xhat, tp, mu, omega, extended_prec, false, accepted_steps == 0);
+        const bool conv = act && R.code == NEWT_CONVERGED;
+        if (conv) {
             vcopy(M.x, M.xbar, nn);
             ds_prev = st_ds();
             st_s = st_sp;
@@ -1270,20 +1426,24 @@ struct Path {
                 accuracy = refine_current_solution(1e-14, 3);
                 refined_extended_prec = true;
             }
-            pred_update(st_t(), true);
+        }
+        pred_update_t<SYNC>(conv, conv ? st_t() : t, true);
+        if (conv) {
             tau = trust_region;
             accepted_steps += 1;
             ext_accepted_steps += extended_prec ? 1 : 0;
             last_steps_failed = 0;
-        } else {
+        } else if (act) {
             rejected_steps += 1;
             ext_rejected_steps += extended_prec ? 1 : 0;
             last_steps_failed += 1;
         }
+        if (!act) return false;
         update_stepsize(R);
         check_terminated();
         return last_steps_failed == 0;
     }
+    HC_HD bool tracker_step() { return tracker_step_t<false>(true); }
 };
 
 }  // namespace hc

@@ -157,6 +157,14 @@ int32_t hc_evaluate_and_jacobian(void* H, const double* x, const double* t, doub
 int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double* u);
 int32_t hc_toric_set_weights(void* H, const double* w);
 
+/* Specialised kernels (reference: `compile = true`, src/model_kit/compiled_system_homotopy.jl:178-243).  Large batches
+ * (HC_B200_JIT_MIN_PATHS, default 8192; HC_B200_JIT = 0 | 1 | auto) are tracked by a kernel that is generated and
+ * compiled for the system at run time (NVRTC, sm_100a): evaluate / Jacobian / Taylor become straight-line code with the
+ * tape slots in registers.  hc_jit_prepare builds that kernel ahead of the first batch (it needs no CUDA device and
+ * fills the on-disk cache); info, if not NULL, receives {cubin bytes, milliseconds, hot lane-state bytes, cold
+ * lane-state bytes, 1 if it came from the cache}.  polyhedral != 0: the variant hc_polyhedral_track_batch runs. */
+int32_t hc_jit_prepare(void* H, int32_t polyhedral, double* info);
+
 /* Page-locks (cudaHostRegister) / releases caller-owned host buffers -- start solutions, parameters, the arrays of
  * hc_results -- so that the copies of hc_track_batch run as DMA transfers.  Optional; the Julia host would pin
  * the arrays of its result struct once per solve (reference: results are plain Julia Vectors, src/solve.jl:637). */
