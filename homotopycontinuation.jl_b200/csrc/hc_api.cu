@@ -102,7 +102,7 @@ struct HomotopyH {
     SystemH* F = nullptr; SystemH* G = nullptr;
     std::vector<void*> owned;
     std::vector<double> tw_hook;  // weights set through hc_toric_set_weights (test hook)
-    std::shared_ptr<jit::Module> jit_mod[2];  // specialised kernels: [0] as created, [1] driven by the polyhedral tracker
+    std::shared_ptr<jit::Module> jit_mod[4];  // specialised kernels: [polyhedral driver ? 1 : 0] + 2 * [per-path parameter rows]
     ~HomotopyH() { for (void* p : owned) dev_free(p); }
 };
 
@@ -185,7 +185,7 @@ __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, cons
     L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = L.prow = 0; L.kind = sA.H.kind;
     carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold);
-    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr;
+    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr; L.a_in_lu = L.rs_raw = false;
     const int n = sA.H.n;
     if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
@@ -227,10 +227,13 @@ struct Plan {
     int jit_tape_cx;
 };
 
+const size_t kSmemMax = 227 * 1024 - 2048;  // dynamic shared memory per CTA (the kernels keep ~1 KB static)
+
 // ------------------------------------------------------------------ specialised kernels: policy + module
 // HC_B200_JIT = 0: never; 1: always; auto (default): batches of at least HC_B200_JIT_MIN_PATHS paths -- compiling a
 // system costs seconds, which only a large batch repays (the reference's `compile = :mixed` makes the same trade).
-bool jit_wanted(const HomotopyH& H, long long N) {
+bool jit_wanted(const HomotopyH& H, long long N, bool complex_t = false) {
+    if (complex_t && H.dev.kind != H_STRAIGHT_LINE) return false;  // the generated parameter code assumes real t
     const char* e = getenv("HC_B200_JIT");
     if (e && !strcmp(e, "0")) return false;
     if (H.dev.n > env_int("HC_B200_JIT_MAX_N", 24)) return false;
@@ -242,19 +245,42 @@ bool jit_wanted(const HomotopyH& H, long long N) {
     return N >= env_int("HC_B200_JIT_MIN_PATHS", 8192);
 #endif
 }
+size_t jit_stage_bytes(const HomotopyH& H) {  // what hc_jit_track stages: DoubleDouble interpreter tables + parameters
+    auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    auto sb = [&](const ProgramH& P) {
+        return r16((size_t)P.dev.n_levels * sizeof(int)) + r16((size_t)P.dev.C * sizeof(cx)) + r16((size_t)P.dev.nu * sizeof(int2));
+    };
+    return sb(H.F->eval) + (H.dev.kind == H_STRAIGHT_LINE ? sb(H.G->eval) : 0) + 2 * 16 * (size_t)std::max(1, std::max(H.dev.P, H.G ? H.G->P : 0));
+}
 int jit_tape_cx(const HomotopyH& H) {  // tape of the DoubleDouble interpreter (2 cx per slot)
     int We = H.F->eval.dev.W;
     if (H.G && H.G->eval.dev.W > We) We = H.G->eval.dev.W;
-    return std::max(2 * We, 3 * H.dev.P);  // ... which also holds the parameter series of a predictor update (jit_fill_pser)
+    return std::max(2 * We, 2 * H.dev.P);  // ... which also holds the factors of the parameter series during a predictor update (jit_fill_pfac)
 }
-std::shared_ptr<jit::Module> jit_module(HomotopyH& H, bool poly, bool load = true) {
-    if (H.jit_mod[poly] && load) return H.jit_mod[poly];
+std::shared_ptr<jit::Module> jit_module(HomotopyH& H, bool poly, bool load = true, bool path_params = false) {
+    const int slot = (poly ? 1 : 0) + (path_params ? 2 : 0);
+    if (H.jit_mod[slot] && load) return H.jit_mod[slot];
     jit::GenInput in;
-    in.kind = H.dev.kind; in.poly = poly; in.n = H.dev.n;
+    in.kind = H.dev.kind; in.poly = poly; in.n = H.dev.n; in.path_params = path_params;
     in.Fe = &H.F->eval.ref; in.Fj = &H.F->jac.ref;
     if (H.G) { in.Ge = &H.G->eval.ref; in.Gj = &H.G->jac.ref; }
-    std::shared_ptr<jit::Module> M = jit::build_module(in, H.dev.P, jit_tape_cx(H), env_int("HC_B200_JIT_BLOCK", 256), load, env_int("HC_B200_JIT_SYNC", 1));
-    if (load) H.jit_mod[poly] = M;
+    // Lanes per SM and where the LU factors live.  The factors are the most re-read piece of lane state; if
+    // block x n^2 x 16 B fit next to the staged programs they go to shared memory (thread-interleaved), and the block
+    // shrinks (in warps) until they do, down to HC_B200_JIT_MIN_BLOCK; otherwise they stay in local memory.
+    int block = env_int("HC_B200_JIT_BLOCK", 256);
+    int lu_smem = env_int("HC_B200_JIT_LU_SMEM", 0);  // measured: L1-cached local memory beats it (the rest of the lane state needs the L1)
+#ifdef HC_HOST_SIM
+    lu_smem = 0;
+#else
+    if (lu_smem) {
+        const size_t per_lane = (size_t)H.dev.n * H.dev.n * 16, avail = kSmemMax - jit_stage_bytes(H);
+        int b = block;
+        while (b > 32 && (size_t)b * per_lane > avail) b -= 32;
+        if ((size_t)b * per_lane <= avail && b >= env_int("HC_B200_JIT_MIN_BLOCK", 128)) block = b; else lu_smem = 0;
+    }
+#endif
+    std::shared_ptr<jit::Module> M = jit::build_module(in, H.dev.P, jit_tape_cx(H), block, load, env_int("HC_B200_JIT_SYNC", 1), lu_smem);
+    if (load) H.jit_mod[slot] = M;
     return M;
 }
 
@@ -265,7 +291,6 @@ size_t program_stage_bytes(const ProgramH& P, bool fast) {
 }
 
 const size_t kLocalSlabMax = 48 * 1024;      // largest instantiated local-memory slab (hc_track_tpl_kernel)
-const size_t kSmemMax = 227 * 1024 - 2048;  // dynamic shared memory per CTA (the kernels keep ~1 KB static)
 
 // Which engine tracks a system of n variables: one thread per path keeps every lane busy but its
 // state (O(n^2) per path) lives in L2/HBM; a lane group per path keeps the state in shared memory
@@ -280,22 +305,17 @@ int engine_for(int n) {
     return n <= env_int("HC_B200_TPP_MAX_N", 14) ? 1 : 0;
 }
 
-Plan make_plan(HomotopyH& H, long long N, int mode) {
+Plan make_plan(HomotopyH& H, long long N, int mode, bool complex_t = false, bool path_params = false) {
     Plan p;
     p.engine = 0; p.grid = p.block = p.group = p.paths_per_block = 0; p.smem = p.slab = p.cold = p.stage_bytes = 0; p.stage = 0; p.lanes = 0;
     p.jit_tape_cx = 0;
     PathMem<0> dummy;
-    if (jit_wanted(H, N)) {
-        auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-        p.jit = jit_module(H, mode == MODE_POLYHEDRAL);
+    if (jit_wanted(H, N, complex_t)) {
+        p.jit = jit_module(H, mode == MODE_POLYHEDRAL, true, path_params);
         p.engine = 2; p.group = 1; p.stage = 1;
         p.jit_tape_cx = jit_tape_cx(H);
         p.slab = p.jit->hot; p.cold = p.jit->cold;
-        auto sb = [&](const ProgramH& P) {
-            return r16((size_t)P.dev.n_levels * sizeof(int)) + r16((size_t)P.dev.C * sizeof(cx)) + r16((size_t)P.dev.nu * sizeof(int2));
-        };
-        p.stage_bytes = sb(H.F->eval) + (H.dev.kind == H_STRAIGHT_LINE ? sb(H.G->eval) : 0) +
-                        2 * 16 * (size_t)std::max(1, std::max(H.dev.P, H.G ? H.G->P : 0));
+        p.stage_bytes = jit_stage_bytes(H);
         p.block = p.jit->block;
         int sms = 148;
 #ifndef HC_HOST_SIM
@@ -310,7 +330,7 @@ Plan make_plan(HomotopyH& H, long long N, int mode) {
         long long want = (want_lanes + p.block - 1) / p.block;
         p.grid = (int)(want < 1 ? 1 : want);
         p.paths_per_block = p.block;
-        p.smem = p.stage_bytes;
+        p.smem = p.stage_bytes + (p.jit->lu_smem ? (size_t)p.block * H.dev.n * H.dev.n * 16 : 0);
         p.lanes = (long long)p.grid * p.block;
         return p;
     }
@@ -459,7 +479,7 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     R.mu = D.alloc<double>(N); R.accepted_steps = D.alloc<int>(N); R.rejected_steps = D.alloc<int>(N);
     R.steps_eg = D.alloc<int>(N); R.extended_precision_used = D.alloc<unsigned char>(N);
     R.counters = D.alloc<long long>((size_t)8 * N);
-    D.plan = make_plan(*H, N, mode);
+    D.plan = make_plan(*H, N, mode, B.t1.im != 0.0 || B.t0.im != 0.0, path_p != nullptr || path_q != nullptr);
     const Plan& pl = D.plan;
     D.A.queue = D.alloc<unsigned long long>(1);
     D.A.stage = pl.stage;
@@ -830,7 +850,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         // HC_B200_JIT=1: the operator API runs on the generated code of the specialised kernels (what the tracker
         // executes there); evaluate_dd and order-4 series only exist in the interpreter
         const char* jenv = getenv("HC_B200_JIT");
-        if (jenv && !strcmp(jenv, "1") && what != 1 && !(what == 3 && K > 3) && jit_wanted(*H, 1)) {
+        if (jenv && !strcmp(jenv, "1") && what != 1 && !(what == 3 && K > 3) && jit_wanted(*H, 1, t[1] != 0.0)) {
             std::shared_ptr<jit::Module> M = jit_module(*H, false);
             A.H.tape_cx = jit_tape_cx(*H);
             unsigned char* jcold = (unsigned char*)A_(M->cold);
@@ -864,7 +884,7 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         L.g.init();
         L.H = &A.H; L.O = &A.O; L.n = n; L.pidx = L.prow = 0; L.kind = A.H.kind;
         carve(L.M, n, P, A.H.tape_cx, (unsigned char*)(((uintptr_t)mem.data() + 15) & ~(uintptr_t)15), A.cold);
-        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr;
+        L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr; L.a_in_lu = L.rs_raw = false;
         if (dtw) for (int i = 0; i < P; ++i) L.M.tw[i] = dtw[i];
         if (what == 3) for (int i = 0; i < K * n; ++i) L.M.tx[i] = dx[i]; else for (int i = 0; i < n; ++i) L.M.x[i] = dx[i];
         if (what == 0) L.eval_f64(L.M.u, nullptr, L.M.x, tt);
@@ -896,12 +916,12 @@ int32_t hc_toric_set_weights(void* Hv, const double* w) {
     return 0;
 }
 
-int32_t hc_jit_prepare(void* Hv, int32_t polyhedral, double* info) {
+int32_t hc_jit_prepare(void* Hv, int32_t flags, double* info) {
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         HomotopyH* H = (HomotopyH*)Hv;
         if (!H) throw std::string("null homotopy handle");
-        std::shared_ptr<jit::Module> M = jit_module(*H, polyhedral != 0, false);
+        std::shared_ptr<jit::Module> M = jit_module(*H, (flags & 1) != 0, false, (flags & 2) != 0);
         if (info) { info[0] = (double)M->cubin_bytes; info[1] = M->compile_ms; info[2] = (double)M->hot; info[3] = (double)M->cold; info[4] = M->from_cache ? 1.0 : 0.0; }
     } catch (const std::string& e) { return fail(e); }
     return 0;

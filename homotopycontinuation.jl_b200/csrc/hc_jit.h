@@ -35,7 +35,7 @@ namespace hc {
 namespace jit {
 
 struct Module {
-    int n = 0, block = 128;
+    int n = 0, block = 128, lu_smem = 0;
     size_t hot = 0, cold = 0, slab = 0;  // lane state: bytes in the hot / cold part, local slab of the kernel
     double compile_ms = 0;
     bool from_cache = false;
@@ -167,11 +167,11 @@ inline std::string cache_dir() {
 
 // Builds (or fetches) the specialised module of one homotopy.  load = false: generate + compile only (no CUDA device
 // needed: NVRTC targets sm_100a offline); the cubin lands in the disk cache.
-inline std::shared_ptr<Module> build_module(const GenInput& in, int P, int tape_cx, int block, bool load = true, int sync = 1) {
+inline std::shared_ptr<Module> build_module(const GenInput& in, int P, int tape_cx, int block, bool load = true, int sync = 1, int lu_smem = 0) {
     static std::map<uint64_t, std::shared_ptr<Module>> cache;
     const double t0 = wall_ms();
     PathMem<0> dummy;
-    const SlabSizes ss = carve(dummy, in.n, P, tape_cx, nullptr, nullptr, true);
+    const SlabSizes ss = carve(dummy, in.n, P, tape_cx, nullptr, nullptr, 1 | (lu_smem ? 2 : 0));
     const size_t slab = (ss.hot + ss.cold + 255) & ~(size_t)255;
     const std::string gen = generate_members(in);
     std::string unit;
@@ -179,6 +179,10 @@ inline std::shared_ptr<Module> build_module(const GenInput& in, int P, int tape_
     unit += "#define HC_JIT_SLAB " + std::to_string(slab) + "\n";
     unit += "#define HC_JIT_BLOCK " + std::to_string(block) + "\n";
     unit += "#define HC_JIT_SYNC " + std::to_string(sync) + "\n";
+#ifndef HC_HOST_SIM
+    unit += "#define HC_JIT_LU_SMEM " + std::to_string(lu_smem) + "\n";
+    unit += std::string("#define HC_JIT_PREFETCH ") + (getenv("HC_B200_JIT_PREFETCH") ? getenv("HC_B200_JIT_PREFETCH") : "0") + "\n";
+#endif
     unit += "#define HC_JIT_GEN \"hc_jit_gen.inc\"\n";
     unit += "#include \"hc_jit_unit.h\"\n";
     const std::string dir = csrc_dir();
@@ -193,7 +197,7 @@ inline std::shared_ptr<Module> build_module(const GenInput& in, int P, int tape_
     auto it = cache.find(h);
     if (it != cache.end() && load) return it->second;
     auto M = std::make_shared<Module>();
-    M->n = in.n; M->block = block; M->hot = ss.hot; M->cold = ss.cold; M->slab = slab;
+    M->n = in.n; M->block = block; M->hot = ss.hot; M->cold = ss.cold; M->slab = slab; M->lu_smem = lu_smem;
     char hex[32];
     snprintf(hex, sizeof hex, "%016llx", (unsigned long long)h);
     const std::string cdir = cache_dir();

@@ -4,6 +4,7 @@
 //     #define HC_JIT_SLAB 7424        // bytes of lane state (hot + cold) in local memory
 //     #define HC_JIT_BLOCK 128
 //     #define HC_JIT_SYNC 1           // lockstep rounds (tpp_loop_sync)
+//     #define HC_JIT_LU_SMEM 1        // LU factors thread-interleaved in shared memory (SV<cx, 3>)
 //     #define HC_JIT_GEN "hc_jit_gen.inc"   // evaluate / evaluate_and_jacobian / taylor of THIS system (hc_jitgen.h)
 //     #include "hc_jit_unit.h"
 //
@@ -35,7 +36,12 @@ extern "C" __global__ void __launch_bounds__(HC_JIT_BLOCK, 1) hc_jit_track(const
     Lane<1, 2> L;
     L.g.init();
     L.H = &sA.H; L.O = &sA.O;
-    carve(L.M, HC_JIT_N, sA.H.P, sA.H.tape_cx, slab, slab + A.slab_bytes, true);
+#if HC_JIT_LU_SMEM
+    carve(L.M, HC_JIT_N, sA.H.P, sA.H.tape_cx, slab, slab + A.slab_bytes, 3);
+    L.M.LU.p = (unsigned)__cvta_generic_to_shared(hc_smem + A.stage_bytes) + 16u * threadIdx.x;  // thread-interleaved (SV<cx, 3>)
+#else
+    carve(L.M, HC_JIT_N, sA.H.P, sA.H.tape_cx, slab, slab + A.slab_bytes, 1);
+#endif
 #if HC_JIT_SYNC
     tpp_loop_sync(L, A, sA);
 #else
@@ -52,7 +58,7 @@ extern "C" __global__ void hc_jit_hook(const KArgs A, int what, int K, const cx*
     L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.pidx = L.prow = 0; L.kind = sA.H.kind;
     carve(L.M, HC_JIT_N, sA.H.P, sA.H.tape_cx, hc_smem, A.cold, true);
-    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr; L.pv_kind = L.ps_kind = -1; L.jit_bind_params();
+    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.a_in_lu = L.rs_raw = false; L.tape_prog = L.tay_prog = nullptr; L.pv_kind = L.ps_kind = -1; L.jit_bind_params();
     const int n = HC_JIT_N;
     if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
@@ -79,7 +85,7 @@ extern "C" void hc_jit_sim_hook(const KArgs* A, unsigned char* hot, unsigned cha
     L.g.init();
     L.H = &A->H; L.O = &A->O; L.pidx = L.prow = 0; L.kind = A->H.kind;
     carve(L.M, HC_JIT_N, A->H.P, A->H.tape_cx, hot, cold, true);
-    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr; L.pv_kind = L.ps_kind = -1; L.jit_bind_params();
+    L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.a_in_lu = L.rs_raw = false; L.tape_prog = L.tay_prog = nullptr; L.pv_kind = L.ps_kind = -1; L.jit_bind_params();
     const int n = HC_JIT_N;
     if (tw) for (int i = 0; i < A->H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }

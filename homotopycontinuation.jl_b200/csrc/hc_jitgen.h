@@ -67,6 +67,9 @@ public:
     void group(const std::string& text, std::vector<int> defs, std::vector<int> deps) { stmts.push_back({text, std::move(defs), std::move(deps), false}); }
     int fresh() { return nvals++; }
     void sink(const std::string& text, std::vector<int> deps) { stmts.push_back({text, {}, std::move(deps), true}); }
+    // a sink that is emitted right after the statement that defines `id` (outputs leave their registers at once)
+    std::vector<std::pair<int, std::string>> after;
+    void sink_after(int id, const std::string& text) { after.push_back({id, text}); }
     // ---- complex arithmetic with symbolic zeros
     int mul(int a, int b) { return (a < 0 || b < 0) ? -1 : def(nm(a) + " * " + nm(b), {a, b}); }
     int add(int a, int b) { return a < 0 ? b : (b < 0 ? a : def(nm(a) + " + " + nm(b), {a, b})); }
@@ -88,6 +91,7 @@ public:
 
     std::string render(const char* indent = "        ") const {
         std::vector<char> live((size_t)nvals, 0), keep(stmts.size(), 0);
+        for (const auto& a : after) live[a.first] = 1;
         for (size_t i = stmts.size(); i-- > 0;) {
             const Stmt& s = stmts[i];
             bool k = s.sink;
@@ -97,7 +101,11 @@ public:
             for (int d : s.deps) if (d >= 0) live[d] = 1;
         }
         std::string out;
-        for (size_t i = 0; i < stmts.size(); ++i) if (keep[i]) { out += indent; out += stmts[i].text; out += "\n"; }
+        for (size_t i = 0; i < stmts.size(); ++i) if (keep[i]) {
+            out += indent; out += stmts[i].text; out += "\n";
+            for (int d : stmts[i].defs)
+                for (const auto& a : after) if (a.first == d) { out += indent; out += a.second; out += "\n"; }
+        }
         return out;
     }
 };
@@ -105,15 +113,16 @@ public:
 typedef std::vector<int> Ser;  // coefficients 0..K of a truncated series (ids, -1 = zero)
 
 // How a program reads its inputs.  mode: 0 = fixed parameters of F, 1 = fixed parameters of G (straight line),
-// 2 = homotopy parameters, linear in t (parameter / coefficient), 3 = homotopy parameters with a full series (toric,
-// or the polyhedral driver that switches toric -> coefficient at run time).
+// 2 = homotopy parameters, linear in t (parameter / coefficient), 3 = the polyhedral driver (toric stage, then
+// coefficient stage: decided per lane at run time), 4 = toric homotopy (full series).
 struct Leaves {
     Emit& E;
     const ProgCopy& pc;
     int mode, K;  // K < 0: scalar evaluation
+    int pp;       // the batch carries per-path parameter rows
     std::vector<Ser> cst, par, var;
     Ser tser;
-    Leaves(Emit& e, const ProgCopy& p, int mode_, int K_) : E(e), pc(p), mode(mode_), K(K_) {
+    Leaves(Emit& e, const ProgCopy& p, int mode_, int K_, int pp_ = 0) : E(e), pc(p), mode(mode_), K(K_), pp(pp_) {
         cst.resize((size_t)(pc.consts.size() / 2)); par.resize((size_t)pc.n_params); var.resize((size_t)pc.n_vars);
     }
     int width() const { return K < 0 ? 1 : K + 1; }
@@ -129,13 +138,19 @@ struct Leaves {
         if (mode == 0) s[0] = E.def("pld<S>(H->F_params + " + I + ")", {});
         else if (mode == 1) s[0] = E.def("pld<S>(H->G_params + " + I + ")", {});
         else {
-            s[0] = E.def("M.pv[" + I + "]", {});
-            if (K >= 1 && mode == 2) s[1] = E.def("jp[" + I + "] - jq[" + I + "]", {});
-            if (K >= 1 && mode == 3) {  // written by jit_fill_pser
-                const std::string b = "M.tape[" + std::to_string(3 * i);
-                s[1] = E.def(b + "]", {});
-                if (K >= 2) s[2] = E.def(b + " + 1]", {});
-                if (K >= 3) s[3] = E.def(b + " + 2]", {});
+            const std::string T = "<" + std::to_string(mode) + ", " + std::to_string(pp) + ">";
+            if (K < 1) s[0] = E.def("jit_par" + T + "(" + I + ", jc)", {});
+            else if (mode == 2) {
+                const int a = E.fresh(), b = E.fresh();
+                E.group("cx " + Emit::nm(a) + ", " + Emit::nm(b) + "; jit_pser_lin<" + std::to_string(pp) + ">(" + I + ", jc, " + Emit::nm(a) + ", " + Emit::nm(b) + ");", {a, b}, {});
+                s[0] = a; s[1] = b;
+            } else {
+                const int a = E.fresh(), b = E.fresh(), c = E.fresh(), d = E.fresh();
+                E.group("cx " + Emit::nm(a) + ", " + Emit::nm(b) + ", " + Emit::nm(c) + ", " + Emit::nm(d) + "; jit_pser" + T + "(" + I + ", jc, " + Emit::nm(a) +
+                            ", " + Emit::nm(b) + ", " + Emit::nm(c) + ", " + Emit::nm(d) + ");", {a, b, c, d}, {});
+                s[0] = a; s[1] = b;
+                if (K >= 2) s[2] = c;
+                if (K >= 3) s[3] = d;
             }
         }
         return par[i] = s;
@@ -334,6 +349,8 @@ inline std::vector<Ser> run_symbolic(Emit& E, const ProgCopy& pc, Leaves& L, int
 struct GenInput {
     int kind = 0;       // HKind of the homotopy handle
     bool poly = false;  // driven by the polyhedral tracker: toric stage first, coefficient stage second (kind switches at run time)
+    bool path_params = false;  // the batch carries per-path parameter rows (hc_track_batch path_p / path_q, hc_track_sweep)
+    int pmode() const { return poly ? 3 : (kind == H_TORIC ? 4 : 2); }
     const ProgCopy *Fe = nullptr, *Fj = nullptr, *Ge = nullptr, *Gj = nullptr;
     int n = 0;
 };
@@ -351,8 +368,19 @@ inline void outputs_of(const ProgCopy& pc, const std::vector<Ser>& cur, int coef
 inline void store_all(Emit& E, const char* dst, const std::vector<int>& v) {
     for (size_t i = 0; i < v.size(); ++i) {
         if (v[i] < 0) E.sink(std::string(dst) + "[" + std::to_string(i) + "] = mk(0.0);", {});
-        else E.sink(std::string(dst) + "[" + std::to_string(i) + "] = " + Emit::nm(v[i]) + ";", {v[i]});
+        else E.sink_after(v[i], std::string(dst) + "[" + std::to_string(i) + "] = " + Emit::nm(v[i]) + ";");
     }
+}
+// Jacobian entries (column-major, j = col * m + row): stored into U, into U2 as well if keepA, and -- if rowsum --
+// added to the Skeel row sums d_i = sum_j |U_ij| w_j (linear_algebra.jl:432-459) while they are in registers
+inline void store_jacobian(Emit& E, const std::vector<int>& U, int m, int n) {
+    for (size_t j = 0; j < U.size(); ++j) {
+        const std::string J = std::to_string(j), row = std::to_string(j % (size_t)m), col = std::to_string(j / (size_t)m);
+        if (U[j] < 0) { E.sink("U[" + J + "] = mk(0.0); if (keepA) U2[" + J + "] = mk(0.0);", {}); continue; }
+        const std::string v = Emit::nm(U[j]);
+        E.sink_after(U[j], "U[" + J + "] = " + v + "; if (keepA) U2[" + J + "] = " + v + "; if (rowsum) jrs" + row + " += cabs(" + v + ") * jw" + col + ";");
+    }
+    (void)n;
 }
 
 // evaluate! (jac = false) / evaluate_and_jacobian! (jac = true) of the homotopy at (x, t)
@@ -372,13 +400,27 @@ inline std::string gen_scalar(const GenInput& in, bool jac) {
         if (jac) { U.resize(Uf.size()); for (size_t i = 0; i < Uf.size(); ++i) U[i] = E.fma(ts, Ug[i], E.mul(tt, Uf[i])); }
     } else {
         const ProgCopy& PF = jac ? *in.Fj : *in.Fe;
-        Leaves LF(E, PF, 2, -1);
+        Leaves LF(E, PF, in.pmode(), -1, in.path_params);
         outputs_of(PF, run_symbolic(E, PF, LF, -1), 0, u, jac ? &U : nullptr);
     }
     store_all(E, "u", u);
-    if (jac) store_all(E, "U", U);
-    std::string s = jac ? "    HC_HDN void jit_evaljac(CV u, CV U, CV x, cx t) {\n" : "    HC_HDN void jit_eval(CV u, CV x, cx t) {\n";
+    const int m = (int)u.size(), n = in.n;
+    if (jac) store_jacobian(E, U, m, n);
+    std::string s = jac ? "    template <class UV, class UV2>\n    HC_HDN void jit_evaljac(CV u, UV U, UV2 U2, CV x, cx t, bool keepA, bool rowsum) {\n" : "    HC_HDN void jit_eval(CV u, CV x, cx t) {\n";
+    if (in.kind != H_STRAIGHT_LINE) s += "        const JPar jc = jit_par_ctx(t);\n";
+    if (jac) {
+        for (int i = 0; i < m; ++i) s += "        double jrs" + std::to_string(i) + " = 0.0;\n";
+        for (int j = 0; j < n; ++j) s += "        double jw" + std::to_string(j) + " = 0.0;\n";
+        s += "        if (rowsum) {";
+        for (int j = 0; j < n; ++j) s += " jw" + std::to_string(j) + " = M.w[" + std::to_string(j) + "];";
+        s += " }\n";
+    }
     s += E.render();
+    if (jac) {
+        s += "        if (rowsum) {";
+        for (int i = 0; i < m; ++i) s += " M.rs[" + std::to_string(i) + "] = jrs" + std::to_string(i) + ";";
+        s += " }\n";
+    }
     s += "    }\n";
     return s;
 }
@@ -400,13 +442,12 @@ inline std::string gen_taylor(const GenInput& in, int K) {
             u[i] = E.add(g, E.sub(E.mul(omt, fK[i]), fK1[i]));
         }
     } else {
-        const bool full = in.poly || in.kind == H_TORIC;
-        Leaves LF(E, *in.Fe, full ? 3 : 2, K);
+        Leaves LF(E, *in.Fe, in.pmode(), K, in.path_params);
         outputs_of(*in.Fe, run_symbolic(E, *in.Fe, LF, K), K, u, nullptr);
     }
     store_all(E, "u", u);
     std::string s = "    HC_HDN void jit_taylor" + std::to_string(K) + "(CV u, CV tx, cx t) {\n";
-    if (in.kind != H_STRAIGHT_LINE && (in.poly || in.kind == H_TORIC)) s += "        jit_fill_pser(t);\n";
+    if (in.kind != H_STRAIGHT_LINE) s += "        const JPar jc = jit_pser_ctx(t);\n";
     s += E.render();
     s += "    }\n";
     return s;

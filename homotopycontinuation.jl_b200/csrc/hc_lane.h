@@ -515,7 +515,7 @@ struct Lane : Path<G, S> {
             HC_PAR(i, nn) M.x[i] = Bt.starts[row * nn + i];
         }
         g.sync();
-        refined_extended_prec = false; factorized = scaled = false; stop_pending = false;
+        refined_extended_prec = false; factorized = scaled = false; B::a_in_lu = B::rs_raw = false; stop_pending = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
         B::tape_prog = B::tay_prog = nullptr; B::pv_kind = B::ps_kind = -1;
 #if defined(HC_JIT_GEN)

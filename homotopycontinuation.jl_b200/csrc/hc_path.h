@@ -12,6 +12,9 @@
 //   src/tracker.jl:509-619, 639-844, 851-926
 #pragma once
 #include "hc_tape.h"
+#ifndef HC_JIT_PREFETCH
+#define HC_JIT_PREFETCH 0
+#endif
 
 namespace hc {
 
@@ -60,12 +63,20 @@ struct DevHomotopy {
 };
 
 // ---------------------------------------------------------------- per-path memory
+// where the LU factors live: with the rest of the lane state, or (specialised thread-per-path kernels built with
+// HC_JIT_LU_SMEM) thread-interleaved in shared memory
+template <int S> struct LUView { using type = SV<cx, S>; };
+#if defined(HC_JIT_LU_SMEM) && HC_JIT_LU_SMEM
+template <> struct LUView<2> { using type = SV<cx, 3>; };
+#endif
 template <int S>
 struct PathMem {
     using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
-    CV x, xhat, xbar, tx, ptx1, ty1, pty1, xtemp, u, dx, r, A, LU, wr, wdx, work;
+    using LV = typename LUView<S>::type;
+    CV x, xhat, xbar, tx, ptx1, ty1, pty1, xtemp, u, dx, r, A, wr, wdx, work;
+    LV LU;
     CV sol, lastp, pred, ppred, samp, tape;
-    CV pv;   // specialised kernels: values of the homotopy parameters at the cached t (jit_refresh_params)
+    CV pv;   // (unused)
     DV<S> rbd;
     RV w, rs, rwork, egrs, egcs, ais, ait, aia, aic, val, tw;
     RV ptw;  // specialised kernels, toric stage: t^w_i at the cached t
@@ -77,19 +88,23 @@ struct PathMem {
 // (endgame samples, valuation history, at-infinity bookkeeping, Hermite-mode predictor data, DD
 // accumulators) in a per-group scratch area in global memory.  With null bases it only counts.
 struct SlabSizes { size_t hot, cold; };
+// flags: bit 0 = specialised kernel (no fp64 / Taylor tape), bit 1 = the LU factors are not part of the slab (shared memory)
 template <int S>
-HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold, bool jit = false) {
+HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* hot, unsigned char* cold, int flags = 0) {
+    const bool jit = (flags & 1) != 0, lu_out = (flags & 2) != 0;
     static_assert(S == 0 || S == 2, "flat layouts only");
     size_t off = 0;
     unsigned char* base = hot;
     auto C = [&](size_t k) { SV<cx, S> v = SV<cx, S>::make(base ? base + off : nullptr); off += 16 * k; return v; };
     auto R = [&](size_t k) { SV<double, S> v = SV<double, S>::make(base ? base + off : nullptr); off += 8 * k; return v; };
     M.x = C(n); M.xhat = C(n); M.xbar = C(n); M.tx = C(4 * n);
-    M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n); M.LU = C((size_t)n * n);
+    M.xtemp = C(n); M.u = C(n); M.dx = C(n); M.r = C(n); M.A = C((size_t)n * n);
+    if (!lu_out) { SV<cx, S> lu = C((size_t)n * n); M.LU.p = (decltype(M.LU.p))lu.p; }
     M.wr = C(n); M.wdx = C(n); M.work = C(n);
     // specialised kernels keep no fp64 / Taylor tape (slots are registers of the generated code): the parameter
     // values take its place in the hot slab, the tape of the DoubleDouble interpreter moves to the cold part
-    if (jit) M.pv = C(P > 0 ? P : 1); else { M.tape = C((size_t)tape_cx); M.pv = M.tape; }
+    if (!jit) M.tape = C((size_t)tape_cx);
+    M.pv = M.tape;
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.tw = R(P > 0 ? P : 1);
     if (jit) M.ptw = R(P > 0 ? P : 1); else M.ptw = M.tw;
     M.ipiv = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
@@ -131,7 +146,7 @@ static HC_HDN cx t_to_s_plane(cx t, int m) {  // predictor.jl:338-351 (cold: win
 
 template <int G, int S>
 struct Path {
-    using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>;
+    using CV = SV<cx, S>; using RV = SV<double, S>; using IV = SV<int, S>; using LV = typename PathMem<S>::LV;
     Grp<G> g;
     // ---- immutable context
     const DevHomotopy* H;
@@ -150,6 +165,7 @@ struct Path {
     double ds_prev, accuracy, omega, omega_prev, mu, tau;
     bool extended_prec, used_extended_prec, refined_extended_prec, keep_extended_prec, use_strict_beta_tau;
     bool factorized, scaled;  // MatrixWorkspace flags
+    bool a_in_lu, rs_raw;     // specialised kernels: the Jacobian sits in the LU buffer (factorize in place); M.rs holds raw Skeel row sums
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
     const DevProgram* tape_prog; int tape_kind; cx tape_t;  // whose inputs (constants, parameters at t) the fp64 tape holds
     const DevProgram* tay_prog; int tay_kind; cx tay_t;     // ... and the series tape
@@ -209,7 +225,8 @@ struct Path {
         } else { HC_PAR(i, len) dst[i] = src[i]; g.sync(); }
     }
     // y[i] -= a[i] * s for i in [lo, hi)
-    HC_HD void col_fnma(CV y, CV a, cx s, int lo, int hi) {
+    template <class YV, class AV>
+    HC_HD void col_fnma(YV y, AV a, cx s, int lo, int hi) {
         if (G == 1) {
             int i = lo;
             for (; i + 3 < hi; i += 4) {
@@ -327,60 +344,107 @@ struct Path {
     // u (and optionally the column-major Jacobian U) of H(x, t)
 #if defined(HC_JIT_GEN)
     // ---- per-system generated code (hc_jitgen.h): straight-line evaluate / evaluate_and_jacobian / taylor with the
-    // tape slots in registers.  The parameters of a parameter / coefficient / toric homotopy are evaluated once per
-    // t into M.pv (the Newton iterations of a step and the predictor update after it share t).
-    HC_HDN void jit_refresh_params(cx t) {
+    // tape slots in registers.  The homotopy parameters are computed where the code uses them -- p_i, q_i come from
+    // shared memory (or the path's row of the per-path arrays), parameter / coefficient homotopies need nothing else
+    // (t p + (1 - t) q); the toric stage keeps t^w_i per lane (M.ptw, one exp per parameter and t) and, for the three
+    // Taylor passes of a predictor update, the real factors of the coefficients 1..3 (M.tape viewed as doubles, idle
+    // then: the DoubleDouble interpreter owns it only during eval_dd).  Complex t never reaches these kernels
+    // (hc_api.cu keeps such batches on the interpreter).
+    struct JPar { double tr, omt, g1, ti; bool toric, at0; };
+    HC_HDN void jit_refresh_ptw(cx t) {  // M.ptw[i] = t^w_i (toric_homotopy.jl:145-177; t == 0: weights that are exactly 0 survive)
         if (pv_kind == kind && pv_t.re == t.re && pv_t.im == t.im) return;
         const int P = H->P;
         const ToricT tt = toric_t(t);
-        if (kind == H_TORIC) {
-            for (int i = 0; i < P; ++i) {
-                const double w = M.tw[i];
-                const double tw = t.re == 0.0 ? (w == 0.0 ? 1.0 : 0.0) : exp(w * tt.lt);
-                M.ptw[i] = tw;
-                M.pv[i] = pld<S>(H->p + i) * tw;
-            }
-        } else for (int i = 0; i < P; ++i) M.pv[i] = param_value(i, t, tt);
+        const bool at0 = t.re == 0.0;
+        int i = 0;
+        for (; i + 3 < P; i += 4) {  // the four weight loads are in flight together
+            const double w0 = M.tw[i], w1 = M.tw[i + 1], w2 = M.tw[i + 2], w3 = M.tw[i + 3];
+            const double e0 = at0 ? (w0 == 0.0 ? 1.0 : 0.0) : exp(w0 * tt.lt), e1 = at0 ? (w1 == 0.0 ? 1.0 : 0.0) : exp(w1 * tt.lt);
+            const double e2 = at0 ? (w2 == 0.0 ? 1.0 : 0.0) : exp(w2 * tt.lt), e3 = at0 ? (w3 == 0.0 ? 1.0 : 0.0) : exp(w3 * tt.lt);
+            M.ptw[i] = e0; M.ptw[i + 1] = e1; M.ptw[i + 2] = e2; M.ptw[i + 3] = e3;
+        }
+        for (; i < P; ++i) { const double w = M.tw[i]; M.ptw[i] = at0 ? (w == 0.0 ? 1.0 : 0.0) : exp(w * tt.lt); }
         pv_kind = kind; pv_t = t;
     }
-    // Taylor coefficients 1..3 of every parameter at t for homotopies whose parameters are full series (toric stage;
-    // the polyhedral driver runs the same code in its coefficient stage, where c2 = c3 = 0): written once per
-    // predictor update into the tape region of the DoubleDouble interpreter, which is idle then (M.tape[3 i + k - 1]);
-    // same formulas as param_series.  A rolled loop: 44 inlined copies of it were a quarter of the kernel's code.
-    HC_HDN void jit_fill_pser(cx t) {
-        if (ps_kind == kind && ps_t.re == t.re && ps_t.im == t.im) return;
-        const int P = H->P;
-        const ToricT tt = toric_t(t);
-        for (int i = 0; i < P; ++i) {
-            cx c1 = mk(0.0), c2 = mk(0.0), c3 = mk(0.0);
-            if (kind == H_TORIC) {
-                const cx u = pld<S>(H->p + i);
-                const double w = M.tw[i];
-                if (t.re == 0.0) {
-                    if (!(w < 1e-12) && fabs(w - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(w), 1.0)) c1 = u;
-                } else {
-                    const double tw = M.ptw[i], ti = tt.ti;
-                    const double tw1 = w * tw * ti; c1 = u * tw1;
-                    const double tw2 = 0.5 * (w - 1) * tw1 * ti; c2 = u * tw2;
-                    const double tw3 = (w - 2) * tw2 * ti / 3; c3 = u * tw3;
-                }
-            } else c1 = jp[i] - jq[i];
-            M.tape[3 * i] = c1; M.tape[3 * i + 1] = c2; M.tape[3 * i + 2] = c3;
-        }
-        ps_kind = kind; ps_t = t;
+    HC_HD JPar jit_par_ctx(cx t) {
+        JPar c; c.toric = kind == H_TORIC; c.at0 = false; c.ti = 0.0;
+        c.tr = t.re; c.omt = c.toric ? 0.0 : 1.0 - t.re; c.g1 = c.toric ? 0.0 : 1.0;
+        if (c.toric) jit_refresh_ptw(t);
+        return c;
     }
-    // this path's start / target parameter arrays behind generic pointers (per-path rows in global memory or the
-    // homotopy's own staged in shared memory): the generated code reads them without a branch per access
+    HC_HD JPar jit_pser_ctx(cx t) {
+        JPar c = jit_par_ctx(t);
+        c.at0 = t.re == 0.0;
+        c.ti = c.at0 ? 0.0 : 1.0 / t.re;
+        return c;
+    }
+    // real factors of the Taylor coefficients 0..3 of a toric parameter: c_k = u_i F_k (same formulas as param_series)
+    HC_HD void jit_tfac(int i, const JPar& c, double& f0, double& f1, double& f2, double& f3) const {
+        const double w = M.tw[i], tw = M.ptw[i];
+        if (c.at0) {
+            f0 = w < 1e-12 ? 1.0 : 0.0;
+            f1 = (!(w < 1e-12) && fabs(w - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(w), 1.0)) ? 1.0 : 0.0;
+            f2 = f3 = 0.0;
+        } else {
+            f0 = tw;
+            f1 = w * tw * c.ti;
+            f2 = 0.5 * (w - 1) * f1 * c.ti;
+            f3 = (w - 2) * f2 * c.ti / 3;
+        }
+    }
+    // this path's start / target parameter arrays behind generic pointers (per-path rows in global memory)
     HC_HD void jit_bind_params() {
         jp = H->path_p ? H->path_p + (size_t)prow * H->P : H->p;
         jq = H->path_q ? H->path_q + (size_t)prow * H->P : H->q;
     }
+    // PP: the batch carries per-path parameter rows; MODE 2: parameter / coefficient homotopy, 3: polyhedral driver
+    // (toric or coefficient stage, decided per lane at run time), 4: toric homotopy
+    template <int PP> HC_HD cx jit_ldp(int i) const { return PP ? jp[i] : pld<S>(H->p + i); }
+    template <int PP> HC_HD cx jit_ldq(int i) const { return PP ? jq[i] : pld<S>(H->q + i); }
+    template <int MODE, int PP> HC_HD cx jit_par(int i, const JPar& c) const {
+        const cx p = jit_ldp<PP>(i);
+        if (MODE == 4) return p * (double)M.ptw[i];
+        const cx q = jit_ldq<PP>(i);
+        const double f = (MODE == 3 && c.toric) ? (double)M.ptw[i] : c.tr;
+        return mk(f * p.re + c.omt * q.re, f * p.im + c.omt * q.im);
+    }
+    template <int PP> HC_HD void jit_pser_lin(int i, const JPar& c, cx& c0, cx& c1) const {
+        const cx p = jit_ldp<PP>(i), q = jit_ldq<PP>(i);
+        c0 = mk(c.tr * p.re + c.omt * q.re, c.tr * p.im + c.omt * q.im);
+        c1 = p - q;
+    }
+    template <int MODE, int PP> HC_HD void jit_pser(int i, const JPar& c, cx& c0, cx& c1, cx& c2, cx& c3) const {
+        const cx p = jit_ldp<PP>(i);
+        if (MODE == 4) {
+            double f0, f1, f2, f3;
+            jit_tfac(i, c, f0, f1, f2, f3);
+            c0 = p * f0; c1 = p * f1; c2 = p * f2; c3 = p * f3;
+            return;
+        }
+        const cx q = jit_ldq<PP>(i);
+        double f0 = c.tr, f1 = 1.0, f2 = 0.0, f3 = 0.0;
+        if (c.toric) jit_tfac(i, c, f0, f1, f2, f3);
+        c0 = mk(f0 * p.re + c.omt * q.re, f0 * p.im + c.omt * q.im);
+        c1 = mk(f1 * p.re - c.g1 * q.re, f1 * p.im - c.g1 * q.im);
+        c2 = p * f2; c3 = p * f3;
+    }
 #include HC_JIT_GEN
     HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
         if (U) n_evaljac++; else n_eval++;
-        if (kind != H_STRAIGHT_LINE) jit_refresh_params(t);
-        if (U) jit_evaljac(u, *U, x, t); else jit_eval(u, x, t);
+        if (U) { jit_evaljac(u, *U, *U, x, t, false, false); a_in_lu = false; rs_raw = false; } else jit_eval(u, x, t);
         g.sync();
+    }
+    // Evaluation of a corrector trip: the Jacobian goes straight into the LU buffer, which is then factorized in place
+    // (no A -> LU copy, no second pass over A for the Skeel row sums: the generated code adds them up while the
+    // entries are in registers).  keepA: a second copy lands in M.A -- the convergence trip's Jacobian is what the
+    // predictor's refinement and the extended-precision refinement multiply with later.
+    HC_HDN void eval_trip(CV u, CV x, cx t, bool keepA, bool rowsum) {
+        n_evaljac++;
+#if HC_JIT_PREFETCH
+        if (kind == H_TORIC && pv_kind == kind && pv_t.re == t.re) { const int P = H->P; for (int i = 0; i < P; i += 2) M.ptw.prefetch(i); }
+#endif
+        jit_evaljac(u, M.LU, M.A, x, t, keepA, rowsum);
+        a_in_lu = true; rs_raw = rowsum;
     }
 #else
     HC_HDN void eval_f64(CV u, const CV* U, CV x, cx t) {
@@ -492,7 +556,6 @@ struct Path {
         if (K == 1) n_tay1++; else if (K == 2) n_tay2++; else n_tay3++;
 #if defined(HC_JIT_GEN)
         static_assert(K <= 3, "specialised kernels generate the orders the tracker uses");
-        if (kind != H_STRAIGHT_LINE) jit_refresh_params(t);
         if (K == 1) jit_taylor1(u, tx, t); else if (K == 2) jit_taylor2(u, tx, t); else jit_taylor3(u, tx, t);
         g.sync();
 #else
@@ -528,7 +591,7 @@ struct Path {
     HC_HD void updated() { factorized = false; scaled = false; }
     HC_HDN void lu_prepare(bool scale) {
         const int nn = n;
-        if (!scale) { vcopy(M.LU, M.A, nn * nn); return; }
+        if (!scale) { for (int i = 0; i < nn * nn; i += G) if (i + g.lane < nn * nn) M.LU[i + g.lane] = M.A[i + g.lane]; g.sync(); return; }
         if (G == 1) {
             for (int j = 0; j < nn; ++j) {
                 int i = 0;
@@ -546,7 +609,7 @@ struct Path {
     }
     HC_HDN void lu_factor() {  // :130-184  right-looking, pivot = max abs2, first index wins ties
         const int nn = n;
-        CV A = M.LU;
+        LV A = M.LU;
         for (int k = 0; k < nn; ++k) {
             double amax = -1.0; int kp = k;
             for (int i = k + g.lane; i < nn; i += G) { double v = abs2(A[k * nn + i]); if (v > amax) { amax = v; kp = i; } }
@@ -579,7 +642,7 @@ struct Path {
     }
     HC_HDN void lu_solve(CV x) {  // :310-316 (in place)
         const int nn = n;
-        CV A = M.LU;
+        LV A = M.LU;
         if (g.lane == 0) for (int i = 0; i < nn; ++i) { int p = M.ipiv[i]; if (p != i) { cx tmp = x[i]; x[i] = x[p]; x[p] = tmp; } }
         g.sync();
         for (int j = 0; j < nn - 1; ++j) {
@@ -603,9 +666,11 @@ struct Path {
     // n^3/3 loads + n^2 stores instead of 2n^3/3 loads + n^3/3 stores.  Every element still sees
     // its updates in increasing k with the same cfnma, so LU, ipiv and the solutions are bit-identical
     // to lu_prepare + lu_factor / lu_solve above (linear_algebra.jl:130-184, 310-316).
-    template <int N>
-    HC_HDN void lu_factor_reg(bool scale) {
-        CV A = M.A, LU = M.LU;
+    // A: where the matrix sits -- M.A, or the LU buffer itself (in place: column j is read in full, in original row order,
+    // before its permuted, eliminated form is written back; the columns to its right are still untouched)
+    template <int N, class AV>
+    HC_HDN void lu_factor_reg(bool scale, AV A) {
+        LV LU = M.LU;
         int rowof[N];  // original row that currently sits in position i
 #pragma unroll
         for (int i = 0; i < N; ++i) rowof[i] = i;
@@ -660,7 +725,7 @@ struct Path {
     // x = (LU)^-1 P (scaled ? rs .* b : b); x may alias b
     template <int N>
     HC_HDN void lu_solve_reg(CV x, CV b, bool scale) {
-        CV A = M.LU;
+        LV A = M.LU;
         cx xr[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) { const int r = M.perm[i]; xr[i] = b[r]; if (scale) xr[i] = M.rs[r] * xr[i]; }
@@ -692,15 +757,21 @@ struct Path {
     HC_HD bool use_reg_lu() const { return G == 1 && S != 1 && n >= 2 && n <= HC_REG_LU_MAX; }
     HC_HD void factorize(bool scale) {
         if (use_reg_lu()) {
-#define HC_CALL_(NN) lu_factor_reg<NN>(scale)
-            HC_REG_LU_DISPATCH(HC_CALL_)
+            if (a_in_lu) {
+#define HC_CALL_(NN) lu_factor_reg<NN>(scale, M.LU)
+                HC_REG_LU_DISPATCH(HC_CALL_)
 #undef HC_CALL_
+            } else {
+#define HC_CALL_(NN) lu_factor_reg<NN>(scale, M.A)
+                HC_REG_LU_DISPATCH(HC_CALL_)
+#undef HC_CALL_
+            }
         } else { lu_prepare(scale); lu_factor(); }
     }
     HC_HDN void lu_solve_adj(CV x) {  // :318-354 (in place)
         HC_COLD_N
         const int nn = n;
-        CV A = M.LU;
+        LV A = M.LU;
         for (int j = 0; j < nn; ++j) {  // U^H z = x: column j of U gives a dot product
             double zr = 0.0, zi = 0.0;
             HC_PAR(i, j) { cx p = conj(A[j * nn + i]) * x[i]; zr += p.re; zi += p.im; }
@@ -743,12 +814,32 @@ struct Path {
         }
         g.sync();
     }
+    // second half of skeel for row sums that the generated Jacobian code left in d
+    HC_HDN void skeel_finish(RV d, double threshold) {
+        const int nn = n;
+        double m = -HC_INF;
+        HC_PAR(i, nn) m = nmax(m, (double)d[i]);
+        m = g.rmax(m);
+        const double s = threshold + m;
+        HC_PAR(i, nn) {
+            int e = 0; double di = d[i];
+            if (di != 0.0 && di == di && di < HC_INF) frexp(di, &e);
+            d[i] = (e < s) ? 1.0 : ldexp(1.0, -e);
+        }
+        g.sync();
+    }
     // ldiv!(x, J, b[, norm])  :389-408, 833-862;  x may alias b
     HC_HDN void ldiv(CV x, CV b, bool with_norm) {
         const int nn = n;
         n_ldiv++;
-        if (with_norm && !factorized) { skeel(M.rs, M.w, -30.0); scaled = true; }
-        if (nn == 1) { cx v = cdiv(b[0], M.A[0]); g.sync(); if (g.lane == 0) x[0] = v; g.sync(); return; }
+        if (with_norm && !factorized) {
+            if (rs_raw) { skeel_finish(M.rs, -30.0); rs_raw = false; } else skeel(M.rs, M.w, -30.0);
+            scaled = true;
+        }
+        if (nn == 1) { cx v = cdiv(b[0], a_in_lu ? (cx)M.LU[0] : (cx)M.A[0]); g.sync(); if (g.lane == 0) x[0] = v; g.sync(); return; }
+#if HC_JIT_PREFETCH
+        if (use_reg_lu()) { for (int i = 0; i < nn * nn; ++i) M.LU.prefetch(i); }
+#endif
         if (!factorized) factorize(scaled);
         if (use_reg_lu()) {
             const bool sc = scaled;
@@ -974,8 +1065,12 @@ struct Path {
         double nrm0 = 0, nrm1 = 0, nrm2 = 0, nrm3 = 0, delta = 0;
         if (SYNC) cta_sync();
         if (act) {
-            HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i];
-            g.sync();
+            // (x, x') of the previous update: read by the Hermite predictor only, i.e. once winding > 1; tx still holds
+            // them here, so the copy into the cold slab waits until then
+            if (winding > 1) { HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i]; g.sync(); }
+#if HC_JIT_PREFETCH
+            for (int i = 0; i < nn * nn; ++i) M.A.prefetch(i);  // refine_fixed multiplies with A after the first Taylor pass
+#endif
             pprev_t = pt; pt = t;
             if (winding > 1) pu_splane(t);
             if (!have_xhat) local_error = HC_NAN;
@@ -1177,6 +1272,9 @@ struct Path {
         while (true) {
             if (SYNC) { if (!cta_any(live)) break; } else if (!live) break;
             if (live) {
+#if defined(HC_JIT_GEN)
+                if (use_reg_lu()) eval_trip(M.r, xi, t, s.final || ext, !s.final); else
+#endif
                 eval_f64(M.r, &M.A, xi, t);
                 if (ext && !s.final) eval_dd(M.r, xi, nullptr, t);
                 updated();
@@ -1294,7 +1392,7 @@ struct Path {
         const int nn = n;
         int deficient = 0;
         if (g.lane == 0) {
-            CV V = M.LU;
+            LV V = M.LU;
             bool has_nan = false;
             for (int i = 0; i < nn * nn; ++i) { V[i] = M.A[i]; has_nan = has_nan || cisnan(M.A[i]); }
             if (!has_nan) {

@@ -82,6 +82,7 @@ struct SV<T, 0> {
     T* p;
     HC_HD T& operator[](int i) const { return p[i]; }
     HC_HD SV at(int off) const { SV r; r.p = p + off; return r; }
+    HC_HD void prefetch(int) const {}
     static HC_HD SV make(void* q) { SV r; r.p = (T*)q; return r; }
 };
 
@@ -145,6 +146,13 @@ struct SV<T, 2> {
     unsigned p;  // byte address in the thread's local window
     HC_HD LRef<T> operator[](int i) const { LRef<T> r; r.a = p + (unsigned)i * (unsigned)sizeof(T); return r; }
     HC_HD SV at(int off) const { SV r; r.p = p + (unsigned)off * (unsigned)sizeof(T); return r; }
+    // asks for the L1 line of element i (non-blocking): the lockstep kernels do this at the start of a phase for what the
+    // phase is about to read, so that the loads of all warps overlap instead of each paying an L2 round trip in turn
+    HC_HD void prefetch(int i) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("prefetch.local.L1 [%0];" ::"r"(p + (unsigned)i * (unsigned)sizeof(T)));
+#endif
+    }
     static HC_HD SV make(void* q) {
         SV r; r.p = 0u;
 #if defined(__CUDA_ARCH__)
@@ -153,6 +161,39 @@ struct SV<T, 2> {
         return r;
     }
 };
+
+// S = 3: shared memory, the threads of the CTA interleaved (specialised kernels, HC_JIT_BLOCK threads): element i of this
+// thread sits at p + i * HC_JIT_BLOCK * sizeof(T), so that a warp access to element i is one contiguous, conflict-free
+// 512 B row -- the same picture as local memory, but on the SM by construction, not by cache luck.  Holds the LU factors
+// (the most re-read piece of lane state: n^3 / 3 loads per factorization, n^2 per solve).
+#if defined(HC_JIT_BLOCK)
+template <class T> struct SRef;
+template <>
+struct SRef<cx> {
+    unsigned a;
+    HC_HD operator cx() const {
+        cx v = mk(0.0);
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(a));
+#endif
+        return v;
+    }
+    HC_HD const SRef& operator=(cx v) const {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.re), "d"(v.im));
+#endif
+        return *this;
+    }
+    HC_HD const SRef& operator=(const SRef& o) const { return *this = (cx)o; }
+};
+template <class T>
+struct SV<T, 3> {
+    unsigned p;  // shared-window byte address of this thread's element 0
+    HC_HD SRef<T> operator[](int i) const { SRef<T> r; r.a = p + (unsigned)i * (unsigned)(HC_JIT_BLOCK * sizeof(T)); return r; }
+    HC_HD SV at(int off) const { SV r; r.p = p + (unsigned)off * (unsigned)(HC_JIT_BLOCK * sizeof(T)); return r; }
+    HC_HD void prefetch(int) const {}
+};
+#endif
 
 template <int S>
 struct DV {  // vector of ComplexDF64: element i = cx 2i (re.hi, re.lo) and 2i+1 (im.hi, im.lo)

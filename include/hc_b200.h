@@ -162,8 +162,9 @@ int32_t hc_toric_set_weights(void* H, const double* w);
  * compiled for the system at run time (NVRTC, sm_100a): evaluate / Jacobian / Taylor become straight-line code with the
  * tape slots in registers.  hc_jit_prepare builds that kernel ahead of the first batch (it needs no CUDA device and
  * fills the on-disk cache); info, if not NULL, receives {cubin bytes, milliseconds, hot lane-state bytes, cold
- * lane-state bytes, 1 if it came from the cache}.  polyhedral != 0: the variant hc_polyhedral_track_batch runs. */
-int32_t hc_jit_prepare(void* H, int32_t polyhedral, double* info);
+ * lane-state bytes, 1 if it came from the cache}.  flags: bit 0 = the variant hc_polyhedral_track_batch runs, bit 1 = the
+ * variant for batches with per-path parameter rows (path_p / path_q, hc_track_sweep). */
+int32_t hc_jit_prepare(void* H, int32_t flags, double* info);
 
 /* Page-locks (cudaHostRegister) / releases caller-owned host buffers -- start solutions, parameters, the arrays of
  * hc_results -- so that the copies of hc_track_batch run as DMA transfers.  Optional; the Julia host would pin
