@@ -51,26 +51,50 @@ int fail(const std::string& msg) { g_err = msg; return -1; }
         cudaError_t e_ = (call);                                                                    \
         if (e_ != cudaSuccess) throw std::string(#call) + ": " + cudaGetErrorString(e_);            \
     } while (0)
-// Device memory comes from the stream-ordered pool of the device (cudaMallocAsync on the legacy default stream, the
-// stream every copy and kernel of this library runs on).  hc_init sets the pool's release threshold to "never", so the
-// ~30 buffers of a batch are recycled by the next call instead of being unmapped and mapped again (cudaFree of a
-// 100 MB buffer synchronises the device and costs milliseconds).  HC_B200_POOL=0 falls back to cudaMalloc / cudaFree.
+// The devices this process drives (hc_init: one; hc_init_devices: a list).  Every device has its own non-blocking
+// stream; handles keep one copy of their programs per device, a batch call splits its path index range over the
+// devices (reference: one solve() drives all workers and stores results by path index, src/solve.jl:628-709).
+// Device memory comes from the stream-ordered pool of the device (cudaMallocAsync on the device's stream) with the
+// release threshold set to "never", so the ~30 buffers of a batch are recycled by the next call instead of being
+// unmapped and mapped again (cudaFree of a 100 MB buffer synchronises the device and costs milliseconds).
+// HC_B200_POOL=0 falls back to cudaMalloc / cudaFree.
+struct Slot { int device = 0; cudaStream_t stream = nullptr; };
+std::vector<Slot> g_slots;
+int g_cur = 0;  // slot that dev_alloc / h2d / d2h / launches address (set by use_slot, under g_mutex)
 bool g_pool = true;
+int* g_cancel = nullptr;  // host-mapped flag polled by the kernels before they pull new paths (hc_request_cancel)
 // HC_B200_NO_DEVICE=1: handles are built in host memory so that hc_jit_prepare can generate and compile the specialised
 // kernel of a system on a machine without a GPU (NVRTC targets sm_100a offline; the driver's build check and the
 // "not gpu" tests use this).  Every compute entry point fails in this mode.
 bool nodev() { static const bool v = getenv("HC_B200_NO_DEVICE") && atoi(getenv("HC_B200_NO_DEVICE")) != 0; return v; }
+int n_slots() { return g_slots.empty() ? 1 : (int)g_slots.size(); }
+cudaStream_t cur_stream() { return g_slots.empty() ? (cudaStream_t)0 : g_slots[(size_t)g_cur].stream; }
+// the CUDA current device is per host thread: every entry point selects its device again (a Julia task may run on
+// any thread), under g_mutex
+void use_slot(int s) {
+    g_cur = s;
+    if (nodev() || g_slots.empty()) return;
+    CK(cudaSetDevice(g_slots[(size_t)s].device));
+}
+void dev_sync() { if (!nodev()) CK(cudaStreamSynchronize(cur_stream())); }
 void* dev_alloc(size_t bytes) {
     void* p = nullptr;
     if (nodev()) return calloc(bytes ? bytes : 16, 1);
-    if (g_pool) CK(cudaMallocAsync(&p, bytes ? bytes : 16, 0)); else CK(cudaMalloc(&p, bytes ? bytes : 16));
+    if (g_pool) CK(cudaMallocAsync(&p, bytes ? bytes : 16, cur_stream())); else CK(cudaMalloc(&p, bytes ? bytes : 16));
     return p;
 }
-void dev_free(void* p) { if (p) { if (nodev()) free(p); else if (g_pool) cudaFreeAsync(p, 0); else cudaFree(p); } }
-void h2d(void* d, const void* h, size_t bytes) { if (bytes) { if (nodev()) memcpy(d, h, bytes); else CK(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice)); } }
-void d2h(void* h, const void* d, size_t bytes) { if (bytes) { if (nodev()) memcpy(h, d, bytes); else CK(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost)); } }
-void dev_zero(void* d, size_t bytes) { if (bytes) { if (nodev()) memset(d, 0, bytes); else CK(cudaMemset(d, 0, bytes)); } }
+void dev_free(void* p) { if (p) { if (nodev()) free(p); else if (g_pool) cudaFreeAsync(p, cur_stream()); else cudaFree(p); } }
+// copies are stream-ordered: from pageable host memory the call returns once the source is staged, from page-locked
+// memory (hc_host_register) it is a DMA transfer that the next dev_sync waits for -- caller-owned arrays outlive the call
+void h2d(void* d, const void* h, size_t bytes) { if (bytes) { if (nodev()) memcpy(d, h, bytes); else CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, cur_stream())); } }
+void d2h(void* h, const void* d, size_t bytes) { if (bytes) { if (nodev()) memcpy(h, d, bytes); else CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, cur_stream())); } }
+void dev_zero(void* d, size_t bytes) { if (bytes) { if (nodev()) memset(d, 0, bytes); else CK(cudaMemsetAsync(d, 0, bytes, cur_stream())); } }
 #else
+int g_cur = 0;
+int* g_cancel = nullptr;
+int n_slots() { return 1; }
+void use_slot(int s) { g_cur = s; }
+void dev_sync() {}
 void* dev_alloc(size_t bytes) { return calloc(bytes ? bytes : 16, 1); }
 void dev_free(void* p) { free(p); }
 void h2d(void* d, const void* h, size_t bytes) { if (bytes) memcpy(d, h, bytes); }
@@ -86,24 +110,30 @@ T* to_dev(const std::vector<T>& v) {
 }
 
 // ------------------------------------------------------------------ handles
+// device allocations of a handle: (slot, pointer)
+struct Owned {
+    std::vector<std::pair<int, void*>> v;
+    void add(void* p) { v.push_back({g_cur, p}); }
+    ~Owned() { const int keep = g_cur; for (auto& e : v) { try { use_slot(e.first); } catch (...) {} dev_free(e.second); } g_cur = keep; }
+};
 struct ProgramH {
-    DevProgram dev;  // pointers into device memory
+    DevProgram dev;                // the copy on slot 0 (its sizes are the same on every device)
+    std::vector<DevProgram> devs;  // pointers into the memory of each device of the process
     LoweredProgram low;
     jit::ProgCopy ref;  // the reference tape as handed over (input of the code generator, hc_jitgen.h)
-    std::vector<void*> owned;
-    ~ProgramH() { for (void* p : owned) dev_free(p); }
+    Owned owned;
 };
 struct SystemH {
     ProgramH eval, jac;
     int m = 0, n = 0, P = 0;
 };
 struct HomotopyH {
-    DevHomotopy dev;
+    DevHomotopy dev;                // slot 0
+    std::vector<DevHomotopy> devs;  // per device
     SystemH* F = nullptr; SystemH* G = nullptr;
-    std::vector<void*> owned;
+    Owned owned;
     std::vector<double> tw_hook;  // weights set through hc_toric_set_weights (test hook)
     std::shared_ptr<jit::Module> jit_mod[4];  // specialised kernels: [polyhedral driver ? 1 : 0] + 2 * [per-path parameter rows]
-    ~HomotopyH() { for (void* p : owned) dev_free(p); }
 };
 
 int env_int(const char* name, int def) { const char* v = getenv(name); return v ? atoi(v) : def; }
@@ -146,25 +176,34 @@ void build_program(ProgramH& H, const hc_program_desc* d, bool is_jac) {
         }
     }
     const LoweredProgram& L = H.low;
-    DevProgram& P = H.dev;
-    P.ops = to_dev(L.ops); P.level_end = to_dev(L.level_end); P.consts = to_dev(L.consts);
-    P.u_assign = to_dev(L.u_assign); P.U_assign = to_dev(L.U_assign);
-    P.fops = to_dev(L.fops); P.segs = to_dev(L.segs); P.n_segs = (int)L.segs.size(); P.n_fops = (int)L.fops.size();
-    H.owned = {(void*)P.ops, (void*)P.level_end, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign, (void*)P.fops, (void*)P.segs};
-    P.n_levels = (int)L.level_end.size(); P.n_ops = (int)L.ops.size();
-    P.C = (int)L.consts.size(); P.param_off = L.param_off; P.P = L.P; P.t_slot = L.t_slot;
-    P.var_off = L.var_off; P.n = L.n; P.out_dim = L.out_dim; P.W = L.W;
-    P.nu = (int)L.u_assign.size(); P.nU = (int)L.U_assign.size();
+    H.devs.assign((size_t)n_slots(), DevProgram());
+    for (int sl = 0; sl < n_slots(); ++sl) {
+        use_slot(sl);
+        DevProgram& P = H.devs[(size_t)sl];
+        P.ops = to_dev(L.ops); P.level_end = to_dev(L.level_end); P.consts = to_dev(L.consts);
+        P.u_assign = to_dev(L.u_assign); P.U_assign = to_dev(L.U_assign);
+        P.fops = to_dev(L.fops); P.segs = to_dev(L.segs); P.n_segs = (int)L.segs.size(); P.n_fops = (int)L.fops.size();
+        for (void* q : {(void*)P.ops, (void*)P.level_end, (void*)P.consts, (void*)P.u_assign, (void*)P.U_assign, (void*)P.fops, (void*)P.segs}) H.owned.add(q);
+        P.n_levels = (int)L.level_end.size(); P.n_ops = (int)L.ops.size();
+        P.C = (int)L.consts.size(); P.param_off = L.param_off; P.P = L.P; P.t_slot = L.t_slot;
+        P.var_off = L.var_off; P.n = L.n; P.out_dim = L.out_dim; P.W = L.W;
+        P.nu = (int)L.u_assign.size(); P.nU = (int)L.U_assign.size();
+        dev_sync();  // the staging vectors of to_dev are temporaries
+    }
+    use_slot(0);
+    H.dev = H.devs[0];
+    const DevProgram& P = H.dev;
     if (getenv("HC_B200_VERBOSE"))
         fprintf(stderr, "[hc_b200] program: %d reference instructions -> %d micro-ops in %d levels (max width %d), %d segments, tape %d -> %d slots\n",
                 d->n_instructions, P.n_ops, P.n_levels, L.max_width, P.n_segs, d->tape_space, P.W);
 }
 
-cx* cvec_dev(const double* p, int n, std::vector<void*>& owned) {
+cx* cvec_dev(const double* p, int n, Owned& owned) {
     std::vector<cx> v(n);
     for (int i = 0; i < n; ++i) v[i] = mk(p[2 * i], p[2 * i + 1]);
     cx* d = to_dev(v);
-    owned.push_back(d);
+    owned.add(d);
+    dev_sync();
     return d;
 }
 
@@ -412,9 +451,23 @@ struct DeviceBatch {  // device-resident inputs and outputs of one batch
     int mode = 0; long long N = 0; int n = 0;
     KArgs A;
     Plan plan;
+    int slot = 0;          // device of the batch
+    long long first = 0;   // index of its first path in the caller's arrays
     std::vector<void*> owned;
     int64_t h2d_bytes = 0;
-    ~DeviceBatch() { for (void* p : owned) dev_free(p); }
+#ifndef HC_HOST_SIM
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+#endif
+    ~DeviceBatch() {
+        const int keep = g_cur;
+        try { use_slot(slot); } catch (...) {}
+        for (void* p : owned) dev_free(p);
+#ifndef HC_HOST_SIM
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+#endif
+        g_cur = keep;
+    }
     template <class T> T* alloc(size_t count) { T* p = (T*)dev_alloc(count * sizeof(T)); owned.push_back(p); return p; }
     template <class T> T* upload(const T* h, size_t count) {
         T* p = alloc<T>(count); h2d(p, h, count * sizeof(T)); h2d_bytes += (int64_t)(count * sizeof(T)); return p;
@@ -431,11 +484,12 @@ struct StartGen {
 
 void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1,
                  const double* t0, const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
-                 const double* cell_weights, int ncells, const StartGen& sg = StartGen()) {
-    D.H = H; D.mode = mode; D.N = N; D.n = H->dev.n;
+                 const double* cell_weights, int ncells, const StartGen& sg = StartGen(), int slot = 0) {
+    D.H = H; D.mode = mode; D.N = N; D.n = H->dev.n; D.slot = slot;
+    use_slot(slot);
     const int n = D.n, P = H->dev.P;
     memset(&D.A, 0, sizeof(D.A));
-    D.A.H = H->dev;
+    D.A.H = H->devs[(size_t)slot];
     D.A.H.N = N;
     D.A.O = to_dev_options(o);
     BatchIn& B = D.A.B;
@@ -467,6 +521,9 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     D.A.H.path_p = path_p ? (const cx*)D.upload<double>(path_p, (size_t)2 * P * prow) : nullptr;
     D.A.H.path_q = path_q ? (const cx*)D.upload<double>(path_q, (size_t)2 * P * prow) : nullptr;
     if (mode == MODE_POLYHEDRAL) {
+        if (!cell_index || !cell_weights || ncells <= 0) throw std::string("polyhedral batch: cell_index / cell_weights missing");
+        for (long long k = 0; k < N; ++k)
+            if (cell_index[k] < 0 || cell_index[k] >= ncells) throw std::string("polyhedral batch: cell_index[") + std::to_string(k) + "] is outside [0, ncells)";
         B.cell_index = D.upload<int32_t>(cell_index, (size_t)N);
         B.cell_weights = D.upload<double>(cell_weights, (size_t)ncells * P);
     }
@@ -479,6 +536,8 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     R.mu = D.alloc<double>(N); R.accepted_steps = D.alloc<int>(N); R.rejected_steps = D.alloc<int>(N);
     R.steps_eg = D.alloc<int>(N); R.extended_precision_used = D.alloc<unsigned char>(N);
     R.counters = D.alloc<long long>((size_t)8 * N);
+    dev_zero(R.return_code, (size_t)N * sizeof(int));  // a cancelled batch leaves the paths it never started at 0 (= tracking)
+    D.A.cancel = g_cancel;
     D.plan = make_plan(*H, N, mode, B.t1.im != 0.0 || B.t0.im != 0.0, path_p != nullptr || path_q != nullptr);
     const Plan& pl = D.plan;
     D.A.queue = D.alloc<unsigned long long>(1);
@@ -493,16 +552,20 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
 }
 
 #ifndef HC_HOST_SIM
+// function attributes and the stack limit are per device: remember what was set where
+bool first_use(const void* kern) {
+    static std::vector<std::pair<const void*, int>> seen;
+    for (auto& e : seen) if (e.first == kern && e.second == g_cur) return false;
+    seen.push_back({kern, g_cur});
+    return true;
+}
 void launch_tpl(const DeviceBatch& D, int SLAB) {
     const void* kern = hc_kernel_tpl(SLAB);
-    static bool attr_set[3] = {false, false, false};
-    bool& done = attr_set[SLAB == 12288 ? 0 : (SLAB == 24576 ? 1 : 2)];
-    if (!done) {
+    if (first_use(kern)) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         size_t cur = 0;
         CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
         if (cur < (size_t)SLAB + 8192) CK(cudaDeviceSetLimit(cudaLimitStackSize, (size_t)SLAB + 8192));
-        done = true;
     }
     // the lane state lives in L1 (local memory): ask for the smallest shared-memory carve-out that holds
     // the staged programs of the CTAs resident on one SM
@@ -516,15 +579,13 @@ void launch_tpl(const DeviceBatch& D, int SLAB) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     void* args[] = {(void*)&D.A};
-    CK(cudaLaunchKernel(kern, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, 0));
+    CK(cudaLaunchKernel(kern, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, cur_stream()));
 }
 void launch_track(const DeviceBatch& D, int G) {
     const void* kern = hc_kernel_group(G);
-    static bool attr_set[2] = {false, false};
-    bool& done = attr_set[G == 8 ? 0 : 1];
-    if (!done) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); done = true; }
+    if (first_use(kern)) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     void* args[] = {(void*)&D.A};
-    CK(cudaLaunchKernel(kern, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, 0));
+    CK(cudaLaunchKernel(kern, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, cur_stream()));
 }
 #endif
 
@@ -534,40 +595,43 @@ void launch_jit(const DeviceBatch& D) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (!M.attr_set) {
+    if (first_use((const void*)M.track)) {
         CK(cudaFuncSetAttribute((const void*)M.track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
         size_t cur = 0;
         CK(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
         if (cur < M.slab + 8192) CK(cudaDeviceSetLimit(cudaLimitStackSize, M.slab + 8192));
-        M.attr_set = true;
     }
     const int per_sm = (D.plan.grid + sms - 1) / sms;
     int pct = env_int("HC_B200_CARVEOUT", (int)((per_sm * (D.plan.smem + 3072) * 100 + 228 * 1024 - 1) / (228 * 1024)));
     if (pct > 100) pct = 100;
     CK(cudaFuncSetAttribute((const void*)M.track, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     void* args[] = {(void*)&D.A};
-    CK(cudaLaunchKernel((const void*)M.track, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, 0));
+    CK(cudaLaunchKernel((const void*)M.track, dim3((unsigned)D.plan.grid), dim3((unsigned)D.plan.block), args, D.plan.smem, cur_stream()));
 }
 #endif
 
-// runs the batch once; returns kernel milliseconds
-double run_batch(DeviceBatch& D) {
+// launches the batch on its device's stream (asynchronous); finish_batch waits for it and returns kernel milliseconds
+void launch_batch(DeviceBatch& D) {
+    use_slot(D.slot);
     dev_zero(D.A.queue, sizeof(unsigned long long));
 #ifndef HC_HOST_SIM
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, 0));
+    if (!D.e0) { CK(cudaEventCreate(&D.e0)); CK(cudaEventCreate(&D.e1)); }
+    CK(cudaEventRecord(D.e0, cur_stream()));
     if (D.plan.engine == 2) launch_jit(D);
     else if (D.plan.engine == 1) {
         const size_t need = D.plan.slab + D.plan.cold;
         launch_tpl(D, need <= 12 * 1024 ? 12 * 1024 : (need <= 24 * 1024 ? 24 * 1024 : 48 * 1024));
     } else launch_track(D, D.plan.group == 32 ? 32 : 8);
-    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventRecord(D.e1, cur_stream()));
     CK(cudaGetLastError());
-    CK(cudaEventSynchronize(e1));
+#endif
+}
+double finish_batch(DeviceBatch& D) {
+    use_slot(D.slot);
+#ifndef HC_HOST_SIM
+    CK(cudaEventSynchronize(D.e1));
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaEventElapsedTime(&ms, D.e0, D.e1));
     return ms;
 #else
     if (D.plan.engine == 2) {
@@ -585,19 +649,23 @@ double run_batch(DeviceBatch& D) {
     return 0.0;
 #endif
 }
+double run_batch(DeviceBatch& D) { launch_batch(D); return finish_batch(D); }
 
+// copies the PathResult arrays of the batch into the caller's arrays at the batch's path offset (stream-ordered:
+// dev_sync() before the host reads them)
 void fetch_results(DeviceBatch& D, hc_results* out) {
+    use_slot(D.slot);
     const DevResults& R = D.A.R;
-    const size_t N = (size_t)D.N, n = (size_t)D.n;
-    d2h(out->return_code, R.return_code, N * 4); d2h(out->solution, R.solution, n * N * 16); d2h(out->t, R.t, N * 8);
-    d2h(out->accuracy, R.accuracy, N * 8); d2h(out->residual, R.residual, N * 8); d2h(out->singular, R.singular, N);
-    d2h(out->condition_jacobian, R.condition_jacobian, N * 8); d2h(out->winding_number, R.winding_number, N * 4);
-    d2h(out->extended_precision, R.extended_precision, N); d2h(out->last_point, R.last_point, n * N * 16);
-    d2h(out->last_t, R.last_t, N * 8); d2h(out->valuation, R.valuation, n * N * 8); d2h(out->has_valuation, R.has_valuation, N);
-    d2h(out->omega, R.omega, N * 8); d2h(out->mu, R.mu, N * 8); d2h(out->accepted_steps, R.accepted_steps, N * 4);
-    d2h(out->rejected_steps, R.rejected_steps, N * 4); d2h(out->steps_eg, R.steps_eg, N * 4);
-    d2h(out->extended_precision_used, R.extended_precision_used, N);
-    if (out->counters) d2h(out->counters, R.counters, N * 64);
+    const size_t N = (size_t)D.N, n = (size_t)D.n, f = (size_t)D.first;
+    d2h(out->return_code + f, R.return_code, N * 4); d2h(out->solution + 2 * n * f, R.solution, n * N * 16); d2h(out->t + f, R.t, N * 8);
+    d2h(out->accuracy + f, R.accuracy, N * 8); d2h(out->residual + f, R.residual, N * 8); d2h(out->singular + f, R.singular, N);
+    d2h(out->condition_jacobian + f, R.condition_jacobian, N * 8); d2h(out->winding_number + f, R.winding_number, N * 4);
+    d2h(out->extended_precision + f, R.extended_precision, N); d2h(out->last_point + 2 * n * f, R.last_point, n * N * 16);
+    d2h(out->last_t + f, R.last_t, N * 8); d2h(out->valuation + n * f, R.valuation, n * N * 8); d2h(out->has_valuation + f, R.has_valuation, N);
+    d2h(out->omega + f, R.omega, N * 8); d2h(out->mu + f, R.mu, N * 8); d2h(out->accepted_steps + f, R.accepted_steps, N * 4);
+    d2h(out->rejected_steps + f, R.rejected_steps, N * 4); d2h(out->steps_eg + f, R.steps_eg, N * 4);
+    d2h(out->extended_precision_used + f, R.extended_precision_used, N);
+    if (out->counters) d2h(out->counters + 8 * f, R.counters, N * 64);
 }
 int64_t result_bytes(long long N, int n, bool counters) {
     return (int64_t)N * (4 + 16 * n + 8 + 8 + 8 + 1 + 8 + 4 + 1 + 16 * n + 8 + 8 * n + 1 + 8 + 8 + 4 + 4 + 4 + 1 + (counters ? 64 : 0));
@@ -616,37 +684,75 @@ HomotopyH* merged_polyhedral(HomotopyH* toric, HomotopyH* coeff) {
     return coeff;  // coeff.p are the start coefficients == toric system coefficients (src/polyhedral.jl:397-406)
 }
 
+void ensure_init();
+
 int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1, const double* t0,
                const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
                const double* cell_weights, int ncells, hc_results* out, const StartGen& sg = StartGen()) {
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         if (N <= 0) return 0;
+        if (!H || !o || !out) throw std::string("null handle / options / results");
 #ifndef HC_HOST_SIM
         if (nodev()) throw std::string("HC_B200_NO_DEVICE is set: this process can only build kernels, not track (there is no CPU fallback)");
 #endif
-        double tA = now_ms(), tB, tC, tD, kms;
-        {
-            DeviceBatch D;
-            setup_batch(D, H, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, cell_index, cell_weights, ncells, sg);
-#ifndef HC_HOST_SIM
-            CK(cudaDeviceSynchronize());
-#endif
-            tB = now_ms();
-            kms = run_batch(D);
-            tC = now_ms();
-            fetch_results(D, out);
-            tD = now_ms();
-            g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
-            g_timing.h2d_bytes = D.h2d_bytes; g_timing.d2h_bytes = result_bytes(N, D.n, out->counters != nullptr);
-            g_timing.grid = D.plan.grid; g_timing.block = D.plan.block; g_timing.lanes = D.plan.group;
-            g_timing.slab_bytes = D.plan.engine == 1 ? (int64_t)D.plan.lanes * (int64_t)(D.plan.slab + D.plan.cold) : (int64_t)D.plan.slab;
+        ensure_init();
+        if ((int)H->devs.size() != n_slots()) throw std::string("handle was created before hc_init_devices changed the device list");
+        if (g_cancel) *g_cancel = 0;
+        const double tA = now_ms();
+        // Shards: contiguous path index ranges, one per device (sweeps: whole parameter points).  Small batches stay on
+        // one device -- a device wants thousands of paths per launch.
+        const int n = H->dev.n, P = H->dev.P;
+        const long long unit = sg.start_rows > 0 ? sg.start_rows : 1;
+        int nd = n_slots();
+        const long long min_per_dev = env_int("HC_B200_MIN_PATHS_PER_DEVICE", 2048);
+        while (nd > 1 && N / nd < min_per_dev) --nd;
+        std::vector<std::unique_ptr<DeviceBatch>> Ds;
+        long long lo = 0;
+        for (int sl = 0; sl < nd; ++sl) {
+            long long hi = sl == nd - 1 ? N : ((N / unit) * (sl + 1) / nd) * unit;
+            if (hi <= lo) continue;
+            const long long prow0 = sg.param_div > 0 ? lo / sg.param_div : lo;
+            StartGen g2 = sg;
+            g2.td_first = sg.td_first + lo;
+            Ds.emplace_back(new DeviceBatch());
+            DeviceBatch& D = *Ds.back();
+            D.first = lo;
+            setup_batch(D, H, o, mode, hi - lo, (starts && sg.start_rows == 0) ? starts + (size_t)2 * n * lo : starts, t1, t0,
+                        path_p ? path_p + (size_t)2 * P * prow0 : nullptr, path_q ? path_q + (size_t)2 * P * prow0 : nullptr,
+                        omega_mu ? omega_mu + 2 * lo : nullptr, cell_index ? cell_index + lo : nullptr, cell_weights, ncells, g2, sl);
+            launch_batch(D);  // asynchronous: the next device is set up while this one tracks
+            lo = hi;
         }
+        const double tB = now_ms();
+        double kms = 0;
+        int64_t h2d_bytes = 0;
+        for (auto& D : Ds) { kms = std::max(kms, finish_batch(*D)); h2d_bytes += D->h2d_bytes; }
+        const double tC = now_ms();
+        for (auto& D : Ds) fetch_results(*D, out);
+        for (auto& D : Ds) { use_slot(D->slot); dev_sync(); }
+        const double tD = now_ms();
+        const DeviceBatch& D0 = *Ds[0];
+        g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
+        g_timing.h2d_bytes = h2d_bytes; g_timing.d2h_bytes = result_bytes(N, n, out->counters != nullptr);
+        g_timing.grid = D0.plan.grid; g_timing.block = D0.plan.block; g_timing.lanes = D0.plan.group;
+        g_timing.slab_bytes = D0.plan.engine != 0 ? (int64_t)D0.plan.lanes * (int64_t)(D0.plan.slab + D0.plan.cold) : (int64_t)D0.plan.slab;
+        g_timing.devices = (int32_t)Ds.size(); g_timing.engine = D0.plan.engine;
+        Ds.clear();
+        use_slot(0);
         if (env_int("HC_B200_VERBOSE", 0) >= 2)
-            fprintf(stderr, "[hc_b200] batch of %lld paths: setup+h2d %.2f ms, launch..done %.2f ms (kernel %.2f ms by events), d2h %.2f ms, release %.2f ms\n",
-                    N, tB - tA, tC - tB, kms, tD - tC, now_ms() - tD);
+            fprintf(stderr, "[hc_b200] batch of %lld paths on %d device(s): setup+h2d+launch %.2f ms, wait %.2f ms (kernel %.2f ms by events), d2h %.2f ms\n",
+                    N, (int)g_timing.devices, tB - tA, tC - tB, kms, tD - tC);
     } catch (const std::string& e) { return fail(e); }
+    catch (const std::exception& e) { return fail(std::string("internal error: ") + e.what()); }
+    catch (...) { return fail("internal error"); }
     return 0;
+}
+
+void ensure_init() {
+#ifndef HC_HOST_SIM
+    if (g_slots.empty() && !nodev()) throw std::string("hc_init / hc_init_devices has not been called");
+#endif
 }
 
 }  // namespace
@@ -656,27 +762,52 @@ extern "C" {
 
 const char* hc_last_error(void) { return g_err.c_str(); }
 
-int32_t hc_init(int32_t device) {
+int32_t hc_init_devices(const int32_t* devices, int32_t n_devices) {
+    std::lock_guard<std::mutex> lock(g_mutex);
 #ifndef HC_HOST_SIM
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) return fail("no CUDA device available (libhc_b200 has no CPU fallback)");
-    if (device < 0 || device >= count) return fail("invalid device index");
-    e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-    cudaDeviceSetLimit(cudaLimitStackSize, (size_t)env_int("HC_B200_STACK", 8192));
-    g_pool = env_int("HC_B200_POOL", 1) != 0;
-    if (g_pool) {
-        cudaMemPool_t mp;
-        unsigned long long keep = ~0ull;
-        if (cudaDeviceGetDefaultMemPool(&mp, device) != cudaSuccess ||
-            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) { cudaGetLastError(); g_pool = false; }
-    }
+    try {
+        if (nodev()) return 0;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) return fail("no CUDA device available (libhc_b200 has no CPU fallback)");
+        if (!devices || n_devices < 1) return fail("device list missing");
+        for (int i = 0; i < n_devices; ++i) {
+            if (devices[i] < 0 || devices[i] >= count) return fail("invalid device index");
+            for (int j = 0; j < i; ++j) if (devices[j] == devices[i]) return fail("device listed twice");
+        }
+        for (Slot& sl : g_slots) { cudaSetDevice(sl.device); if (sl.stream) cudaStreamDestroy(sl.stream); }
+        g_slots.clear();
+        g_pool = env_int("HC_B200_POOL", 1) != 0;
+        for (int i = 0; i < n_devices; ++i) {
+            Slot sl; sl.device = devices[i];
+            CK(cudaSetDevice(sl.device));
+            CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            cudaDeviceSetLimit(cudaLimitStackSize, (size_t)env_int("HC_B200_STACK", 8192));
+            if (g_pool) {
+                cudaMemPool_t mp;
+                unsigned long long keep = ~0ull;
+                if (cudaDeviceGetDefaultMemPool(&mp, sl.device) != cudaSuccess ||
+                    cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) { cudaGetLastError(); g_pool = false; }
+            }
+            g_slots.push_back(sl);
+        }
+        if (!g_cancel) {
+            CK(cudaHostAlloc((void**)&g_cancel, sizeof(int), cudaHostAllocPortable | cudaHostAllocMapped));
+            *g_cancel = 0;
+        }
+        use_slot(0);
+    } catch (const std::string& e) { return fail(e); }
 #else
-    (void)device;
+    (void)devices; (void)n_devices;
 #endif
     return 0;
 }
+
+int32_t hc_init(int32_t device) { return hc_init_devices(&device, 1); }
+
+int32_t hc_device_count(void) { return (int32_t)n_slots(); }
+
+void hc_request_cancel(int32_t on) { if (g_cancel) *(volatile int*)g_cancel = on ? 1 : 0; }
 
 void hc_options_default(hc_options* o) {
     // TrackerOptions / TrackerParameters (src/tracker.jl:45-62, 105-115)
@@ -695,8 +826,11 @@ void hc_options_default(hc_options* o) {
 }
 
 void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac) {
+    std::lock_guard<std::mutex> lock(g_mutex);
     SystemH* S = nullptr;
     try {
+        if (!eval || !jac) throw std::string("program descriptors missing");
+        ensure_init();
         if (eval->n_vars != jac->n_vars || eval->out_dim != jac->out_dim || eval->n_params != jac->n_params)
             throw std::string("eval and Jacobian tapes disagree on dimensions");
         if (eval->out_dim != eval->n_vars) throw std::string("only square systems are supported");
@@ -705,46 +839,62 @@ void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac) 
         build_program(S->jac, jac, true);
         S->m = eval->out_dim; S->n = eval->n_vars; S->P = eval->n_params;
     } catch (const std::string& e) { delete S; fail(e); return nullptr; }
+    catch (...) { delete S; fail("internal error"); return nullptr; }
     return S;
 }
-void hc_system_destroy(void* s) { delete (SystemH*)s; }
+void hc_system_destroy(void* s) { std::lock_guard<std::mutex> lock(g_mutex); delete (SystemH*)s; }
 
 void* hc_homotopy_create(const hc_homotopy_desc* d) {
+    std::lock_guard<std::mutex> lock(g_mutex);
     HomotopyH* H = nullptr;
     try {
-        if (!d->F) throw std::string("homotopy needs a system F");
+        if (!d || !d->F) throw std::string("homotopy needs a system F");
+        if (d->kind < HC_STRAIGHT_LINE || d->kind > HC_TORIC) throw std::string("unknown homotopy kind");
         H = new HomotopyH();
         H->F = (SystemH*)d->F; H->G = (SystemH*)d->G;
-        DevHomotopy& D = H->dev;
-        memset(&D, 0, sizeof(D));
-        D.kind = d->kind; D.n = H->F->n; D.P = H->F->P;
-        D.Fe = H->F->eval.dev; D.Fj = H->F->jac.dev;
-        D.gamma = mk(d->gamma[0], d->gamma[1]);
+        if ((int)H->F->eval.devs.size() != n_slots()) throw std::string("system was created before hc_init_devices changed the device list");
         int W = H->F->jac.dev.W, We = H->F->eval.dev.W;
         if (d->kind == HC_STRAIGHT_LINE) {
             if (!H->G) throw std::string("straight-line homotopy needs a start system G");
             if (H->G->n != H->F->n) throw std::string("G and F have different sizes");
             if (d->n_G_params != H->G->P || d->n_F_params != H->F->P) throw std::string("wrong number of fixed parameters");
-            D.Ge = H->G->eval.dev; D.Gj = H->G->jac.dev;
-            static const double dummy[2] = {0, 0};
-            D.G_params = cvec_dev(d->n_G_params ? d->G_params : dummy, d->n_G_params ? d->n_G_params : 1, H->owned);
-            D.F_params = cvec_dev(d->n_F_params ? d->F_params : dummy, d->n_F_params ? d->n_F_params : 1, H->owned);
+            if ((d->n_G_params > 0 && !d->G_params) || (d->n_F_params > 0 && !d->F_params)) throw std::string("fixed parameters missing");
             if (H->G->jac.dev.W > W) W = H->G->jac.dev.W;
             if (H->G->eval.dev.W > We) We = H->G->eval.dev.W;
         } else {
             if (d->n_pq != H->F->P) throw std::string("wrong number of parameters");
-            static const double dummy[2] = {0, 0};
-            D.p = cvec_dev(d->n_pq ? d->p : dummy, d->n_pq ? d->n_pq : 1, H->owned);
-            if (d->kind != HC_TORIC) D.q = cvec_dev(d->n_pq ? d->q : dummy, d->n_pq ? d->n_pq : 1, H->owned);
+            if (d->n_pq > 0 && !d->p) throw std::string("start parameters p missing");
+            if (d->n_pq > 0 && d->kind != HC_TORIC && !d->q) throw std::string("target parameters q missing");
         }
-        // tape region (cx units): Jacobian tape, DD eval tape (2x), order-3 Taylor eval tape (4x)
-        int need = W;
-        if (4 * We > need) need = 4 * We;
-        D.tape_cx = need;
+        static const double dummy[2] = {0, 0};
+        H->devs.assign((size_t)n_slots(), DevHomotopy());
+        for (int sl = 0; sl < n_slots(); ++sl) {
+            use_slot(sl);
+            DevHomotopy& D = H->devs[(size_t)sl];
+            memset(&D, 0, sizeof(D));
+            D.kind = d->kind; D.n = H->F->n; D.P = H->F->P;
+            D.Fe = H->F->eval.devs[(size_t)sl]; D.Fj = H->F->jac.devs[(size_t)sl];
+            D.gamma = mk(d->gamma[0], d->gamma[1]);
+            if (d->kind == HC_STRAIGHT_LINE) {
+                D.Ge = H->G->eval.devs[(size_t)sl]; D.Gj = H->G->jac.devs[(size_t)sl];
+                D.G_params = cvec_dev(d->n_G_params ? d->G_params : dummy, d->n_G_params ? d->n_G_params : 1, H->owned);
+                D.F_params = cvec_dev(d->n_F_params ? d->F_params : dummy, d->n_F_params ? d->n_F_params : 1, H->owned);
+            } else {
+                D.p = cvec_dev(d->n_pq ? d->p : dummy, d->n_pq ? d->n_pq : 1, H->owned);
+                if (d->kind != HC_TORIC) D.q = cvec_dev(d->n_pq ? d->q : dummy, d->n_pq ? d->n_pq : 1, H->owned);
+            }
+            // tape region (cx units): Jacobian tape, DD eval tape (2x), order-3 Taylor eval tape (4x)
+            int need = W;
+            if (4 * We > need) need = 4 * We;
+            D.tape_cx = need;
+        }
+        use_slot(0);
+        H->dev = H->devs[0];
     } catch (const std::string& e) { delete H; fail(e); return nullptr; }
+    catch (...) { delete H; fail("internal error"); return nullptr; }
     return H;
 }
-void hc_homotopy_destroy(void* h) { delete (HomotopyH*)h; }
+void hc_homotopy_destroy(void* h) { std::lock_guard<std::mutex> lock(g_mutex); delete (HomotopyH*)h; }
 
 int32_t hc_homotopy_set_parameters(void* Hv, const double* p, const double* q) {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -754,8 +904,13 @@ int32_t hc_homotopy_set_parameters(void* Hv, const double* p, const double* q) {
         if (H->dev.kind == H_STRAIGHT_LINE) throw std::string("a straight-line homotopy has no start / target parameters");
         if (q && H->dev.kind == H_TORIC) throw std::string("a toric homotopy has no target parameters");
         const size_t bytes = (size_t)H->dev.P * 16;
-        if (p) h2d((void*)H->dev.p, p, bytes);
-        if (q) h2d((void*)H->dev.q, q, bytes);
+        for (int sl = 0; sl < (int)H->devs.size(); ++sl) {
+            use_slot(sl);
+            if (p) h2d((void*)H->devs[(size_t)sl].p, p, bytes);
+            if (q) h2d((void*)H->devs[(size_t)sl].q, q, bytes);
+            dev_sync();
+        }
+        use_slot(0);
     } catch (const std::string& e) { return fail(e); }
     return 0;
 }
@@ -765,6 +920,7 @@ int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, co
                        int32_t) {
     if (mode != MODE_ENDGAME && mode != MODE_TRACKER) return fail("mode must be 0 (endgame tracker) or 1 (tracker)");
     HomotopyH* h = (HomotopyH*)H;
+    if (!h) return fail("null homotopy handle");
     if (h->dev.kind == H_TORIC) return fail("toric homotopies are tracked through hc_polyhedral_track_batch");
     return track_impl(h, o, mode, N, starts, t1, t0, path_p, path_q, omega_mu, nullptr, nullptr, 0, out);
 }
@@ -772,6 +928,7 @@ int32_t hc_track_batch(void* H, const hc_options* o, int32_t mode, int64_t N, co
 int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* o, int64_t N, const double* starts,
                                   const int32_t* cell_index, const double* cell_weights, int32_t ncells, hc_results* out, int32_t) {
     try {
+        if (!Htoric || !Hcoeff) throw std::string("null homotopy handle");
         HomotopyH* h = merged_polyhedral((HomotopyH*)Htoric, (HomotopyH*)Hcoeff);
         return track_impl(h, o, MODE_POLYHEDRAL, N, starts, nullptr, nullptr, nullptr, nullptr, nullptr, cell_index, cell_weights, ncells, out);
     } catch (const std::string& e) { return fail(e); }
@@ -802,30 +959,41 @@ void* hc_resident_create(void* H, void* Hcoeff, const hc_options* o, int32_t mod
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceBatch* D = nullptr;
     try {
+        if (!H || !o) throw std::string("null handle / options");
+        ensure_init();
         HomotopyH* h = (HomotopyH*)H;
         if (mode == MODE_POLYHEDRAL) h = merged_polyhedral((HomotopyH*)H, (HomotopyH*)Hcoeff);
+        if (g_cancel) *g_cancel = 0;
         D = new DeviceBatch();
         setup_batch(*D, h, o, mode, N, starts, t1, t0, path_p, path_q, nullptr, cell_index, cell_weights, ncells);
+        dev_sync();
     } catch (const std::string& e) { delete D; fail(e); return nullptr; }
+    catch (...) { delete D; fail("internal error"); return nullptr; }
     return D;
 }
 int32_t hc_resident_run(void* r, double* kernel_ms) {
     std::lock_guard<std::mutex> lock(g_mutex);
     try { double ms = run_batch(*(DeviceBatch*)r); if (kernel_ms) *kernel_ms = ms; }
     catch (const std::string& e) { return fail(e); }
+    catch (...) { return fail("internal error"); }
     return 0;
 }
 int32_t hc_resident_fetch(void* r, hc_results* out) {
-    try { fetch_results(*(DeviceBatch*)r, out); } catch (const std::string& e) { return fail(e); }
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try { fetch_results(*(DeviceBatch*)r, out); dev_sync(); } catch (const std::string& e) { return fail(e); }
+    catch (...) { return fail("internal error"); }
     return 0;
 }
-void hc_resident_destroy(void* r) { delete (DeviceBatch*)r; }
+void hc_resident_destroy(void* r) { std::lock_guard<std::mutex> lock(g_mutex); delete (DeviceBatch*)r; }
 
 // ------------------------------------------------------------------ operator API hooks
 static int hook(void* Hv, int what, int K, const double* x, const double* xlo, const double* t, double* u, double* U) {
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         HomotopyH* H = (HomotopyH*)Hv;
+        if (!H || !x || !t || !u) throw std::string("null argument");
+        ensure_init();
+        use_slot(0);
         const int n = H->dev.n, P = H->dev.P;
         hc_options o; hc_options_default(&o);
         KArgs A; memset(&A, 0, sizeof(A));
@@ -859,15 +1027,16 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
             if (M->hot > kSmemMax) throw std::string("system too large for one shared-memory slab");
             CK(cudaFuncSetAttribute((const void*)M->hook, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
             void* args[] = {(void*)&A, (void*)&what, (void*)&K, (void*)&dx, (void*)&tt, (void*)&dtw, (void*)&du, (void*)&dU};
-            CK(cudaLaunchKernel((const void*)M->hook, dim3(1), dim3(1), args, M->hot, 0));
+            CK(cudaLaunchKernel((const void*)M->hook, dim3(1), dim3(1), args, M->hot, cur_stream()));
             CK(cudaGetLastError());
-            CK(cudaDeviceSynchronize());
+            dev_sync();
 #else
             std::vector<unsigned char> hot(M->hot + 16);
             M->hook(&A, (unsigned char*)(((uintptr_t)hot.data() + 15) & ~(uintptr_t)15), jcold, what, K, dx, tt, dtw, du, dU);
 #endif
             d2h(u, du, (size_t)n * 16);
             if (U) d2h(U, dU, (size_t)n * n * 16);
+            dev_sync();
             for (void* p : owned) dev_free(p);
             return 0;
         }
@@ -875,9 +1044,9 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
         if (slab > kSmemMax) throw std::string("system too large for one shared-memory slab");
         static bool attr_set = false;
         if (!attr_set) { CK(cudaFuncSetAttribute(hc_hook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)); attr_set = true; }
-        hc_hook_kernel<<<1, 1, slab>>>(A, what, K, dx, dlo, tt, dtw, du, dU);
+        hc_hook_kernel<<<1, 1, slab, cur_stream()>>>(A, what, K, dx, dlo, tt, dtw, du, dU);
         CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
+        dev_sync();
 #else
         std::vector<unsigned char> mem(slab + 16);
         Lane<1, 0> L;
@@ -899,8 +1068,10 @@ static int hook(void* Hv, int what, int K, const double* x, const double* xlo, c
 #endif
         d2h(u, du, (size_t)n * 16);
         if (U) d2h(U, dU, (size_t)n * n * 16);
+        dev_sync();
         for (void* p : owned) dev_free(p);
     } catch (const std::string& e) { return fail(e); }
+    catch (...) { return fail("internal error"); }
     return 0;
 }
 int32_t hc_evaluate(void* H, const double* x, const double* t, double* u) { return hook(H, 0, 0, x, nullptr, t, u, nullptr); }

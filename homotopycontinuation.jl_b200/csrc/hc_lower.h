@@ -127,13 +127,16 @@ inline LoweredProgram lower_program(const hc_program_desc* d, int cap, bool prio
             case OP_MULADD: r = emit(MC_MA, 0, 0, x, rd(1), rd(2), -1); break;
             case OP_MULSUB: r = emit(MC_MA, 0, 1, x, rd(1), rd(2), -1); break;
             case OP_SUBMUL: r = emit(MC_MA, 1, 0, x, rd(1), rd(2), -1); break;
+            // the reference's association (operations.jl: a + b + c + d and a * b * c * d fold from the left), so that
+            // the interpreter rounds like the reference; the Taylor rules pair them ((a+b)+(c+d), taylor.jl) -- for a
+            // sum the coefficients are independent and the pairing is exact per coefficient either way
             case OP_ADD4: {
-                int t1 = emit(MC_AA, 0, 0, x, -1, rd(1), -1), t2 = emit(MC_AA, 0, 0, rd(2), -1, rd(3), -1);
-                r = emit(MC_AA, 0, 0, t1, -1, t2, -1);
+                int t1 = emit(MC_AA, 0, 0, x, -1, rd(1), -1), t2 = emit(MC_AA, 0, 0, t1, -1, rd(2), -1);
+                r = emit(MC_AA, 0, 0, t2, -1, rd(3), -1);
             } break;
             case OP_MUL4: {
-                int t1 = emit(MC_M, 0, 0, x, rd(1), -1, -1), t2 = emit(MC_M, 0, 0, rd(2), rd(3), -1, -1);
-                r = emit(MC_M, 0, 0, t1, t2, -1, -1);
+                int t1 = emit(MC_M, 0, 0, x, rd(1), -1, -1), t2 = emit(MC_M, 0, 0, t1, rd(2), -1, -1);
+                r = emit(MC_M, 0, 0, t2, rd(3), -1, -1);
             } break;
             case OP_MULMULADD: r = emit(MC_MM, 0, 0, x, rd(1), rd(2), rd(3)); break;
             default: r = emit(MC_MM, 0, 1, x, rd(1), rd(2), rd(3)); break;  // OP_MULMULSUB

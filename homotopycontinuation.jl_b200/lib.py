@@ -16,12 +16,20 @@ _api: CApi | None = None
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
-                ("grid", C.c_int32), ("block", C.c_int32), ("lanes", C.c_int32), ("slab_bytes", C.c_int64)]
+                ("grid", C.c_int32), ("block", C.c_int32), ("lanes", C.c_int32), ("slab_bytes", C.c_int64),
+                ("devices", C.c_int32), ("engine", C.c_int32)]
 
 
-def load(device: int | None = None) -> CApi:
-    """Returns the ctypes API bound to libhc_b200.so with the CUDA device selected."""
+def load(device: int | None = None, devices: list[int] | None = None) -> CApi:
+    """Returns the ctypes API bound to libhc_b200.so.  `device`: the one CUDA device this process drives (default:
+    LOCAL_RANK); `devices`: a list -- every batch call is then split over them (hc_init_devices).  Calling it again
+    with another device list re-initialises the library (handles created before must not be used afterwards)."""
     global _api
+    if _api is not None and devices is not None:
+        arr = (C.c_int32 * len(devices))(*devices)
+        if _api.raw.hc_init_devices(arr, len(devices)) != 0:
+            raise RuntimeError("hc_init_devices failed: " + _api.raw.hc_last_error().decode())
+        return _api
     if _api is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -41,9 +49,17 @@ def load(device: int | None = None) -> CApi:
         lib.hc_resident_destroy.restype, lib.hc_resident_destroy.argtypes = None, [C.c_void_p]
         lib.hc_host_register.restype, lib.hc_host_register.argtypes = C.c_int32, [C.c_void_p, C.c_int64]
         lib.hc_host_unregister.restype, lib.hc_host_unregister.argtypes = C.c_int32, [C.c_void_p]
+        lib.hc_init_devices.restype, lib.hc_init_devices.argtypes = C.c_int32, [C.POINTER(C.c_int32), C.c_int32]
+        lib.hc_device_count.restype, lib.hc_device_count.argtypes = C.c_int32, []
+        lib.hc_request_cancel.restype, lib.hc_request_cancel.argtypes = None, [C.c_int32]
+        lib.hc_jit_prepare.restype, lib.hc_jit_prepare.argtypes = C.c_int32, [C.c_void_p, C.c_int32, c_double_p]
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
-        rc = lib.hc_init(device)
+        if devices is not None:
+            arr = (C.c_int32 * len(devices))(*devices)
+            rc = lib.hc_init_devices(arr, len(devices))
+        else:
+            rc = lib.hc_init(device)
         if rc != 0:
             raise RuntimeError("hc_init failed: " + lib.hc_last_error().decode())
         _api = api

@@ -46,12 +46,14 @@ def gather_results(res: BatchResults, dist=None, dst: int = 0) -> BatchResults |
     return concat_results(buf) if rank == dst else None
 
 
-def class_counts(res: BatchResults) -> dict:
-    """Solution-class counts in the sense of the reference's ResultStatistics (src/result.jl:146-212)
-    before multiplicity clustering: success / nonsingular / singular / real / at_infinity / failed."""
+def class_counts(res: BatchResults, mode: int = 0) -> dict:
+    """Per-path class counts (before multiplicity clustering; `result.statistics` gives the reference's
+    ResultStatistics).  mode 0 / 2: return codes are EndgameTrackerCode values (src/endgame_tracker.jl:100-117);
+    mode 1 (plain Tracker batches): TrackerCode values (src/tracker.jl:166-176), where nothing is "at infinity" and
+    every code but success is a failure."""
     ok = res.return_code == 1
     real = ok & (np.abs(res.solution.imag).max(axis=1) < 1e-6)       # src/path_result.jl:280-298
+    at_inf = np.isin(res.return_code, (2, 3)) if mode != 1 else np.zeros(res.N, dtype=bool)
     return {"paths": int(res.N), "success": int(ok.sum()), "nonsingular": int((ok & (res.singular == 0)).sum()),
             "singular": int((ok & (res.singular == 1)).sum()), "real": int(real.sum()),
-            "at_infinity": int(np.isin(res.return_code, (2, 3)).sum()),
-            "failed": int((~ok & ~np.isin(res.return_code, (2, 3))).sum())}
+            "at_infinity": int(at_inf.sum()), "failed": int((~ok & ~at_inf).sum())}

@@ -45,6 +45,12 @@ def total_degree(F: System, gamma: complex, target_parameters=None) -> TotalDegr
     supports, coeffs = F.support_coefficients(p)
     if F.n_eqs != F.n_vars:
         raise NotImplementedError("only square affine systems (SURVEY.md section 8: all five configs)")
+    # src/total_degree.jl:48-61: a system whose every polynomial has all its monomials of one degree is homogeneous; the
+    # reference then tracks on an affine chart with G = s .* (x[1:n-1].^D .- x[n].^D).  Charts are outside this path
+    # (SURVEY.md section 8f-3), so say so instead of silently building the affine start system.
+    if all(len(set(int(d) for d in A.sum(axis=0))) == 1 for A in supports):
+        raise NotImplementedError("homogeneous system: the reference puts it on an affine chart (src/total_degree.jl:94-108), "
+                                  "which this path does not build")
     D = np.array([int(A.sum(axis=0).max()) for A in supports], dtype=np.int64)
     scaling = np.array([np.abs(c).max() for c in coeffs], dtype=np.float64)
     n = F.n_vars

@@ -105,9 +105,23 @@ typedef struct {                 /* device timing of the last batch call on this
     int64_t h2d_bytes, d2h_bytes;
     int32_t grid, block, lanes;
     int64_t slab_bytes;
+    int32_t devices;             /* devices the batch was split over */
+    int32_t engine;              /* 0 lane group per path, 1 thread per path (interpreter), 2 thread per path (specialised kernel) */
 } hc_timing;
 
-int32_t hc_init(int32_t device);            /* selects the CUDA device of this process */
+int32_t hc_init(int32_t device);            /* the process drives this one CUDA device (= hc_init_devices(&device, 1)) */
+/* The process drives these CUDA devices with ONE host call per batch: every hc_track_* call splits its path index
+ * range into contiguous shards, one per device (sweeps: whole parameter points), launches them concurrently on
+ * per-device streams and copies each device's PathResult slice into the caller's arrays at the shard offset
+ * (reference: threaded_solve stores results by path index, src/solve.jl:628-709).  Batches with fewer than
+ * HC_B200_MIN_PATHS_PER_DEVICE (2048) paths per device use fewer devices.  Handles created afterwards hold one copy of
+ * their programs per device; call it before creating handles. */
+int32_t hc_init_devices(const int32_t* devices, int32_t n_devices);
+int32_t hc_device_count(void);
+/* stop_early_cb / catch_interrupt (reference src/solve.jl:618, 677, 685-707): on != 0 makes the running (and any
+ * later) batch kernel stop handing out new paths -- paths in flight finish, paths never started keep return_code 0
+ * (tracking).  May be called from another thread / a signal handler; every hc_track_* call clears it on entry. */
+void hc_request_cancel(int32_t on);
 const char* hc_last_error(void);
 void hc_options_default(hc_options* o);
 void* hc_system_create(const hc_program_desc* eval, const hc_program_desc* jac);
