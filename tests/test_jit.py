@@ -190,12 +190,14 @@ def test_jit_large_batch_is_deterministic_and_equals_interpreter(gpu, monkeypatc
 
 @pytest.mark.gpu
 def test_parity_build_is_bit_identical_to_the_host_compiled_code(sim, gpu, monkeypatch):
-    """What separates the GPU results from the CPU's is FMA contraction, nothing else: with --fmad=false the
-    specialised kernel reproduces the g++ build of the same unit (x86-64 baseline: no contraction) bit for bit --
-    return codes, step counts and endpoints -- on a slice of tritangents that contains ill-conditioned, dying and
-    extended-precision paths (IEEE sqrt / division on both sides; no transcendental on the path of a total-degree
-    homotopy).  The remaining deviation between device code and oracle is then an operation-order question that the
-    CPU suite covers."""
+    """What separates the GPU results from the CPU's is FMA contraction (and libm), nothing else: built with
+    --fmad=false the specialised kernel reproduces the g++ build of the same unit (x86-64 baseline: no contraction)
+    BIT FOR BIT -- return code, accepted / rejected steps, endpoint, t -- on every path of a tritangents slice
+    (diverging, dying at t < 1e-9, extended-precision and winding-number-4 singular paths included) except the
+    singular endpoints of winding number 3, whose Cauchy endgame takes a cube root (cbrt of CUDA's libdevice and of
+    glibc differ in the last bit); those still agree in code, winding number and, to the endgame's accuracy, endpoint.
+    (+, -, *, /, sqrt and fma are IEEE-exact on both sides.)  Measured first with tests/tools/gpu_parity_build.py:
+    739 of 768 paths bit-identical, the other 29 all of winding number 3."""
     from hcb200 import workloads
     monkeypatch.setenv("HC_B200_JIT", "1")
     w = workloads.tritangents_total_degree().subset(768)
@@ -203,10 +205,16 @@ def test_parity_build_is_bit_identical_to_the_host_compiled_code(sim, gpu, monke
     monkeypatch.setenv("HC_B200_JIT_FLAGS", "--fmad=false")
     rg = w.track(gpu, w.build(gpu))
     assert (rs.return_code == rg.return_code).all(), np.flatnonzero(rs.return_code != rg.return_code)
-    assert (rs.accepted_steps == rg.accepted_steps).all() and (rs.rejected_steps == rg.rejected_steps).all()
-    ok = rs.return_code == 1
-    assert np.array_equal(rs.solution[ok], rg.solution[ok])
-    assert np.array_equal(rs.t, rg.t)
+    assert (rs.winding_number == rg.winding_number).all() and (rs.singular == rg.singular).all()
+    exact = np.isin(rs.winding_number, (0, 1, 2, 4))      # nthroot(., m) is sqrt-only for these m
+    assert exact.sum() > 0.9 * w.N and (rs.extended_precision_used[exact] != 0).any() and (rs.winding_number[exact] > 1).any()
+    assert (rs.accepted_steps[exact] == rg.accepted_steps[exact]).all() and (rs.rejected_steps[exact] == rg.rejected_steps[exact]).all()
+    assert np.array_equal(rs.solution[exact], rg.solution[exact], equal_nan=True)
+    assert np.array_equal(rs.t[exact], rg.t[exact]) and np.array_equal(rs.accuracy[exact], rg.accuracy[exact], equal_nan=True)
+    rest = ~exact
+    if rest.any():
+        tol = max(1e-6, 10 * float(np.nanmax(rs.accuracy[rest])))
+        assert np.abs(rs.solution[rest] - rg.solution[rest]).max() < tol
     monkeypatch.delenv("HC_B200_JIT_FLAGS")
     rf = w.track(gpu, w.build(gpu))   # the production build (contraction on): same classes, different last bits
     assert_classes_match(rs, rf)
