@@ -10,7 +10,9 @@ import os
 
 from . import capi, flops, polyhedral, start_systems, systems
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+# mixed cells of the polyhedral configs (deterministic in the lifting seeds; enumerating them takes a minute for cyclic-7
+# and much longer for cyclooctane with the pure-Python enumerator of polyhedral.py): shipped with the package
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
 
 @dataclass
@@ -90,9 +92,9 @@ def cyclic7_total_degree(replicas: int = 1) -> Workload:
 
 def cyclic_polyhedral(n: int = 7, replicas: int = 1) -> Workload:
     """BASELINE.json configs[1]: cyclic-7 polyhedral start system, 924 mixed-volume paths (x replicas).
-    Lifting and mixed cells are cached in tests/golden (deterministic in the seeds; the enumeration
+    Lifting and mixed cells are cached in the package's data/ directory (deterministic in the seeds; the enumeration
     takes about a minute for n = 7)."""
-    ps = polyhedral.polyhedral(systems.cyclic(n), cache=os.path.join(_GOLDEN, f"cyclic{n}_cells.json"))
+    ps = polyhedral.polyhedral(systems.cyclic(n), cache=os.path.join(_DATA, f"cyclic{n}_cells.json"))
     S, ci = ps.start_solutions()
     cw = ps.cell_weights()
 
@@ -148,7 +150,7 @@ def cyclooctane_total_degree(limit: int | None = None) -> Workload:
 def cyclooctane_polyhedral() -> Workload:
     """BASELINE.json configs[3]: cyclooctane (benchmarks/cyclooctane.jl:4-27) on the polyhedral start system."""
     ps = polyhedral.polyhedral(systems.cyclooctane(), target_parameters=cyclooctane_parameters(), seed_coeffs=14, seed_origin=15,
-                               seed_lifting=16, cache=os.path.join(_GOLDEN, "cyclooctane_cells.json"))
+                               seed_lifting=16, cache=os.path.join(_DATA, "cyclooctane_cells.json"))
     S, ci = ps.start_solutions()
     cw = ps.cell_weights()
 
@@ -197,3 +199,29 @@ def biochem_sweep_from_starts(starts: np.ndarray, p1: np.ndarray, points: int, s
     return Workload("biochem_sweep", f"bio-chemical network 1 parameter sweep, {points} parameter points x {k} start solutions",
                     3, S, 0, build, path_q=Q, costs=flops.homotopy_costs(F),
                     sweep_starts=np.ascontiguousarray(starts, dtype=np.complex128), sweep_q=np.ascontiguousarray(q, dtype=np.complex128))
+
+
+def specialised_kernel_builders():
+    """(name, build(api) -> homotopy handle, hc_jit_prepare flags) of the BASELINE.json configs that run on the
+    specialised (run-time compiled) kernels: lets `__graft_entry__.build()` fill the on-disk kernel cache ahead of the
+    first batch -- NVRTC needs no device -- so that a bench or a solve on a fresh box loads cubins instead of compiling.
+    Only the code matters for the cache key: parameter values, gamma and start solutions are run-time data."""
+    def sl(F, tp=None):
+        def build(api):
+            td = start_systems.total_degree(F(), 0.4 + 1.3j, tp() if tp else None)
+            return api.homotopy(capi.H_STRAIGHT_LINE, api.system(td.F), api.system(td.G), gamma=td.gamma, G_params=td.scaling,
+                                F_params=td.target_parameters if td.target_parameters is not None else [])
+        return build
+
+    def cyclic7(api):
+        ps = polyhedral.polyhedral(systems.cyclic(7), cache=os.path.join(_DATA, "cyclic7_cells.json"))
+        h = api.system(ps.F)
+        api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs)
+        return api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)
+
+    def biochem(api):
+        z = np.zeros(10, dtype=np.complex128)
+        return api.homotopy(capi.H_PARAMETER, api.system(systems.biochem1()), p=z, q=z)
+    return [("cyclic7_polyhedral", cyclic7, 1), ("katsura8", sl(lambda: systems.katsura(8)), 0),
+            ("tritangents", sl(systems.tritangents, lambda: np.random.default_rng(3).normal(size=20)), 0),
+            ("biochem_sweep", biochem, 2)]

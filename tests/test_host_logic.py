@@ -75,7 +75,7 @@ def test_mixed_cells_give_the_mixed_volume():
     ps = ph.polyhedral(systems.cyclic(5))
     assert ps.n_paths() == 70
     import os
-    cache = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cyclic7_cells.json")
+    cache = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "homotopycontinuation.jl_b200", "data", "cyclic7_cells.json")
     ps = ph.polyhedral(systems.cyclic(7), cache=cache)
     assert ps.n_paths() == 924
     for cell in ps.cells:   # every cached cell satisfies the mixed-cell inequalities for the cached lifting
