@@ -275,7 +275,7 @@ bool jit_wanted(const HomotopyH& H, long long N, bool complex_t = false) {
     if (complex_t && H.dev.kind != H_STRAIGHT_LINE) return false;  // the generated parameter code assumes real t
     const char* e = getenv("HC_B200_JIT");
     if (e && !strcmp(e, "0")) return false;
-    if (H.dev.n > env_int("HC_B200_JIT_MAX_N", 24)) return false;
+    if (H.dev.n > env_int("HC_B200_JIT_MAX_N", 14)) return false;  // beyond the register-blocked LU the lane-group engine wins (measured: cyclooctane, n = 17)
     if (e && !strcmp(e, "1")) return true;
 #ifdef HC_HOST_SIM
     return false;

@@ -79,7 +79,8 @@ struct PathMem {
     CV pv;   // (unused)
     DV<S> rbd;
     RV w, rs, rwork, egrs, egcs, ais, ait, aia, aic, val, tw;
-    RV ptw;  // specialised kernels, toric stage: t^w_i at the cached t
+    RV ptw;  // (unused)
+    CV wt;   // specialised kernels, toric stage: the pairs (w_i, t^w_i) at the cached t -- one 16-byte load gives both
     IV ipiv, perm;
 };
 
@@ -105,8 +106,9 @@ HC_HD SlabSizes carve(PathMem<S>& M, int n, int P, int tape_cx, unsigned char* h
     // values take its place in the hot slab, the tape of the DoubleDouble interpreter moves to the cold part
     if (!jit) M.tape = C((size_t)tape_cx);
     M.pv = M.tape;
+    if (jit) M.wt = C(P > 0 ? P : 1); else M.wt = M.tape;
     M.w = R(n); M.rs = R(n); M.rwork = R(n); M.tw = R(P > 0 ? P : 1);
-    if (jit) M.ptw = R(P > 0 ? P : 1); else M.ptw = M.tw;
+    M.ptw = M.tw;
     M.ipiv = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
     M.perm = SV<int, S>::make(base ? base + off : nullptr); off += 4 * (size_t)n;
     SlabSizes s;
@@ -351,7 +353,7 @@ struct Path {
     // then: the DoubleDouble interpreter owns it only during eval_dd).  Complex t never reaches these kernels
     // (hc_api.cu keeps such batches on the interpreter).
     struct JPar { double tr, omt, g1, ti; bool toric, at0; };
-    HC_HDN void jit_refresh_ptw(cx t) {  // M.ptw[i] = t^w_i (toric_homotopy.jl:145-177; t == 0: weights that are exactly 0 survive)
+    HC_HDN void jit_refresh_ptw(cx t) {  // M.wt[i] = (w_i, t^w_i) (toric_homotopy.jl:145-177; t == 0: weights that are exactly 0 survive)
         if (pv_kind == kind && pv_t.re == t.re && pv_t.im == t.im) return;
         const int P = H->P;
         const ToricT tt = toric_t(t);
@@ -361,9 +363,9 @@ struct Path {
             const double w0 = M.tw[i], w1 = M.tw[i + 1], w2 = M.tw[i + 2], w3 = M.tw[i + 3];
             const double e0 = at0 ? (w0 == 0.0 ? 1.0 : 0.0) : exp(w0 * tt.lt), e1 = at0 ? (w1 == 0.0 ? 1.0 : 0.0) : exp(w1 * tt.lt);
             const double e2 = at0 ? (w2 == 0.0 ? 1.0 : 0.0) : exp(w2 * tt.lt), e3 = at0 ? (w3 == 0.0 ? 1.0 : 0.0) : exp(w3 * tt.lt);
-            M.ptw[i] = e0; M.ptw[i + 1] = e1; M.ptw[i + 2] = e2; M.ptw[i + 3] = e3;
+            M.wt[i] = mk(w0, e0); M.wt[i + 1] = mk(w1, e1); M.wt[i + 2] = mk(w2, e2); M.wt[i + 3] = mk(w3, e3);
         }
-        for (; i < P; ++i) { const double w = M.tw[i]; M.ptw[i] = at0 ? (w == 0.0 ? 1.0 : 0.0) : exp(w * tt.lt); }
+        for (; i < P; ++i) { const double w = M.tw[i]; M.wt[i] = mk(w, at0 ? (w == 0.0 ? 1.0 : 0.0) : exp(w * tt.lt)); }
         pv_kind = kind; pv_t = t;
     }
     HC_HD JPar jit_par_ctx(cx t) {
@@ -380,7 +382,8 @@ struct Path {
     }
     // real factors of the Taylor coefficients 0..3 of a toric parameter: c_k = u_i F_k (same formulas as param_series)
     HC_HD void jit_tfac(int i, const JPar& c, double& f0, double& f1, double& f2, double& f3) const {
-        const double w = M.tw[i], tw = M.ptw[i];
+        const cx wt = M.wt[i];
+        const double w = wt.re, tw = wt.im;
         if (c.at0) {
             f0 = w < 1e-12 ? 1.0 : 0.0;
             f1 = (!(w < 1e-12) && fabs(w - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(w), 1.0)) ? 1.0 : 0.0;
@@ -403,9 +406,9 @@ struct Path {
     template <int PP> HC_HD cx jit_ldq(int i) const { return PP ? jq[i] : pld<S>(H->q + i); }
     template <int MODE, int PP> HC_HD cx jit_par(int i, const JPar& c) const {
         const cx p = jit_ldp<PP>(i);
-        if (MODE == 4) return p * (double)M.ptw[i];
+        if (MODE == 4) return p * ((cx)M.wt[i]).im;
         const cx q = jit_ldq<PP>(i);
-        const double f = (MODE == 3 && c.toric) ? (double)M.ptw[i] : c.tr;
+        const double f = (MODE == 3 && c.toric) ? ((cx)M.wt[i]).im : c.tr;
         return mk(f * p.re + c.omt * q.re, f * p.im + c.omt * q.im);
     }
     template <int PP> HC_HD void jit_pser_lin(int i, const JPar& c, cx& c0, cx& c1) const {
@@ -440,8 +443,8 @@ struct Path {
     // predictor's refinement and the extended-precision refinement multiply with later.
     HC_HDN void eval_trip(CV u, CV x, cx t, bool keepA, bool rowsum) {
         n_evaljac++;
-#if HC_JIT_PREFETCH
-        if (kind == H_TORIC && pv_kind == kind && pv_t.re == t.re) { const int P = H->P; for (int i = 0; i < P; i += 2) M.ptw.prefetch(i); }
+#if HC_JIT_PREFETCH & 2
+        if (kind == H_TORIC && pv_kind == kind && pv_t.re == t.re) { const int P = H->P; for (int i = 0; i < P; ++i) M.wt.prefetch(i); }
 #endif
         jit_evaljac(u, M.LU, M.A, x, t, keepA, rowsum);
         a_in_lu = true; rs_raw = rowsum;
@@ -837,7 +840,7 @@ struct Path {
             scaled = true;
         }
         if (nn == 1) { cx v = cdiv(b[0], a_in_lu ? (cx)M.LU[0] : (cx)M.A[0]); g.sync(); if (g.lane == 0) x[0] = v; g.sync(); return; }
-#if HC_JIT_PREFETCH
+#if HC_JIT_PREFETCH & 1
         if (use_reg_lu()) { for (int i = 0; i < nn * nn; ++i) M.LU.prefetch(i); }
 #endif
         if (!factorized) factorize(scaled);
@@ -1068,8 +1071,11 @@ struct Path {
             // (x, x') of the previous update: read by the Hermite predictor only, i.e. once winding > 1; tx still holds
             // them here, so the copy into the cold slab waits until then
             if (winding > 1) { HC_PAR(i, 2 * nn) M.ptx1[i] = M.tx[i]; g.sync(); }
-#if HC_JIT_PREFETCH
+#if HC_JIT_PREFETCH & 1
             for (int i = 0; i < nn * nn; ++i) M.A.prefetch(i);  // refine_fixed multiplies with A after the first Taylor pass
+#endif
+#if HC_JIT_PREFETCH & 2
+            if (kind == H_TORIC) { const int P = H->P; for (int i = 0; i < P; ++i) M.wt.prefetch(i); }
 #endif
             pprev_t = pt; pt = t;
             if (winding > 1) pu_splane(t);
