@@ -181,6 +181,7 @@ inline std::shared_ptr<Module> build_module(const GenInput& in, int P, int tape_
     unit += "#define HC_JIT_SYNC " + std::to_string(sync) + "\n";
 #ifndef HC_HOST_SIM
     unit += "#define HC_JIT_LU_SMEM " + std::to_string(lu_smem) + "\n";
+    unit += std::string("#define HC_JIT_LU_UNROLL_MAX_N ") + (getenv("HC_B200_JIT_LU_UNROLL_MAX_N") ? getenv("HC_B200_JIT_LU_UNROLL_MAX_N") : "0") + "\n";
     unit += std::string("#define HC_JIT_PREFETCH ") + (getenv("HC_B200_JIT_PREFETCH") ? getenv("HC_B200_JIT_PREFETCH") : "0") + "\n";
 #endif
     unit += "#define HC_JIT_GEN \"hc_jit_gen.inc\"\n";

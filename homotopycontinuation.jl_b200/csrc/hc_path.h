@@ -669,6 +669,55 @@ struct Path {
     // n^3/3 loads + n^2 stores instead of 2n^3/3 loads + n^3/3 stores.  Every element still sees
     // its updates in increasing k with the same cfnma, so LU, ipiv and the solutions are bit-identical
     // to lu_prepare + lu_factor / lu_solve above (linear_algebra.jl:130-184, 310-316).
+    // Fully unrolled variant (N^3 / 3 code, no selects: every index is a compile-time constant).  Lockstep kernels stream
+    // their code once for all warps of the CTA, so for small N the shorter instruction count wins over the footprint
+    // (HC_JIT_LU_UNROLL_MAX_N); same arithmetic, same pivots, bit-identical factors.
+    template <int N, class AV>
+    HC_HDN void lu_factor_reg_unrolled(bool scale, AV A) {
+        LV LU = M.LU;
+        int rowof[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) rowof[i] = i;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            cx col[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) col[i] = A[j * N + rowof[i]];
+            if (scale) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) col[i] = col[i] * M.rs[rowof[i]];
+            }
+#pragma unroll
+            for (int k = 0; k < j; ++k) {
+#pragma unroll
+                for (int i = k + 1; i < N; ++i) col[i] = cfnma(LU[k * N + i], col[k], col[i]);
+            }
+            double amax = -1.0; int kp = j;
+#pragma unroll
+            for (int i = j; i < N; ++i) { double v = abs2(col[i]); if (v > amax) { amax = v; kp = i; } }
+            M.ipiv[j] = kp;
+            if (amax > 0.0) {
+                if (kp != j) {
+                    const cx cj = col[j]; cx ck = cj;
+                    const int rj = rowof[j]; int rk = rj;
+#pragma unroll
+                    for (int i = j + 1; i < N; ++i) if (i == kp) { ck = col[i]; col[i] = cj; rk = rowof[i]; rowof[i] = rj; }
+                    col[j] = ck; rowof[j] = rk;
+#pragma unroll
+                    for (int k = 0; k < j; ++k) { cx t0 = LU[k * N + j], t1 = LU[k * N + kp]; LU[k * N + j] = t1; LU[k * N + kp] = t0; }
+                }
+                const cx pinv = cinv(col[j]);
+#pragma unroll
+                for (int i = j + 1; i < N; ++i) col[i] = col[i] * pinv;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) M.perm[i] = rowof[i];
+        factorized = true;
+        n_fact++;
+    }
     // A: where the matrix sits -- M.A, or the LU buffer itself (in place: column j is read in full, in original row order,
     // before its permuted, eliminated form is written back; the columns to its right are still untouched)
     template <int N, class AV>
@@ -760,6 +809,13 @@ struct Path {
     HC_HD bool use_reg_lu() const { return G == 1 && S != 1 && n >= 2 && n <= HC_REG_LU_MAX; }
     HC_HD void factorize(bool scale) {
         if (use_reg_lu()) {
+#if defined(HC_JIT_N) && defined(HC_JIT_LU_UNROLL_MAX_N)
+            if (HC_JIT_N <= HC_JIT_LU_UNROLL_MAX_N) {
+                if (a_in_lu) lu_factor_reg_unrolled<(HC_JIT_N >= 2 && HC_JIT_N <= HC_REG_LU_MAX) ? HC_JIT_N : 2>(scale, M.LU);
+                else lu_factor_reg_unrolled<(HC_JIT_N >= 2 && HC_JIT_N <= HC_REG_LU_MAX) ? HC_JIT_N : 2>(scale, M.A);
+                return;
+            }
+#endif
             if (a_in_lu) {
 #define HC_CALL_(NN) lu_factor_reg<NN>(scale, M.LU)
                 HC_REG_LU_DISPATCH(HC_CALL_)
