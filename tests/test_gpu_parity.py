@@ -325,3 +325,31 @@ def test_cancel_stops_handing_out_paths(gpu):
     assert (r.return_code[done] == 1).all()
     full = H.track_batch(S[:256])                     # the flag is cleared on entry of the next call
     assert (full.return_code == 1).all()
+
+
+def test_polyhedral_on_the_lane_group_engine(oracle, gpu, monkeypatch):
+    """MODE_POLYHEDRAL (toric stage, re-weighted restart, coefficient stage; src/polyhedral.jl:414-530) on the lane-group
+    engine: forced onto a small system, where the thread-per-path engine would run by default."""
+    from hcb200 import polyhedral as ph
+    monkeypatch.setenv("HC_B200_ENGINE", "group")
+    ps = ph.polyhedral(systems.cyclic(5))
+    S, ci = ps.start_solutions()
+    res = []
+    for api in (oracle, gpu):
+        h = api.system(ps.F)
+        res.append(capi.polyhedral_track_batch(api, api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs),
+                                               api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs), S, ci, ps.cell_weights()))
+    assert lib.timing().lanes in (8, 32)
+    assert_batches_match(*res)
+    assert (res[1].return_code == 1).sum() == 70
+
+
+def test_cyclooctane_polyhedral_slice_config4(oracle, gpu):
+    """BASELINE.json configs[3] as the benchmark runs it (benchmarks/cyclooctane.jl:27-29: solve(F0), polyhedral start
+    system by default, src/solve.jl:121): n = 17, lane-group engine, the first 2048 of 32 768 mixed-volume paths."""
+    from hcb200 import workloads
+    w = workloads.cyclooctane_polyhedral().subset(2048)
+    ro, rg = (w.track(api, w.build(api), nthreads=8) for api in (oracle, gpu))
+    assert lib.timing().lanes in (8, 32)
+    assert_classes_match(ro, rg)
+    assert (rg.return_code == 1).sum() > 0
