@@ -301,6 +301,7 @@ std::shared_ptr<jit::Module> jit_module(HomotopyH& H, bool poly, bool load = tru
     if (H.jit_mod[slot] && load) return H.jit_mod[slot];
     jit::GenInput in;
     in.kind = H.dev.kind; in.poly = poly; in.n = H.dev.n; in.path_params = path_params;
+    in.hoist = env_int("HC_B200_JIT_HOIST", 1000);
     in.Fe = &H.F->eval.ref; in.Fj = &H.F->jac.ref;
     if (H.G) { in.Ge = &H.G->eval.ref; in.Gj = &H.G->jac.ref; }
     // Lanes per SM and where the LU factors live.  The factors are the most re-read piece of lane state; if

@@ -381,8 +381,10 @@ struct Path {
         return c;
     }
     // real factors of the Taylor coefficients 0..3 of a toric parameter: c_k = u_i F_k (same formulas as param_series)
-    HC_HD void jit_tfac(int i, const JPar& c, double& f0, double& f1, double& f2, double& f3) const {
-        const cx wt = M.wt[i];
+    // (w_i, t^w_i) of a toric parameter; a separate statement of the generated code, issued well ahead of its use
+    // (hc_jitgen.h hoists it), because this is a per-lane array that the L1 does not keep between uses
+    template <int MODE> HC_HD cx jit_ldw(int i, const JPar& c) const { return (MODE == 4 || c.toric) ? (cx)M.wt[i] : mk(0.0); }
+    HC_HD void jit_tfac(const cx wt, const JPar& c, double& f0, double& f1, double& f2, double& f3) const {
         const double w = wt.re, tw = wt.im;
         if (c.at0) {
             f0 = w < 1e-12 ? 1.0 : 0.0;
@@ -404,11 +406,11 @@ struct Path {
     // (toric or coefficient stage, decided per lane at run time), 4: toric homotopy
     template <int PP> HC_HD cx jit_ldp(int i) const { return PP ? jp[i] : pld<S>(H->p + i); }
     template <int PP> HC_HD cx jit_ldq(int i) const { return PP ? jq[i] : pld<S>(H->q + i); }
-    template <int MODE, int PP> HC_HD cx jit_par(int i, const JPar& c) const {
+    template <int MODE, int PP> HC_HD cx jit_par(int i, const JPar& c, const cx wt) const {
         const cx p = jit_ldp<PP>(i);
-        if (MODE == 4) return p * ((cx)M.wt[i]).im;
+        if (MODE == 4) return p * wt.im;
         const cx q = jit_ldq<PP>(i);
-        const double f = (MODE == 3 && c.toric) ? ((cx)M.wt[i]).im : c.tr;
+        const double f = (MODE == 3 && c.toric) ? wt.im : c.tr;
         return mk(f * p.re + c.omt * q.re, f * p.im + c.omt * q.im);
     }
     template <int PP> HC_HD void jit_pser_lin(int i, const JPar& c, cx& c0, cx& c1) const {
@@ -416,17 +418,17 @@ struct Path {
         c0 = mk(c.tr * p.re + c.omt * q.re, c.tr * p.im + c.omt * q.im);
         c1 = p - q;
     }
-    template <int MODE, int PP> HC_HD void jit_pser(int i, const JPar& c, cx& c0, cx& c1, cx& c2, cx& c3) const {
+    template <int MODE, int PP> HC_HD void jit_pser(int i, const JPar& c, const cx wt, cx& c0, cx& c1, cx& c2, cx& c3) const {
         const cx p = jit_ldp<PP>(i);
         if (MODE == 4) {
             double f0, f1, f2, f3;
-            jit_tfac(i, c, f0, f1, f2, f3);
+            jit_tfac(wt, c, f0, f1, f2, f3);
             c0 = p * f0; c1 = p * f1; c2 = p * f2; c3 = p * f3;
             return;
         }
         const cx q = jit_ldq<PP>(i);
         double f0 = c.tr, f1 = 1.0, f2 = 0.0, f3 = 0.0;
-        if (c.toric) jit_tfac(i, c, f0, f1, f2, f3);
+        if (c.toric) jit_tfac(wt, c, f0, f1, f2, f3);
         c0 = mk(f0 * p.re + c.omt * q.re, f0 * p.im + c.omt * q.im);
         c1 = mk(f1 * p.re - c.g1 * q.re, f1 * p.im - c.g1 * q.im);
         c2 = p * f2; c3 = p * f3;
