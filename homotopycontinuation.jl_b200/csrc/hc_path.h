@@ -167,6 +167,7 @@ struct Path {
     double ds_prev, accuracy, omega, omega_prev, mu, tau;
     bool extended_prec, used_extended_prec, refined_extended_prec, keep_extended_prec, use_strict_beta_tau;
     bool factorized, scaled;  // MatrixWorkspace flags
+    unsigned long long perm_bits;  // row permutation of the register-blocked LU, 4 bits per row (n <= 12)
     bool a_in_lu, rs_raw;     // specialised kernels: the Jacobian sits in the LU buffer (factorize in place); M.rs holds raw Skeel row sums
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
     const DevProgram* tape_prog; int tape_kind; cx tape_t;  // whose inputs (constants, parameters at t) the fp64 tape holds
@@ -352,7 +353,7 @@ struct Path {
     // Taylor passes of a predictor update, the real factors of the coefficients 1..3 (M.tape viewed as doubles, idle
     // then: the DoubleDouble interpreter owns it only during eval_dd).  Complex t never reaches these kernels
     // (hc_api.cu keeps such batches on the interpreter).
-    struct JPar { double tr, omt, g1, ti; bool toric, at0; };
+    struct JPar { double tr, omt, g1, ti; bool toric, at0; const cx *pg, *qg; unsigned ps, qs; };
     HC_HDN void jit_refresh_ptw(cx t) {  // M.wt[i] = (w_i, t^w_i) (toric_homotopy.jl:145-177; t == 0: weights that are exactly 0 survive)
         if (pv_kind == kind && pv_t.re == t.re && pv_t.im == t.im) return;
         const int P = H->P;
@@ -370,6 +371,12 @@ struct Path {
     }
     HC_HD JPar jit_par_ctx(cx t) {
         JPar c; c.toric = kind == H_TORIC; c.at0 = false; c.ti = 0.0;
+        // where p and q are: generic pointers (per-path rows, host build) and, on the device, the shared-window address of
+        // the staged arrays -- resolved once per function, not once per parameter
+        c.pg = jp; c.qg = jq; c.ps = c.qs = 0u;
+#if defined(__CUDA_ARCH__)
+        if (S == 2) { c.ps = (unsigned)__cvta_generic_to_shared(H->p); c.qs = H->q ? (unsigned)__cvta_generic_to_shared(H->q) : 0u; }
+#endif
         c.tr = t.re; c.omt = c.toric ? 0.0 : 1.0 - t.re; c.g1 = c.toric ? 0.0 : 1.0;
         if (c.toric) jit_refresh_ptw(t);
         return c;
@@ -404,29 +411,36 @@ struct Path {
     }
     // PP: the batch carries per-path parameter rows; MODE 2: parameter / coefficient homotopy, 3: polyhedral driver
     // (toric or coefficient stage, decided per lane at run time), 4: toric homotopy
-    template <int PP> HC_HD cx jit_ldp(int i) const { return PP ? jp[i] : pld<S>(H->p + i); }
-    template <int PP> HC_HD cx jit_ldq(int i) const { return PP ? jq[i] : pld<S>(H->q + i); }
+    HC_HD static cx jit_lds(unsigned a) {
+        cx v = mk(0.0);
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(a));
+#endif
+        return v;
+    }
+    template <int PP> HC_HD cx jit_ldp(int i, const JPar& c) const { return (PP || S != 2) ? c.pg[i] : jit_lds(c.ps + 16u * (unsigned)i); }
+    template <int PP> HC_HD cx jit_ldq(int i, const JPar& c) const { return (PP || S != 2) ? c.qg[i] : jit_lds(c.qs + 16u * (unsigned)i); }
     template <int MODE, int PP> HC_HD cx jit_par(int i, const JPar& c, const cx wt) const {
-        const cx p = jit_ldp<PP>(i);
+        const cx p = jit_ldp<PP>(i, c);
         if (MODE == 4) return p * wt.im;
-        const cx q = jit_ldq<PP>(i);
+        const cx q = jit_ldq<PP>(i, c);
         const double f = (MODE == 3 && c.toric) ? wt.im : c.tr;
         return mk(f * p.re + c.omt * q.re, f * p.im + c.omt * q.im);
     }
     template <int PP> HC_HD void jit_pser_lin(int i, const JPar& c, cx& c0, cx& c1) const {
-        const cx p = jit_ldp<PP>(i), q = jit_ldq<PP>(i);
+        const cx p = jit_ldp<PP>(i, c), q = jit_ldq<PP>(i, c);
         c0 = mk(c.tr * p.re + c.omt * q.re, c.tr * p.im + c.omt * q.im);
         c1 = p - q;
     }
     template <int MODE, int PP> HC_HD void jit_pser(int i, const JPar& c, const cx wt, cx& c0, cx& c1, cx& c2, cx& c3) const {
-        const cx p = jit_ldp<PP>(i);
+        const cx p = jit_ldp<PP>(i, c);
         if (MODE == 4) {
             double f0, f1, f2, f3;
             jit_tfac(wt, c, f0, f1, f2, f3);
             c0 = p * f0; c1 = p * f1; c2 = p * f2; c3 = p * f3;
             return;
         }
-        const cx q = jit_ldq<PP>(i);
+        const cx q = jit_ldq<PP>(i, c);
         double f0 = c.tr, f1 = 1.0, f2 = 0.0, f3 = 0.0;
         if (c.toric) jit_tfac(wt, c, f0, f1, f2, f3);
         c0 = mk(f0 * p.re + c.omt * q.re, f0 * p.im + c.omt * q.im);
@@ -716,7 +730,7 @@ struct Path {
             for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
         }
 #pragma unroll
-        for (int i = 0; i < N; ++i) M.perm[i] = rowof[i];
+        { unsigned long long pk = 0; for (int i = 0; i < N; ++i) pk |= (unsigned long long)rowof[i] << (4 * i); perm_bits = pk; }
         factorized = true;
         n_fact++;
     }
@@ -772,7 +786,7 @@ struct Path {
             for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
         }
 #pragma unroll
-        for (int i = 0; i < N; ++i) M.perm[i] = rowof[i];
+        { unsigned long long pk = 0; for (int i = 0; i < N; ++i) pk |= (unsigned long long)rowof[i] << (4 * i); perm_bits = pk; }
         factorized = true;
         n_fact++;
     }
@@ -782,7 +796,9 @@ struct Path {
         LV A = M.LU;
         cx xr[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) { const int r = M.perm[i]; xr[i] = b[r]; if (scale) xr[i] = M.rs[r] * xr[i]; }
+        const unsigned long long pk = perm_bits;  // one scalar instead of N dependent index loads: the b[r] loads go out at once
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const int r = (int)((pk >> (4 * i)) & 15u); xr[i] = b[r]; if (scale) xr[i] = M.rs[r] * xr[i]; }
 #pragma unroll
         for (int j = 0; j < N - 1; ++j) {
 #pragma unroll
