@@ -153,3 +153,27 @@ def biochem1() -> System:
             x[1] + x[2] - 1.0,
         ]
     return make_system(build, 3, 10)
+
+
+# bio-chemical reaction networks 2 - 4 of the reference benchmark (benchmarks/bio-chemical-rection-networks.jl:46-61, 106,
+# 128-131; networks 2 and 3 are the same polynomials at two parameter points)
+BIOCHEM2_PVALS = np.array([0.005, 0.1, 2.8, 10, 100, 0.1, 0.01, 0.0])
+BIOCHEM3_PVALS = np.array([0.005, 0.1, 2.8, 10, 100, 0.1, 0.01, 1.0])
+BIOCHEM4_PVALS = np.array([1.0, 0.2, 1.0])
+
+
+def biochem2() -> System:
+    def build(x, p):
+        p34 = p[2] ** 4
+        return [
+            -x[0] ** 5 * x[1] * p[4] + x[0] ** 4 * x[2] * p[5] * p[7] - x[0] * x[1] * p34 * p[4] + x[2] * p34 * p[5] * p[7]
+            - x[0] ** 5 * p[6] + x[0] ** 4 * x[2] * p[3] - x[0] * p34 * p[6] + x[2] * p34 * p[3] + x[0] ** 4 * p[0] + x[0] ** 4 * p[1] + p[0] * p34,
+            -x[0] ** 5 * x[1] * p[4] - x[0] * x[1] * p34 * p[4] - x[0] ** 4 * x[1] * p[6] + x[0] ** 4 * x[2] * p[3] - x[1] * p34 * p[6]
+            + x[2] * p34 * p[3] + x[0] ** 4 * p[0] + x[0] ** 4 * p[1] + p[0] * p34,
+            x[0] * x[1] * p[4] - x[2] * p[5] * p[7] - x[2] * p[3] - x[2] * p[6],
+        ]
+    return make_system(build, 3, 8)
+
+
+def biochem4() -> System:
+    return make_system(lambda x, p: [-x[0] ** 3 * p[2] - x[0] * p[1] ** 2 * p[2] + x[0] ** 2 * p[0]], 1, 3)
