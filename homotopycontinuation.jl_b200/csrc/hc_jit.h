@@ -124,7 +124,10 @@ inline std::string nvrtc_compile(const std::string& unit, const std::string& gen
     nvrtcProgram prog;
     nvrtcResult r = N.create(&prog, unit.c_str(), "hc_jit_unit.cu", (int)names.size(), texts.data(), names.data());
     if (r != NVRTC_SUCCESS) throw std::string("nvrtcCreateProgram: ") + N.errstr(r);
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DHC_JIT=1"};
+    // no FMA contraction by default (HC_B200_FMAD=1 turns it on: + 4 ... 7 % paths/s, results then differ from the
+    // CPU build of the same code in the last bits, and rounding-sensitive paths may end differently)
+    const bool fmad = getenv("HC_B200_FMAD") && atoi(getenv("HC_B200_FMAD")) != 0;
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DHC_JIT=1", fmad ? "--fmad=true" : "--fmad=false"};
     std::string extra;
     if (const char* e = getenv("HC_B200_JIT_FLAGS")) extra = e;
     std::vector<std::string> extra_opts;
@@ -192,6 +195,7 @@ inline std::shared_ptr<Module> build_module(const GenInput& in, int P, int tape_
     h = fnv1a(gen, h);
     for (const std::string& nme : header_names()) { hdr_text.push_back(read_file(dir + "/" + nme)); h = fnv1a(hdr_text.back(), h); }
     if (const char* e = getenv("HC_B200_JIT_FLAGS")) h = fnv1a(e, h);
+    if (const char* e = getenv("HC_B200_FMAD")) h = fnv1a(std::string("fmad") + e, h);
 #ifdef HC_HOST_SIM
     h = fnv1a("host-sim", h);
 #endif
