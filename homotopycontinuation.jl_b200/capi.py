@@ -180,6 +180,9 @@ class CApi:
         # device-side start generation: entry points of libhc_b200 only (the oracle takes explicit starts)
         f("track_total_degree", C.c_int32, [C.c_void_p, C.POINTER(Options), c_int32_p, C.c_int64, C.c_int64,
                                             C.POINTER(ResultsDesc)], optional=True)
+        f("polyhedral_track_cells", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(Options), C.c_int64, C.c_int64, C.c_int32,
+                                                c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p,
+                                                C.POINTER(ResultsDesc)], optional=True)
         f("track_sweep", C.c_int32, [C.c_void_p, C.POINTER(Options), C.c_int64, c_double_p, C.c_int64, c_double_p,
                                      C.POINTER(ResultsDesc)], optional=True)
 
@@ -408,4 +411,29 @@ def polyhedral_track_batch(api: CApi, Htoric: HomotopyHandle, Hcoeff: HomotopyHa
                                      _ip(ci), _dp(cw), cw.shape[0], C.byref(d), nthreads)
     if rc:
         raise RuntimeError(f"polyhedral_track_batch failed ({rc})")
+    return res
+
+
+def polyhedral_track_cells(api: CApi, Htoric: HomotopyHandle, Hcoeff: HomotopyHandle, cells: dict, cell_weights,
+                           first: int = 0, count: int | None = None, options: Options | None = None,
+                           out: BatchResults | None = None) -> BatchResults:
+    """Polyhedral batch whose start solutions are made on the device from per-cell data (hc_polyhedral_track_cells;
+    `cells` = PolyhedralStart.binomial_data(): volume, H, mu, r).  Path k = start solution (first + k) mod mixed volume."""
+    if api._polyhedral_track_cells is None:
+        raise RuntimeError("device-side start generation is an entry point of libhc_b200")
+    n, P = Htoric.n, Htoric.P
+    vol = np.ascontiguousarray(cells["volume"], dtype=np.int64)
+    Hm = np.ascontiguousarray(cells["H"], dtype=np.int64).reshape(len(vol), n, n)
+    mu = np.ascontiguousarray(cells["mu"], dtype=np.float64).reshape(len(vol), n)
+    r = np.ascontiguousarray(cells["r"], dtype=np.float64).reshape(len(vol), n)
+    cw = np.ascontiguousarray(cell_weights, dtype=np.float64).reshape(len(vol), P)
+    N = int(vol.sum()) - int(first) if count is None else int(count)
+    opts = options if options is not None else api.default_options()
+    res = _out_or_new(out, n, N)
+    d = res.desc()
+    rc = api._polyhedral_track_cells(Htoric.handle, Hcoeff.handle, C.byref(opts), int(first), N, len(vol),
+                                     vol.ctypes.data_as(c_int64_p), Hm.ctypes.data_as(c_int64_p), _dp(mu), _dp(r), _dp(cw),
+                                     C.byref(d))
+    if rc:
+        raise RuntimeError(f"polyhedral_track_cells failed ({rc}): {_last_error(api)}")
     return res

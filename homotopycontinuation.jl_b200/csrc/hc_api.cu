@@ -480,7 +480,13 @@ struct StartGen {
     long long start_rows = 0;           // > 0: `starts` holds this many rows, path k starts from row k % start_rows
     long long param_div = 0;            // > 0: the per-path parameter arrays hold one row per param_div consecutive paths
     const int32_t* degrees = nullptr;   // total degree: no `starts` at all
-    long long td_first = 0;
+    long long td_first = 0;             // index of the batch's first path in the start system (total degree and binomial starts)
+    // polyhedral start solutions made on the device: per mixed cell its volume, the Hermite normal form of its binomial
+    // system, the transformed angles and the moduli (hc_polyhedral_track_cells)
+    const int64_t* bin_volume = nullptr;
+    const int64_t* bin_H = nullptr;
+    const double* bin_mu = nullptr;
+    const double* bin_r = nullptr;
 };
 
 void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1,
@@ -509,6 +515,26 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
         B.td_roots = (const cx*)D.upload<double>(roots.data(), roots.size());
         B.td_degrees = D.upload<int>(deg.data(), (size_t)n);
         B.td_first = sg.td_first;
+    } else if (sg.bin_H) {
+        if (mode != MODE_POLYHEDRAL || ncells <= 0 || !sg.bin_volume || !sg.bin_mu || !sg.bin_r) throw std::string("binomial start solutions: cell data missing");
+        std::vector<long long> first((size_t)ncells + 1, 0);
+        for (int c = 0; c < ncells; ++c) {
+            long long det = 1;
+            for (int i = 0; i < n; ++i) {
+                const long long d = sg.bin_H[((size_t)c * n + i) * n + i];
+                if (d < 1) throw std::string("binomial start solutions: the diagonal of a Hermite normal form must be positive");
+                det *= d;
+            }
+            if (det != sg.bin_volume[c]) throw std::string("binomial start solutions: volume of cell ") + std::to_string(c) + " is not det(H)";
+            first[(size_t)c + 1] = first[(size_t)c] + det;
+        }
+        if (sg.td_first < 0) throw std::string("binomial start solutions: negative first path index");
+        B.ncells = ncells;
+        B.cell_first = D.upload<long long>(first.data(), first.size());
+        B.bin_H = D.upload<long long>((const long long*)sg.bin_H, (size_t)ncells * n * n);
+        B.bin_mu = D.upload<double>(sg.bin_mu, (size_t)ncells * n);
+        B.bin_r = D.upload<double>(sg.bin_r, (size_t)ncells * n);
+        B.k_first = sg.td_first;
     } else {
         if (!starts) throw std::string("start solutions missing");
         B.start_mod = sg.start_rows;
@@ -522,10 +548,12 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     D.A.H.path_p = path_p ? (const cx*)D.upload<double>(path_p, (size_t)2 * P * prow) : nullptr;
     D.A.H.path_q = path_q ? (const cx*)D.upload<double>(path_q, (size_t)2 * P * prow) : nullptr;
     if (mode == MODE_POLYHEDRAL) {
-        if (!cell_index || !cell_weights || ncells <= 0) throw std::string("polyhedral batch: cell_index / cell_weights missing");
-        for (long long k = 0; k < N; ++k)
-            if (cell_index[k] < 0 || cell_index[k] >= ncells) throw std::string("polyhedral batch: cell_index[") + std::to_string(k) + "] is outside [0, ncells)";
-        B.cell_index = D.upload<int32_t>(cell_index, (size_t)N);
+        if ((!cell_index && !sg.bin_H) || !cell_weights || ncells <= 0) throw std::string("polyhedral batch: cell_index / cell_weights missing");
+        if (!sg.bin_H) {
+            for (long long k = 0; k < N; ++k)
+                if (cell_index[k] < 0 || cell_index[k] >= ncells) throw std::string("polyhedral batch: cell_index[") + std::to_string(k) + "] is outside [0, ncells)";
+            B.cell_index = D.upload<int32_t>(cell_index, (size_t)N);
+        }
         B.cell_weights = D.upload<double>(cell_weights, (size_t)ncells * P);
     }
     DevResults& R = D.A.R;
@@ -932,6 +960,18 @@ int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* 
         if (!Htoric || !Hcoeff) throw std::string("null homotopy handle");
         HomotopyH* h = merged_polyhedral((HomotopyH*)Htoric, (HomotopyH*)Hcoeff);
         return track_impl(h, o, MODE_POLYHEDRAL, N, starts, nullptr, nullptr, nullptr, nullptr, nullptr, cell_index, cell_weights, ncells, out);
+    } catch (const std::string& e) { return fail(e); }
+}
+
+int32_t hc_polyhedral_track_cells(void* Htoric, void* Hcoeff, const hc_options* o, int64_t first, int64_t N, int32_t ncells,
+                                  const int64_t* cell_volume, const int64_t* bin_H, const double* bin_mu, const double* bin_r,
+                                  const double* cell_weights, hc_results* out) {
+    try {
+        if (!Htoric || !Hcoeff) return fail("null homotopy handle");
+        if (!cell_volume || !bin_H || !bin_mu || !bin_r || !cell_weights || ncells <= 0) return fail("hc_polyhedral_track_cells: cell data missing");
+        HomotopyH* h = merged_polyhedral((HomotopyH*)Htoric, (HomotopyH*)Hcoeff);
+        StartGen sg; sg.td_first = first; sg.bin_volume = cell_volume; sg.bin_H = bin_H; sg.bin_mu = bin_mu; sg.bin_r = bin_r;
+        return track_impl(h, o, MODE_POLYHEDRAL, N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, cell_weights, ncells, out, sg);
     } catch (const std::string& e) { return fail(e); }
 }
 

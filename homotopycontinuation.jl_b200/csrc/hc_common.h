@@ -105,6 +105,14 @@ HC_HD double nthroot(double x, int N) {  // src/utils.jl:408-422
         default: return pow(x, 1.0 / N);
     }
 }
+// cos(pi x), sin(pi x): CUDA built-ins; the g++ build of the device code takes glibc's cos / sin of pi x (|x| <= 2 here)
+#if defined(__CUDACC__)
+HC_HD double hc_cospi(double x) { return ::cospi(x); }
+HC_HD double hc_sinpi(double x) { return ::sinpi(x); }
+#else
+inline double hc_cospi(double x) { return cos(3.141592653589793 * x); }
+inline double hc_sinpi(double x) { return sin(3.141592653589793 * x); }
+#endif
 HC_HD double eps_of(double x) {  // Julia eps(x): ulp of |x|
     x = fabs(x);
     if (!(x < HC_INF)) return HC_NAN;

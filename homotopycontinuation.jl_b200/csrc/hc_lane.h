@@ -67,8 +67,17 @@ struct BatchIn {
     long long td_first;
     cx t1, t0;
     const double* omega_mu;    // optional 2 x N
-    const int* cell_index;     // polyhedral: N
+    const int* cell_index;     // polyhedral: N (nullptr when the starts are made on the device: the cell follows from cell_first)
     const double* cell_weights;// polyhedral: ncells x P (unscaled s_ij, 0 on the cell's vertices)
+    // binomial start solutions made on the device (BinomialSystemSolver, src/binomial_system.jl:55-106, 238-261):
+    // per mixed cell the Hermite normal form H of its binomial system (n x n, row-major), the angles mu = U^T angle(b) / 2 pi
+    // (mod 1) and the moduli r = exp(A^-T log|b|); path k of the batch = solution (k_first + k) - cell_first[cell] of its cell
+    int ncells;
+    const long long* cell_first;  // ncells + 1 prefix sums of the cell volumes
+    const long long* bin_H;
+    const double* bin_mu;
+    const double* bin_r;
+    long long k_first;
 };
 
 template <int G, int S>
@@ -97,6 +106,7 @@ struct Lane : Path<G, S> {
     double logt2, logt1;
     // ---- polyhedral
     int toric_acc, toric_rej; double poly_maxw, saved_min_step;
+    int cell;  // mixed cell of the path
     // ---- flop accounting totals of finished stages
     int c_fact, c_ldiv;
 
@@ -493,6 +503,46 @@ struct Lane : Path<G, S> {
         req.kind = IK_EG; req.t1 = mk(t1); req.t0 = mk(0.0); req.omega = omega_; req.mu = mu_; req.tau = HC_INF; req.max_init = HC_INF;
         req.keep_steps = false; req.ext = false;
     }
+    // Start solution k of a polyhedral batch from its index (reference: PolyhedralStartSolutionsIterator +
+    // BinomialSystemSolver, src/polyhedral.jl:104-144, src/binomial_system.jl:55-106, 238-261): the cell by binary search
+    // in the volume prefix sums, the unit-root combination from the mixed-radix digits of the local index
+    // (fill_unit_roots_combinations!: first coordinate slowest), the angles by the triangular solve over H in
+    // double-double arithmetic reduced mod 2 as the reference does, x_j = r_j cis(2 pi alpha_j).
+    HC_HDN void binomial_start(long long k, const BatchIn& Bt) {
+        HC_COLD_N
+        const int nn = n;
+        const long long kk = (Bt.k_first + k) % Bt.cell_first[Bt.ncells];  // indices beyond the mixed volume wrap (replicated batches)
+        int lo = 0, hi = Bt.ncells;
+        while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (Bt.cell_first[mid] <= kk) lo = mid; else hi = mid; }
+        cell = lo;
+        long long c = kk - Bt.cell_first[lo];
+        const long long* Hm = Bt.bin_H + (size_t)lo * nn * nn;
+        const double* mu = Bt.bin_mu + (size_t)lo * nn;
+        const double* rr = Bt.bin_r + (size_t)lo * nn;
+        // alpha_j lives in M.work[j] as a double-double (re = hi, im = lo); every lane of a group computes all of them
+        long long tail = 1;  // product of the diagonal entries behind j
+        for (int j = nn - 1; j >= 0; --j) {
+            const long long dj = Hm[j * nn + j];
+            const long long root = (c / tail) % dj;
+            tail *= dj;
+            dd a = (mkdd(mu[j]) + mkdd((double)root)) / mkdd((double)dj);
+            a = a - mkdd(2.0 * rint(0.5 * a.hi));
+            for (int q = nn - 1; q > j; --q) {
+                const cx w = M.work[q];
+                dd ak = (mkdd(w.re, w.im) * (double)Hm[q * nn + j]) / mkdd((double)dj);
+                ak = ak - mkdd(2.0 * rint(0.5 * ak.hi));
+                a = a - ak;
+            }
+            a = a - mkdd(2.0 * rint(0.5 * a.hi));  // rem(alpha, 2, RoundNearest)
+            g.sync();
+            if (g.lane == 0) M.work[j] = mk(a.hi, a.lo);
+            g.sync();
+        }
+        HC_PAR(j, nn) {
+            const double a = ((cx)M.work[j]).re;
+            M.x[j] = mk(rr[j] * hc_cospi(2.0 * a), rr[j] * hc_sinpi(2.0 * a));
+        }
+    }
     // a new path: load the start, reset the per-path state, request the first tracker initialisation
     HC_HDN void start_pre(long long k, const BatchIn& Bt) {
         HC_COLD_N
@@ -510,10 +560,12 @@ struct Lane : Path<G, S> {
                 if (i % G == g.lane) M.x[i] = Bt.td_roots[off + j];
                 off += d;
             }
-        } else {
+        } else if (Bt.bin_H) binomial_start(k, Bt);
+        else {
             const long long row = Bt.start_mod > 0 ? k % Bt.start_mod : k;
             HC_PAR(i, nn) M.x[i] = Bt.starts[row * nn + i];
         }
+        if (Bt.mode == MODE_POLYHEDRAL && !Bt.bin_H) cell = Bt.cell_index[k];
         g.sync();
         refined_extended_prec = false; factorized = scaled = false; B::a_in_lu = B::rs_raw = false; stop_pending = false;
         min_step_size = O->min_step_size; min_rel_step_size = O->min_rel_step_size;
@@ -536,7 +588,7 @@ struct Lane : Path<G, S> {
         } else {  // polyhedral.jl:414-465
             kind = H_TORIC;
             double smin, smax;
-            const double* raw = Bt.cell_weights + (size_t)Bt.cell_index[k] * H->P;
+            const double* raw = Bt.cell_weights + (size_t)cell * H->P;
             set_weights(raw, true, 1.0, smin, smax);
             poly_maxw = smax;
             double tend = smax < 10 ? 1.0 : clampd(pow(0.1, 10 / smax), 0.9, 1 - 1e-6);
@@ -549,7 +601,7 @@ struct Lane : Path<G, S> {
     HC_HDN void toric_pre(const BatchIn& Bt) {
         if (phase == PH_TORIC_A && poly_maxw >= 10 && code == TC_success) {
             double smin, smax;
-            const double* raw = Bt.cell_weights + (size_t)Bt.cell_index[pidx] * H->P;
+            const double* raw = Bt.cell_weights + (size_t)cell * H->P;
             double t0 = st_target.re;
             set_weights(raw, false, 10.0, smin, smax);
             double t_restart = pow(t0, 1 / smin);

@@ -213,7 +213,8 @@ def solve_binomial_system(A, b) -> np.ndarray:
     # angular part: x = e^{2 pi i alpha};  A^T alpha = gamma (mod 1)  <=>  H^T (U^-1 alpha) ... solve with
     # y = U^T-transformed angles exactly in rationals: (A U)^T alpha = U^T gamma (mod 1)
     gamma = [Fraction(float(np.angle(z)) / (2 * np.pi)) for z in b]
-    mu = [sum(int(U[i][j]) * gamma[i] for i in range(n)) % 1 for j in range(n)]
+    mu = [sum(int(U[i][j]) * gamma[i] for i in range(n)) for j in range(n)]
+    mu = [m - 2 * round(m / 2) for m in mu]   # rem(mu, 2, RoundNearest) as the reference (:88): fixes the order inside a cell
     X = np.empty((n, dhat), dtype=np.complex128)
     # unit-root combinations in the reference's order (fill_unit_roots_combinations!, :55-70)
     table = np.zeros((n, dhat), dtype=np.int64)
@@ -232,7 +233,9 @@ def solve_binomial_system(A, b) -> np.ndarray:
             s = mu[j] + int(table[j, c])
             for k in range(j + 1, n):
                 s -= int(H[k][j]) * alpha[k]
-            alpha[j] = (s / diag[j]) % 1
+            a = s / diag[j]
+            alpha[j] = a - 2 * round(a / 2)   # the reference keeps alpha in [-1, 1] (rem(alpha, 2, RoundNearest), :101);
+            # the representative matters: alpha_k enters alpha_j through H[k, j] / H[j, j], so it fixes the order inside a cell
         for j in range(n):
             a = float(alpha[j])
             X[j, c] = complex(np.cos(2 * np.pi * a), np.sin(2 * np.pi * a))
@@ -271,6 +274,33 @@ class PolyhedralStart:
             xs.append(X.T)
             ci += [k] * cell.volume
         return np.concatenate(xs, axis=0), np.array(ci, dtype=np.int32)
+
+    def binomial_systems(self):
+        """(A, b) of every mixed cell: columns of A = support differences, b_i = -c_i[b] / c_i[a] (binomial_system.jl:45-53)."""
+        for cell in self.cells:
+            A = np.stack([self.support[i][:, a] - self.support[i][:, b] for i, (a, b) in enumerate(cell.indices)], axis=1)
+            bb = np.array([-self.start_coeffs[self.offsets[i] + b] / self.start_coeffs[self.offsets[i] + a]
+                           for i, (a, b) in enumerate(cell.indices)])
+            yield A, bb
+
+    def binomial_data(self) -> dict:
+        """Per-cell inputs of hc_polyhedral_track_cells (start solutions made on the device): volume, Hermite normal
+        form H (A U = H), mu = rem(U^T angle(b) / 2 pi, 2) and r = exp(A^-T log|b|) -- the host half of
+        BinomialSystemSolver (hnf!, the coordinate change of compute_angular_part!, the modulus solve of solve!,
+        src/binomial_system.jl:72-90, 238-261); the device does the d^ triangular solves."""
+        vol, Hs, mus, rs = [], [], [], []
+        for (A, bb), cell in zip(self.binomial_systems(), self.cells):
+            H, U = hnf(A)
+            n = A.shape[0]
+            gamma = [Fraction(float(np.angle(z)) / (2 * np.pi)) for z in bb]
+            mu = []
+            for j in range(n):
+                m = sum(int(U[i][j]) * gamma[i] for i in range(n))
+                m -= 2 * round(m / 2)   # rem(mu, 2, RoundNearest)
+                mu.append(float(m))
+            vol.append(int(cell.volume)); Hs.append(np.array(H.tolist(), dtype=np.int64)); mus.append(mu)
+            rs.append(np.exp(np.linalg.solve(A.T.astype(float), np.log(np.abs(bb)))))
+        return {"volume": np.array(vol, dtype=np.int64), "H": np.array(Hs, dtype=np.int64), "mu": np.array(mus), "r": np.array(rs)}
 
     def cell_weights(self) -> np.ndarray:
         """ncells x P raw weights s_ij (0 on each cell's two vertices), toric_homotopy.jl:76-97."""

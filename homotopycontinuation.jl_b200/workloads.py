@@ -32,6 +32,10 @@ class Workload:
     # `path_q` above are their per-path replication (path j * k + s = start s to point j)
     sweep_starts: np.ndarray | None = None
     sweep_q: np.ndarray | None = None
+    # polyhedral batches: per-cell binomial data (PolyhedralStart.binomial_data()) -- libhc_b200 makes the start solutions
+    # on the device from it (hc_polyhedral_track_cells); path k = start solution cells_first + k (mod mixed volume)
+    cells: dict | None = None
+    cells_first: int = 0
 
     @property
     def N(self):
@@ -42,6 +46,7 @@ class Workload:
         w = Workload(self.name, self.description, self.n, self.starts[:count], self.mode, self.build,
                      None if self.path_q is None else self.path_q[:count],
                      None if self.cell_index is None else self.cell_index[:count], self.cell_weights, self.costs, {})
+        w.cells, w.cells_first = self.cells, self.cells_first
         return w
 
     def slice(self, lo: int, hi: int) -> "Workload":
@@ -49,6 +54,7 @@ class Workload:
         w = Workload(self.name, self.description, self.n, self.starts[lo:hi], self.mode, self.build,
                      None if self.path_q is None else self.path_q[lo:hi],
                      None if self.cell_index is None else self.cell_index[lo:hi], self.cell_weights, self.costs, {})
+        w.cells, w.cells_first = self.cells, self.cells_first + lo
         if self.sweep_starts is not None:
             k = len(self.sweep_starts)
             if lo % k == 0 and hi % k == 0:   # the shard holds whole parameter points
@@ -58,6 +64,9 @@ class Workload:
     def track(self, api, handles, options=None, nthreads=1, out=None):
         if self.sweep_starts is not None and getattr(api, "_track_sweep", None) is not None:
             return capi.track_sweep(handles["H"], self.sweep_starts, self.sweep_q, options, out=out)
+        if self.mode == 2 and self.cells is not None and getattr(api, "_polyhedral_track_cells", None) is not None:
+            return capi.polyhedral_track_cells(api, handles["H"], handles["Hcoeff"], self.cells, self.cell_weights,
+                                               self.cells_first, self.N, options, out=out)
         if self.mode == 2:
             return capi.polyhedral_track_batch(api, handles["H"], handles["Hcoeff"], self.starts, self.cell_index,
                                                self.cell_weights, options, nthreads, out=out)
@@ -104,7 +113,7 @@ def cyclic_polyhedral(n: int = 7, replicas: int = 1) -> Workload:
                 "Hcoeff": api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)}
     return Workload(f"cyclic{n}_polyhedral", f"cyclic-{n} polyhedral homotopy, {len(S)} mixed-volume paths x {replicas} replicas", n,
                     np.tile(S, (replicas, 1)), 2, build, cell_index=np.tile(ci, replicas), cell_weights=cw,
-                    costs=flops.homotopy_costs(ps.F), expected={"success": len(S) * replicas})
+                    costs=flops.homotopy_costs(ps.F), expected={"success": len(S) * replicas}, cells=ps.binomial_data())
 
 
 def tritangents_total_degree(limit: int | None = None) -> Workload:
@@ -159,7 +168,8 @@ def cyclooctane_polyhedral() -> Workload:
         return {"H": api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs),
                 "Hcoeff": api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)}
     return Workload("cyclooctane_polyhedral", f"cyclooctane polyhedral homotopy, {len(S)} mixed-volume paths", 17, S, 2, build,
-                    cell_index=ci, cell_weights=cw, costs=flops.homotopy_costs(ps.F), expected={"success": 1408})
+                    cell_index=ci, cell_weights=cw, costs=flops.homotopy_costs(ps.F), expected={"success": 1408},
+                    cells=ps.binomial_data())
 
 
 def biochem_generic_start(api, seed: int = 5):

@@ -15,6 +15,8 @@
  *                               many_solve (src/solve.jl:815-881) inverted to (parameter point x start)
  *                    mode 1     track(::Tracker, x, t1, t0)                     (src/tracker.jl:1023-1026)
  *   hc_polyhedral_track_batch   track(::PolyhedralTracker, (cell, x))           (src/polyhedral.jl:414-530)
+ *   hc_polyhedral_track_cells   the same with the start solutions of every mixed cell made on the device
+ *                               (PolyhedralStartSolutionsIterator, src/polyhedral.jl:104-144; src/binomial_system.jl:55-106)
  *   hc_evaluate, hc_evaluate_dd, hc_evaluate_and_jacobian, hc_taylor
  *                               the operator API evaluate!/evaluate_and_jacobian!/taylor!
  *                               (src/model_kit/abstract_system_homotopy.jl:96-120), single point test hooks
@@ -147,6 +149,18 @@ int32_t hc_polyhedral_track_batch(void* Htoric, void* Hcoeff, const hc_options* 
  * collect(starts), src/solve.jl:543).  `first` lets every GPU take an index range without a start matrix. */
 int32_t hc_track_total_degree(void* H, const hc_options* o, const int32_t* degrees, int64_t first, int64_t N,
                               hc_results* out);
+/* Polyhedral start solutions produced on the device (second half): only per-CELL data crosses
+ * the bus.  Replaces PolyhedralStartSolutionsIterator + BinomialSystemSolver.X (reference src/polyhedral.jl:104-144,
+ * src/binomial_system.jl:55-106, 238-261): the host keeps hnf! and the two n x n solves per cell and sends, per mixed
+ * cell c, its volume, the Hermite normal form H_c (n x n int64, row-major, lower triangular: A U = H), the transformed
+ * angles mu_c = rem(U^T angle(b) / 2 pi, 2) and the moduli r_c = exp(A^-T log|b|) (both n doubles).  Path k of the call
+ * is start solution (first + k) mod (sum of the volumes) in the iterator's order: cells in order, inside a cell the
+ * unit-root combinations of fill_unit_roots_combinations! (first coordinate slowest); the device solves the triangular
+ * system for the angles in double-double arithmetic as compute_angular_part! does and sets x_j = r_j cis(2 pi alpha_j).
+ * cell_weights: ncells x P as in hc_polyhedral_track_batch. */
+int32_t hc_polyhedral_track_cells(void* Htoric, void* Hcoeff, const hc_options* o, int64_t first, int64_t N, int32_t ncells,
+                                  const int64_t* cell_volume, const int64_t* bin_H, const double* bin_mu, const double* bin_r,
+                                  const double* cell_weights, hc_results* out);
 /* Many-parameter solve (reference many_solve, src/solve.jl:815-881: the same S start solutions tracked to each
  * of M target parameter vectors): starts is n x S, target_params P x M (column per point).  Path j * S + s =
  * start s to parameter point j; `out` holds S * M paths in that order.  Only the S starts and one parameter

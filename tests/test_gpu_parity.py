@@ -205,6 +205,34 @@ def test_cyclic7_polyhedral_config2(oracle, gpu):  # BASELINE.json configs[1]: 9
     assert rg.residual.max() < 1e-10
 
 
+@pytest.mark.parametrize("engine", ["auto", "group"])
+def test_polyhedral_starts_made_on_the_device(oracle, gpu, monkeypatch, engine):
+    """hc_polyhedral_track_cells (second half): only per-cell data (Hermite normal form, angles, moduli)
+    crosses the bus, a lane makes its start solution from its path index (BinomialSystemSolver, reference
+    src/binomial_system.jl:55-106, 238-261).  Same results as the oracle's run from the host-made start solutions, same
+    results as the explicit-start call, an index range gives the slice, and the upload no longer grows with N."""
+    from hcb200 import workloads
+    if engine == "group":
+        monkeypatch.setenv("HC_B200_ENGINE", "group")
+    w = workloads.cyclic_polyhedral(7 if engine == "auto" else 5)
+    assert w.cells is not None and int(w.cells["volume"].sum()) == w.N
+    ro = w.track(oracle, w.build(oracle), nthreads=8)            # explicit starts (the oracle has no start generator)
+    h = w.build(gpu)
+    rg = w.track(gpu, h)                                         # hc_polyhedral_track_cells
+    cells_bytes = lib.timing().h2d_bytes
+    assert_batches_match(ro, rg)
+    rx = capi.polyhedral_track_batch(gpu, h["H"], h["Hcoeff"], w.starts, w.cell_index, w.cell_weights)
+    assert lib.timing().h2d_bytes - cells_bytes >= 16 * w.n * w.N - 8 * (w.n * w.n + 2 * w.n + 2) * len(w.cells["volume"])
+    assert (rx.return_code == rg.return_code).all()
+    assert np.abs(rx.solution - rg.solution).max() <= 1e-10 * np.abs(rx.solution).max()
+    lo, hi = w.N // 3, w.N // 3 + w.N // 2
+    part = w.slice(lo, hi).track(gpu, h)
+    assert np.array_equal(part.solution, rg.solution[lo:hi]) and (part.return_code == rg.return_code[lo:hi]).all()
+    # replicated batch: indices beyond the mixed volume wrap
+    big = capi.polyhedral_track_cells(gpu, h["H"], h["Hcoeff"], w.cells, w.cell_weights, first=0, count=2 * w.N + 3)
+    assert np.array_equal(big.solution[w.N:2 * w.N], rg.solution) and np.array_equal(big.solution[2 * w.N:], rg.solution[:3])
+
+
 @pytest.mark.parametrize("k", [1, 2, 3, 5, 7, 9, 10, 11, 12, 15])
 def test_system_sizes(oracle, gpu, k):
     """n = k + 1: every register-blocked LU instantiation class (n <= 12), the generic LU of the

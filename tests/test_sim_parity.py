@@ -142,6 +142,39 @@ def test_polyhedral_cyclic5(oracle, sim):
     assert len(np.unique(np.round(res[1].solution, 6), axis=0)) == 70
 
 
+def test_polyhedral_starts_made_on_the_device(oracle, sim):
+    """hc_polyhedral_track_cells: the start solutions of every mixed cell are made from per-cell data
+    (H, mu, r) by the device code -- BinomialSystemSolver's unit-root combinations and double-double triangular solve,
+    reference src/binomial_system.jl:55-106.  They solve their binomial systems (test/binomial_system_test.jl:107-120
+    checks residuals the same way) and the tracked batch equals the oracle's run from the host-made start solutions;
+    an index range (first, count) gives the slice, indices beyond the mixed volume wrap."""
+    from hcb200 import polyhedral as ph
+    for F in (systems.cyclic(5), systems.katsura(4)):
+        ps = ph.polyhedral(F)
+        S, ci = ps.start_solutions()
+        cw, cells = ps.cell_weights(), ps.binomial_data()
+        assert int(cells["volume"].sum()) == len(S)
+        def handles(api):
+            h = api.system(ps.F)
+            return (api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs),
+                    api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs))
+        ref = capi.polyhedral_track_batch(oracle, *handles(oracle), S, ci, cw)
+        Ht, Hc = handles(sim)
+        dev = capi.polyhedral_track_cells(sim, Ht, Hc, cells, cw)
+        assert_batches_match(ref, dev)
+        # against the same code started from the host-made solutions: the starts agree to rounding, so do the step counts
+        host = capi.polyhedral_track_batch(sim, Ht, Hc, S, ci, cw)
+        assert (host.return_code == dev.return_code).all()
+        assert np.abs(host.accepted_steps - dev.accepted_steps).max() <= 3
+        assert np.abs(host.solution - dev.solution).max() <= 1e-12 * np.abs(host.solution).max()
+        lo, cnt = len(S) // 3, len(S) // 2
+        part = capi.polyhedral_track_cells(sim, Ht, Hc, cells, cw, first=lo, count=cnt)
+        assert (part.return_code == dev.return_code[lo:lo + cnt]).all()
+        assert np.array_equal(part.solution, dev.solution[lo:lo + cnt])
+        wrap = capi.polyhedral_track_cells(sim, Ht, Hc, cells, cw, first=len(S) - 2, count=5)
+        assert np.array_equal(wrap.solution[2:], dev.solution[:3])
+
+
 @pytest.mark.parametrize("k", [1, 2, 4, 6, 10, 11, 12])
 def test_system_sizes(oracle, sim, k):
     """n = k + 1 = 2 .. 13: the register-blocked LU / solve instantiations (n <= 12) and the generic
