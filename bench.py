@@ -141,7 +141,7 @@ class Arm:
         self.handles = w.build(api)
 
     def resident(self, steps, warmup, barrier=lambda: None):
-        from hcb200 import capi
+        from hcb200 import capi, lib
         w, raw = self.w, self.raw
         dp = lambda a: a.ctypes.data_as(capi.c_double_p)
         starts = np.ascontiguousarray(w.starts)
@@ -150,10 +150,20 @@ class Arm:
         ci = np.ascontiguousarray(w.cell_index, dtype=np.int32) if w.cell_index is not None else None
         cw = np.ascontiguousarray(w.cell_weights, dtype=np.float64) if w.cell_weights is not None else None
         h = self.handles
-        res_h = raw.hc_resident_create(h["H"].handle, h["Hcoeff"].handle if "Hcoeff" in h else None, C.byref(self.opts), w.mode,
-                                       w.N, dp(starts.view(np.float64)), dp(t1), dp(t0), None, dp(pq) if pq is not None else None,
-                                       ci.ctypes.data_as(capi.c_int32_p) if ci is not None else None, dp(cw) if cw is not None else None,
-                                       cw.shape[0] if cw is not None else 0)
+        if w.mode == 2 and w.cells is not None:   # polyhedral start solutions made on the device, as the e2e arm's call does
+            i64 = lambda a: a.ctypes.data_as(capi.c_int64_p)
+            vol, Hm = np.ascontiguousarray(w.cells["volume"], dtype=np.int64), np.ascontiguousarray(w.cells["H"], dtype=np.int64)
+            mu, rr = np.ascontiguousarray(w.cells["mu"], dtype=np.float64), np.ascontiguousarray(w.cells["r"], dtype=np.float64)
+            raw.hc_resident_create_cells.restype = C.c_void_p
+            raw.hc_resident_create_cells.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(capi.Options), C.c_int64, C.c_int64, C.c_int32,
+                                                     capi.c_int64_p, capi.c_int64_p, capi.c_double_p, capi.c_double_p, capi.c_double_p]
+            res_h = raw.hc_resident_create_cells(h["H"].handle, h["Hcoeff"].handle, C.byref(self.opts), w.cells_first, w.N, len(vol),
+                                                 i64(vol), i64(Hm), dp(mu), dp(rr), dp(cw))
+        else:
+            res_h = raw.hc_resident_create(h["H"].handle, h["Hcoeff"].handle if "Hcoeff" in h else None, C.byref(self.opts), w.mode,
+                                           w.N, dp(starts.view(np.float64)), dp(t1), dp(t0), None, dp(pq) if pq is not None else None,
+                                           ci.ctypes.data_as(capi.c_int32_p) if ci is not None else None, dp(cw) if cw is not None else None,
+                                           cw.shape[0] if cw is not None else 0)
         if not res_h:
             raise SystemExit("hc_resident_create failed: " + raw.hc_last_error().decode())
         res_h = C.c_void_p(res_h)
@@ -163,9 +173,11 @@ class Arm:
         barrier()
         kernel_ms = []
         tw0 = time.perf_counter()
+        self.launches = 0
         for _ in range(steps):
             assert raw.hc_resident_run(res_h, C.byref(ms)) == 0, raw.hc_last_error()
             kernel_ms.append(ms.value)
+            self.launches += 1 + (lib.timing().handoff_paths > 0)   # a two-pass batch launches the lane-group kernel as well
         barrier()
         wall = time.perf_counter() - tw0
         res = capi.BatchResults.allocate(w.n, w.N)
@@ -336,6 +348,9 @@ def main():
                              "unit": "paths/s", "engine": ENGINES.get(tm2.engine, str(tm2.engine)), "grid": tm2.grid, "block": tm2.block,
                              "class_counts": result.statistics(rc).asdict(), "expected": wc.expected,
                              "roofline_frac": roofline_of(wc, rc, kms, peak_gflops, name, tm2.engine)["frac"]}
+                    if tm2.handoff_paths:
+                        entry["second_pass"] = {"paths": int(tm2.handoff_paths), "ms": round(tm2.handoff_ms, 1),
+                                                "engine": "lane group per path (interpreter): paths beyond 120 endgame steps or in extended precision, tracked again from their starts"}
                     if not args.no_cpu_baseline:
                         budget = {"katsura8": 65536, "tritangents": 16384, "cyclooctane_td": 8192, "cyclooctane_polyhedral": 4096, "biochem_sweep": 524288}[name]
                         v, sample, rcpu, dtc = cpu_arm(wc, budget, os.cpu_count() or 1)
@@ -382,10 +397,10 @@ def main():
         "e2e": {"value": e2e, "unit": "paths/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(tm.d2h_bytes),
                 "last_call_ms": {"setup_h2d_launch": round(tm.h2d_ms, 2), "kernel": round(tm.kernel_ms, 2), "d2h": round(tm.d2h_ms, 2),
                                  "whole_step_mean": round(1e3 * e2e_dt_max / args.steps, 2)},
-                "entry_point": "hc_track_sweep" if w.sweep_starts is not None else ("hc_polyhedral_track_batch" if w.mode == 2 else "hc_track_batch"),
+                "entry_point": "hc_track_sweep" if w.sweep_starts is not None else (("hc_polyhedral_track_cells" if w.cells is not None else "hc_polyhedral_track_batch") if w.mode == 2 else "hc_track_batch"),
                 "host_buffers": pin_note,
                 "results_identical_to_resident_arm": e2e_same},
-        "gpu_launches": args.steps,
+        "gpu_launches": arm.launches,
         "clocks": clocks,
         "roofline": roofline_of(w, res, kernel_ms, peak_gflops, args.workload, tm.engine),
         "wall_s_timed_region": wall_max,

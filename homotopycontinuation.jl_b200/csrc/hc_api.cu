@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -120,11 +121,15 @@ struct ProgramH {
     DevProgram dev;                // the copy on slot 0 (its sizes are the same on every device)
     std::vector<DevProgram> devs;  // pointers into the memory of each device of the process
     LoweredProgram low;
+    bool tpp = false;   // segment-scheduled (thread-per-path engines) rather than level-scheduled (lane groups)
     jit::ProgCopy ref;  // the reference tape as handed over (input of the code generator, hc_jitgen.h)
     Owned owned;
 };
 struct SystemH {
     ProgramH eval, jac;
+    // level-scheduled copies for the lane-group engine of a system whose programs were segment-scheduled for the
+    // thread-per-path engines (n <= 14): built on first use by the second pass of a two-pass batch (group_programs)
+    std::unique_ptr<ProgramH> eval_g, jac_g;
     int m = 0, n = 0, P = 0;
 };
 struct HomotopyH {
@@ -149,13 +154,15 @@ int group_size_for(int n) {
 int engine_for(int n);
 
 // Lower the reference's 24-byte, 1-based Instruction stream (hc_lower.h) and upload it.
-void build_program(ProgramH& H, const hc_program_desc* d, bool is_jac) {
+void build_program(ProgramH& H, const hc_program_desc* d, bool is_jac, bool force_group = false) {
     H.ref.assign(d);
 #ifdef HC_HOST_SIM
     const bool tpp = true;
+    (void)force_group;
 #else
-    const bool tpp = engine_for(d->n_vars) != 0;
+    const bool tpp = !force_group && engine_for(d->n_vars) != 0;
 #endif
+    H.tpp = tpp;
     // thread per path: segment scheduling (window of tape-order ops) feeds the segment loops of hc_tape.h;
     // lane groups: rounds of at most `cap` independent ops
     const int cap = tpp ? 0 : env_int("HC_B200_ROUND_CAP", 2 * group_size_for(d->n_vars));
@@ -275,7 +282,7 @@ bool jit_wanted(const HomotopyH& H, long long N, bool complex_t = false) {
     if (complex_t && H.dev.kind != H_STRAIGHT_LINE) return false;  // the generated parameter code assumes real t
     const char* e = getenv("HC_B200_JIT");
     if (e && !strcmp(e, "0")) return false;
-    if (H.dev.n > env_int("HC_B200_JIT_MAX_N", 14)) return false;  // beyond the register-blocked LU the lane-group engine wins (measured: cyclooctane, n = 17)
+    if (H.dev.n > env_int("HC_B200_JIT_MAX_N", 20)) return false;  // the register-blocked LU of the specialised kernels goes up to n = 20
     if (e && !strcmp(e, "1")) return true;
 #ifdef HC_HOST_SIM
     return false;
@@ -456,6 +463,9 @@ struct DeviceBatch {  // device-resident inputs and outputs of one batch
     long long first = 0;   // index of its first path in the caller's arrays
     std::vector<void*> owned;
     int64_t h2d_bytes = 0;
+    // two-pass batches: paths the thread-per-path pass handed over are tracked again by the lane-group engine
+    long long handoff_paths = 0; double handoff_ms = 0;
+    unsigned char* cold2 = nullptr; size_t cold2_bytes = 0; long long* map2 = nullptr; size_t map2_count = 0;
 #ifndef HC_HOST_SIM
     cudaEvent_t e0 = nullptr, e1 = nullptr;
 #endif
@@ -578,6 +588,17 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     D.A.stage_bytes = (int)pl.stage_bytes;
     if (pl.engine == 2) { D.A.H.tape_cx = pl.jit_tape_cx; D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8); }
     D.A.sync_cta = env_int("HC_B200_SYNC_CTA", 0);
+#ifndef HC_HOST_SIM
+    // Two-pass batch: the specialised thread-per-path kernel gives up paths beyond HC_B200_HANDOFF_EG_STEPS endgame steps
+    // (typical paths need 10 - 80; the 99th percentile of the heavy-tailed configs is 210 - 230), beyond
+    // HC_B200_HANDOFF_STEPS steps in total, or in extended precision; finish_batch tracks them again on the lane-group
+    // engine (second_pass).
+    if (pl.engine == 2 && mode != MODE_TRACKER && env_int("HC_B200_HANDOFF", 1)) {
+        B.handoff_steps = env_int("HC_B200_HANDOFF_STEPS", 1000);
+        B.handoff_eg_steps = env_int("HC_B200_HANDOFF_EG_STEPS", 120);
+        B.handoff_ext = env_int("HC_B200_HANDOFF_EXT", 1);
+    }
+#endif
 }
 
 #ifndef HC_HOST_SIM
@@ -655,12 +676,116 @@ void launch_batch(DeviceBatch& D) {
     CK(cudaGetLastError());
 #endif
 }
+#ifndef HC_HOST_SIM
+hc_program_desc desc_of(const jit::ProgCopy& r) {
+    hc_program_desc d;
+    d.instructions = r.instr.data(); d.n_instructions = (int32_t)(r.instr.size() / 6);
+    d.constants = r.consts.data(); d.n_constants = (int32_t)(r.consts.size() / 2);
+    d.param_offset = r.param_offset; d.n_params = r.n_params; d.t_index = r.t_index; d.var_offset = r.var_offset; d.n_vars = r.n_vars;
+    d.u_assign = r.u_assign.data(); d.n_u = (int32_t)(r.u_assign.size() / 2);
+    d.U_assign = r.U_assign.data(); d.n_U = (int32_t)(r.U_assign.size() / 2);
+    d.out_dim = r.out_dim; d.tape_space = r.tape_space;
+    return d;
+}
+// the programs of a system as the lane-group engine wants them (level-scheduled)
+void group_programs(SystemH& S, ProgramH*& e, ProgramH*& j) {
+    if (!S.eval.tpp) { e = &S.eval; j = &S.jac; return; }
+    if (!S.eval_g) {
+        const int keep = g_cur;
+        std::unique_ptr<ProgramH> pe(new ProgramH()), pj(new ProgramH());
+        const jit::ProgCopy re = S.eval.ref, rj = S.jac.ref;  // (build_program re-assigns ref from the descriptor)
+        hc_program_desc de = desc_of(re), dj = desc_of(rj);
+        build_program(*pe, &de, false, true);
+        build_program(*pj, &dj, true, true);
+        S.eval_g = std::move(pe); S.jac_g = std::move(pj);
+        use_slot(keep);
+    }
+    e = S.eval_g.get(); j = S.jac_g.get();
+}
+
+// Second pass of a two-pass batch: the paths the thread-per-path kernel gave up (return_code == RC_HANDOFF) are tracked
+// again, from their start solutions, by the lane-group engine -- a group of lanes walks one long path several times
+// faster than a single lane, and nothing waits for it.  Results land at the paths' own indices.  Returns milliseconds.
+double second_pass(DeviceBatch& D) {
+    const long long N = D.N;
+    std::vector<int> rc((size_t)N);
+    d2h(rc.data(), D.A.R.return_code, (size_t)N * 4);
+    dev_sync();
+    std::vector<long long> idx;
+    for (long long k = 0; k < N; ++k) if (rc[(size_t)k] == RC_HANDOFF) idx.push_back(k);
+    D.handoff_paths = (long long)idx.size();
+    if (idx.empty()) return 0.0;
+    HomotopyH& H = *D.H;
+    KArgs A2 = D.A;
+    ProgramH *Fe, *Fj, *Ge = nullptr, *Gj = nullptr;
+    group_programs(*H.F, Fe, Fj);
+    if (H.dev.kind == H_STRAIGHT_LINE) group_programs(*H.G, Ge, Gj);
+    use_slot(D.slot);
+    A2.H.Fe = Fe->devs[(size_t)D.slot]; A2.H.Fj = Fj->devs[(size_t)D.slot];
+    int W = Fj->dev.W, We = Fe->dev.W;
+    if (Ge) { A2.H.Ge = Ge->devs[(size_t)D.slot]; A2.H.Gj = Gj->devs[(size_t)D.slot]; W = std::max(W, Gj->dev.W); We = std::max(We, Ge->dev.W); }
+    A2.H.tape_cx = std::max(W, 4 * We);
+    // launch shape: as make_plan's lane-group branch
+    PathMem<0> dummy;
+    const SlabSizes ss = carve(dummy, H.dev.n, H.dev.P, A2.H.tape_cx, nullptr, nullptr);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t stage_bytes = program_stage_bytes(*Fe, false) + program_stage_bytes(*Fj, false) + (Ge ? program_stage_bytes(*Ge, false) + program_stage_bytes(*Gj, false) : 0) +
+                         2 * 16 * (size_t)std::max(1, std::max(H.dev.P, H.G ? H.G->P : 0));
+    int stage = stage_bytes <= (size_t)env_int("HC_B200_STAGE_MAX", 96 * 1024) && env_int("HC_B200_STAGE", 1);
+    if (!stage || stage_bytes + ss.hot > kSmemMax) { stage = 0; stage_bytes = 0; }
+    if (ss.hot > kSmemMax) throw std::string("system too large for the lane-group engine");
+    const long long N2 = (long long)idx.size();
+    // few paths: wide groups (latency of the single path decides); many: narrow groups (throughput)
+    int G = env_int("HC_B200_HANDOFF_GROUP", 0);
+    if (G != 8 && G != 32) G = N2 * 32 <= (long long)sms * 512 ? 32 : 8;
+    int block = 256;
+    const long long small = (N2 * G + sms - 1) / sms;
+    while (block > 32 && block / 2 >= small) block /= 2;
+    if (block < G) block = G;
+    while (block > G && stage_bytes + (size_t)(block / G) * ss.hot > kSmemMax) block -= 32;
+    const int ppb = block / G;
+    const size_t smem = stage_bytes + (size_t)ppb * ss.hot;
+    int per_sm = (int)((228 * 1024) / (smem + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * block > 512) per_sm = 512 / block;
+    const long long want = (N2 + ppb - 1) / ppb, cap = (long long)sms * per_sm;
+    const int grid = (int)std::max(1LL, std::min(want, cap));
+    const size_t cold_need = (size_t)grid * ppb * ss.cold;
+    if (cold_need > D.cold2_bytes) { D.cold2 = D.alloc<unsigned char>(cold_need); D.cold2_bytes = cold_need; }
+    if (idx.size() > D.map2_count) { D.map2 = D.alloc<long long>(idx.size()); D.map2_count = idx.size(); }
+    h2d(D.map2, idx.data(), idx.size() * sizeof(long long));
+    A2.B.N = N2; A2.B.index_map = D.map2; A2.B.handoff_steps = 0; A2.B.handoff_eg_steps = 0; A2.B.handoff_ext = 0;
+    A2.stage = stage; A2.stage_bytes = (int)stage_bytes; A2.slab_bytes = (int)ss.hot; A2.cold_bytes = (int)ss.cold; A2.cold = D.cold2;
+    dev_zero(A2.queue, sizeof(unsigned long long));
+    const void* kern = hc_kernel_group(G);
+    if (first_use(kern)) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+    cudaEvent_t f0, f1;
+    CK(cudaEventCreate(&f0)); CK(cudaEventCreate(&f1));
+    CK(cudaEventRecord(f0, cur_stream()));
+    void* args[] = {(void*)&A2};
+    cudaError_t le = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)block), args, smem, cur_stream());
+    cudaEventRecord(f1, cur_stream());
+    cudaError_t se = cudaEventSynchronize(f1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, f0, f1);
+    cudaEventDestroy(f0); cudaEventDestroy(f1);
+    CK(le); CK(se);
+    if (env_int("HC_B200_VERBOSE", 0) >= 1)
+        fprintf(stderr, "[hc_b200] second pass: %lld of %lld paths on the lane-group engine (G = %d, grid %d x %d): %.1f ms\n", N2, N, G, grid, block, (double)ms);
+    return ms;
+}
+#endif
+
 double finish_batch(DeviceBatch& D) {
     use_slot(D.slot);
 #ifndef HC_HOST_SIM
     CK(cudaEventSynchronize(D.e1));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, D.e0, D.e1));
+    D.handoff_paths = 0; D.handoff_ms = 0;
+    if (D.A.B.handoff_steps > 0) { D.handoff_ms = second_pass(D); ms += (float)D.handoff_ms; }
     return ms;
 #else
     if (D.plan.engine == 2) {
@@ -756,7 +881,8 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
         const double tB = now_ms();
         double kms = 0;
         int64_t h2d_bytes = 0;
-        for (auto& D : Ds) { kms = std::max(kms, finish_batch(*D)); h2d_bytes += D->h2d_bytes; }
+        long long ho_paths = 0; double ho_ms = 0;
+        for (auto& D : Ds) { kms = std::max(kms, finish_batch(*D)); h2d_bytes += D->h2d_bytes; ho_paths += D->handoff_paths; ho_ms = std::max(ho_ms, D->handoff_ms); }
         const double tC = now_ms();
         for (auto& D : Ds) fetch_results(*D, out);
         for (auto& D : Ds) { use_slot(D->slot); dev_sync(); }
@@ -767,6 +893,7 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
         g_timing.grid = D0.plan.grid; g_timing.block = D0.plan.block; g_timing.lanes = D0.plan.group;
         g_timing.slab_bytes = D0.plan.engine != 0 ? (int64_t)D0.plan.lanes * (int64_t)(D0.plan.slab + D0.plan.cold) : (int64_t)D0.plan.slab;
         g_timing.devices = (int32_t)Ds.size(); g_timing.engine = D0.plan.engine;
+        g_timing.handoff_paths = ho_paths; g_timing.handoff_ms = ho_ms;
         Ds.clear();
         use_slot(0);
         if (env_int("HC_B200_VERBOSE", 0) >= 2)
@@ -1012,9 +1139,33 @@ void* hc_resident_create(void* H, void* Hcoeff, const hc_options* o, int32_t mod
     catch (...) { delete D; fail("internal error"); return nullptr; }
     return D;
 }
+void* hc_resident_create_cells(void* Htoric, void* Hcoeff, const hc_options* o, int64_t first, int64_t N, int32_t ncells,
+                               const int64_t* cell_volume, const int64_t* bin_H, const double* bin_mu, const double* bin_r,
+                               const double* cell_weights) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceBatch* D = nullptr;
+    try {
+        if (!Htoric || !Hcoeff || !o) throw std::string("null handle / options");
+        if (!cell_volume || !bin_H || !bin_mu || !bin_r || !cell_weights || ncells <= 0) throw std::string("hc_resident_create_cells: cell data missing");
+        ensure_init();
+        HomotopyH* h = merged_polyhedral((HomotopyH*)Htoric, (HomotopyH*)Hcoeff);
+        if (g_cancel) *g_cancel = 0;
+        StartGen sg; sg.td_first = first; sg.bin_volume = cell_volume; sg.bin_H = bin_H; sg.bin_mu = bin_mu; sg.bin_r = bin_r;
+        D = new DeviceBatch();
+        setup_batch(*D, h, o, MODE_POLYHEDRAL, N, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, cell_weights, ncells, sg);
+        dev_sync();
+    } catch (const std::string& e) { delete D; fail(e); return nullptr; }
+    catch (...) { delete D; fail("internal error"); return nullptr; }
+    return D;
+}
 int32_t hc_resident_run(void* r, double* kernel_ms) {
     std::lock_guard<std::mutex> lock(g_mutex);
-    try { double ms = run_batch(*(DeviceBatch*)r); if (kernel_ms) *kernel_ms = ms; }
+    try {
+        DeviceBatch& D = *(DeviceBatch*)r;
+        double ms = run_batch(D);
+        if (kernel_ms) *kernel_ms = ms;
+        g_timing.handoff_paths = D.handoff_paths; g_timing.handoff_ms = D.handoff_ms;
+    }
     catch (const std::string& e) { return fail(e); }
     catch (...) { return fail("internal error"); }
     return 0;

@@ -42,7 +42,8 @@ enum Phase : int { PH_IDLE = 0, PH_PLAIN, PH_EG, PH_SING, PH_TORIC_A, PH_TORIC_B
 // residual of a finished path) is not run where it arises: the lane parks with an event, and the kernel
 // handles the events of a warp together (event_finish / event_begin below), each kind of work from ONE call
 // site -- otherwise every lane would run its initialisations alone while the other 31 lanes of the warp wait.
-enum Event : int { EV_NONE = 0, EV_START, EV_TORIC_NEXT, EV_FINISH_EG, EV_FINISH_PLAIN, EV_FINISH_POLY_FAILED };
+enum Event : int { EV_NONE = 0, EV_START, EV_TORIC_NEXT, EV_FINISH_EG, EV_FINISH_PLAIN, EV_FINISH_POLY_FAILED, EV_HANDOFF };
+enum { RC_HANDOFF = -1 };  // return_code of a path the first pass of a two-pass batch gave up on (never leaves the library)
 enum InitKind : int { IK_NONE = 0, IK_TRACKER, IK_EG, IK_POLY_A, IK_POLY_B };
 struct InitReq { int kind; cx t1, t0; double omega, mu, tau, max_init; bool keep_steps, ext; };
 enum Mode : int { MODE_ENDGAME = 0, MODE_TRACKER = 1, MODE_POLYHEDRAL = 2 };
@@ -78,6 +79,15 @@ struct BatchIn {
     const double* bin_mu;
     const double* bin_r;
     long long k_first;
+    // Two-pass batches (hc_api.cu: second_pass).  Pass 1, thread per path: a lane gives up a path (return_code =
+    // RC_HANDOFF) that needs more than handoff_eg_steps endgame steps or handoff_steps tracker steps in total, or that
+    // switches to extended precision -- one lane walks such a path 20 x slower than a CPU core while the rest of its CTA
+    // waits.  The criteria depend on the path alone, so which pass tracks a path does not depend on timing.  Pass 2,
+    // lane group per path: path k of the launch is path index_map[k] of the batch, tracked again from its start solution.
+    int handoff_steps;            // 0 = off
+    int handoff_eg_steps;
+    int handoff_ext;
+    const long long* index_map;   // nullptr = identity
 };
 
 template <int G, int S>
@@ -107,6 +117,7 @@ struct Lane : Path<G, S> {
     // ---- polyhedral
     int toric_acc, toric_rej; double poly_maxw, saved_min_step;
     int cell;  // mixed cell of the path
+    int path_rounds, ho_steps, ho_eg_steps; bool ho_ext;  // tracker steps of the path so far (all stages); hand-off thresholds of the batch
     // ---- flop accounting totals of finished stages
     int c_fact, c_ldiv;
 
@@ -546,6 +557,8 @@ struct Lane : Path<G, S> {
     // a new path: load the start, reset the per-path state, request the first tracker initialisation
     HC_HDN void start_pre(long long k, const BatchIn& Bt) {
         HC_COLD_N
+        if (Bt.index_map) k = Bt.index_map[k];
+        path_rounds = 0; ho_steps = Bt.handoff_steps; ho_eg_steps = Bt.handoff_eg_steps; ho_ext = Bt.handoff_ext != 0;
         pidx = k; mode = Bt.mode;
         const int nn = n;
         g.sync();
@@ -626,6 +639,7 @@ struct Lane : Path<G, S> {
             ev = EV_START;
         } else if (ev == EV_FINISH_PLAIN) { finish_plain(R); ev = EV_START; }
         else if (ev == EV_FINISH_POLY_FAILED) { finish_poly_failed(R); ev = EV_START; }
+        else if (ev == EV_HANDOFF) { if (g.lane == 0) R.return_code[pidx] = RC_HANDOFF; phase = PH_IDLE; ev = EV_START; }
     }
     // Event round, part 2: free lanes take path k (if any is left), toric lanes decide their next stage; all
     // requested tracker initialisations then run from one call site.
@@ -660,6 +674,7 @@ struct Lane : Path<G, S> {
             case PH_EG: if (do_step) eg_post(ok); if (eg_code != EG_tracking) ev = EV_FINISH_EG; break;
             default: break;
         }
+        if (ho_steps > 0 && ev == EV_NONE && (++path_rounds > ho_steps || (ho_ext && extended_prec) || ((phase == PH_EG || phase == PH_SING) && steps_eg > ho_eg_steps))) ev = EV_HANDOFF;
     }
     HC_HD void iterate(const BatchIn&, const DevResults&) { iterate_t<false>(true); }
 };

@@ -167,7 +167,7 @@ struct Path {
     double ds_prev, accuracy, omega, omega_prev, mu, tau;
     bool extended_prec, used_extended_prec, refined_extended_prec, keep_extended_prec, use_strict_beta_tau;
     bool factorized, scaled;  // MatrixWorkspace flags
-    unsigned long long perm_bits;  // row permutation of the register-blocked LU, 4 bits per row (n <= 12)
+    unsigned long long perm_bits, perm_bits2;  // row permutation of the register-blocked LU, 5 bits per row, rows 0-11 / 12-23
     bool a_in_lu, rs_raw;     // specialised kernels: the Jacobian sits in the LU buffer (factorize in place); M.rs holds raw Skeel row sums
     int code, accepted_steps, rejected_steps, last_steps_failed, ext_accepted_steps, ext_rejected_steps;
     const DevProgram* tape_prog; int tape_kind; cx tape_t;  // whose inputs (constants, parameters at t) the fp64 tape holds
@@ -730,7 +730,7 @@ struct Path {
             for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
         }
 #pragma unroll
-        { unsigned long long pk = 0; for (int i = 0; i < N; ++i) pk |= (unsigned long long)rowof[i] << (4 * i); perm_bits = pk; }
+        { unsigned long long pk = 0, pk2 = 0; for (int i = 0; i < N; ++i) { if (i < 12) pk |= (unsigned long long)rowof[i] << (5 * i); else pk2 |= (unsigned long long)rowof[i] << (5 * (i - 12)); } perm_bits = pk; if (N > 12) perm_bits2 = pk2; }
         factorized = true;
         n_fact++;
     }
@@ -786,7 +786,7 @@ struct Path {
             for (int i = 0; i < N; ++i) LU[j * N + i] = col[i];
         }
 #pragma unroll
-        { unsigned long long pk = 0; for (int i = 0; i < N; ++i) pk |= (unsigned long long)rowof[i] << (4 * i); perm_bits = pk; }
+        { unsigned long long pk = 0, pk2 = 0; for (int i = 0; i < N; ++i) { if (i < 12) pk |= (unsigned long long)rowof[i] << (5 * i); else pk2 |= (unsigned long long)rowof[i] << (5 * (i - 12)); } perm_bits = pk; if (N > 12) perm_bits2 = pk2; }
         factorized = true;
         n_fact++;
     }
@@ -795,10 +795,9 @@ struct Path {
     HC_HDN void lu_solve_reg(CV x, CV b, bool scale) {
         LV A = M.LU;
         cx xr[N];
+        const unsigned long long pk = perm_bits, pk2 = N > 12 ? perm_bits2 : 0ull;  // scalars instead of N dependent index loads: the b[r] loads go out at once
 #pragma unroll
-        const unsigned long long pk = perm_bits;  // one scalar instead of N dependent index loads: the b[r] loads go out at once
-#pragma unroll
-        for (int i = 0; i < N; ++i) { const int r = (int)((pk >> (4 * i)) & 15u); xr[i] = b[r]; if (scale) xr[i] = M.rs[r] * xr[i]; }
+        for (int i = 0; i < N; ++i) { const int r = (int)(((i < 12 ? pk >> (5 * i) : pk2 >> (5 * (i - 12)))) & 31u); xr[i] = b[r]; if (scale) xr[i] = M.rs[r] * xr[i]; }
 #pragma unroll
         for (int j = 0; j < N - 1; ++j) {
 #pragma unroll
@@ -813,7 +812,11 @@ struct Path {
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = xr[i];
     }
-#define HC_REG_LU_MAX 12
+#if defined(HC_JIT_N)
+#define HC_REG_LU_MAX 20   // specialised kernels instantiate exactly their own N
+#else
+#define HC_REG_LU_MAX 12   // interpreter kernels: one instance per N of the dispatch below
+#endif
 #if defined(HC_JIT_N)
 #define HC_REG_LU_DISPATCH(CALL) CALL((((HC_JIT_N) >= 2 && (HC_JIT_N) <= HC_REG_LU_MAX) ? (HC_JIT_N) : 2));
 #else

@@ -17,7 +17,7 @@ class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("grid", C.c_int32), ("block", C.c_int32), ("lanes", C.c_int32), ("slab_bytes", C.c_int64),
-                ("devices", C.c_int32), ("engine", C.c_int32)]
+                ("devices", C.c_int32), ("engine", C.c_int32), ("handoff_paths", C.c_int64), ("handoff_ms", C.c_double)]
 
 
 def load(device: int | None = None, devices: list[int] | None = None) -> CApi:

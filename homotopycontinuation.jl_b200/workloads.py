@@ -229,9 +229,17 @@ def specialised_kernel_builders():
         api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs)
         return api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)
 
+    def cyclooctane(api):
+        ps = polyhedral.polyhedral(systems.cyclooctane(), target_parameters=cyclooctane_parameters(), seed_coeffs=14, seed_origin=15,
+                                   seed_lifting=16, cache=os.path.join(_DATA, "cyclooctane_cells.json"))
+        h = api.system(ps.F)
+        api.homotopy(capi.H_TORIC, h, p=ps.start_coeffs)
+        return api.homotopy(capi.H_COEFFICIENT, h, p=ps.start_coeffs, q=ps.target_coeffs)
+
     def biochem(api):
         z = np.zeros(10, dtype=np.complex128)
         return api.homotopy(capi.H_PARAMETER, api.system(systems.biochem1()), p=z, q=z)
     return [("cyclic7_polyhedral", cyclic7, 1), ("katsura8", sl(lambda: systems.katsura(8)), 0),
             ("tritangents", sl(systems.tritangents, lambda: np.random.default_rng(3).normal(size=20)), 0),
-            ("biochem_sweep", biochem, 2)]
+            ("biochem_sweep", biochem, 2),
+            ("cyclooctane_td", sl(systems.cyclooctane, cyclooctane_parameters), 0), ("cyclooctane_polyhedral", cyclooctane, 1)]

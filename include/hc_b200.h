@@ -109,6 +109,8 @@ typedef struct {                 /* device timing of the last batch call on this
     int64_t slab_bytes;
     int32_t devices;             /* devices the batch was split over */
     int32_t engine;              /* 0 lane group per path, 1 thread per path (interpreter), 2 thread per path (specialised kernel) */
+    int64_t handoff_paths;       /* two-pass batches: paths the thread-per-path kernel handed to the lane-group engine ... */
+    double handoff_ms;           /* ... and the time of that second kernel (included in kernel_ms) */
 } hc_timing;
 
 int32_t hc_init(int32_t device);            /* the process drives this one CUDA device (= hc_init_devices(&device, 1)) */
@@ -174,6 +176,10 @@ void hc_get_timing(hc_timing* t);
 void* hc_resident_create(void* H, void* Hcoeff_or_null, const hc_options* o, int32_t mode, int64_t N, const double* starts,
                          const double* t1, const double* t0, const double* path_p, const double* path_q,
                          const int32_t* cell_index, const double* cell_weights, int32_t ncells);
+/* the same for a polyhedral batch whose start solutions are made on the device (arguments of hc_polyhedral_track_cells) */
+void* hc_resident_create_cells(void* Htoric, void* Hcoeff, const hc_options* o, int64_t first, int64_t N, int32_t ncells,
+                               const int64_t* cell_volume, const int64_t* bin_H, const double* bin_mu, const double* bin_r,
+                               const double* cell_weights);
 int32_t hc_resident_run(void* r, double* kernel_ms);
 int32_t hc_resident_fetch(void* r, hc_results* out);
 void hc_resident_destroy(void* r);

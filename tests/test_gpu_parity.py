@@ -273,6 +273,33 @@ def test_cyclooctane_slice_config4(oracle, gpu):
     assert_classes_match(ro, rg)
 
 
+@pytest.mark.parametrize("name", ["tritangents", "cyclooctane_td", "cyclooctane_polyhedral"])
+def test_two_pass_batches_on_the_heavy_tailed_configs(oracle, gpu, monkeypatch, name):
+    """Large batches of the heavy-tailed configs run in two passes (hc_api.cu: second_pass): the specialised
+    thread-per-path kernel hands over the paths that need more than 120 endgame steps or extended precision, the
+    lane-group engine tracks those again from their start solutions.  Same classes and nonsingular solutions as the
+    oracle; which pass tracks a path depends on the path alone, so two runs are bit-identical; with the hand-over
+    switched off the same classes come out of the single pass."""
+    from hcb200 import workloads
+    monkeypatch.setenv("HC_B200_JIT", "1")
+    w = {"tritangents": lambda: workloads.tritangents_total_degree().subset(4096),
+         "cyclooctane_td": lambda: workloads.cyclooctane_total_degree().subset(2048),
+         "cyclooctane_polyhedral": lambda: workloads.cyclooctane_polyhedral().subset(2048)}[name]()
+    ro = w.track(oracle, w.build(oracle), nthreads=8)
+    h = w.build(gpu)
+    rg = w.track(gpu, h)
+    tm = lib.timing()
+    assert tm.engine == 2 and 0 < tm.handoff_paths < 0.2 * w.N, (tm.engine, tm.handoff_paths)
+    assert (rg.return_code > 0).all()                      # no path is left handed over
+    assert_classes_match(ro, rg)
+    again = w.track(gpu, h)
+    _same(rg, again)
+    monkeypatch.setenv("HC_B200_HANDOFF", "0")
+    single = w.track(gpu, h)
+    assert lib.timing().handoff_paths == 0
+    assert_classes_match(single, rg)
+
+
 def test_set_parameters_between_batches(gpu):
     """start_parameters! / target_parameters! / parameters! (reference test/tracker_test.jl:81-91 "Change parameters"):
     hc_homotopy_set_parameters rewrites the device copies of p and q; the next batch equals a homotopy created with

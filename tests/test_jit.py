@@ -98,6 +98,15 @@ def test_generated_code_tracks_like_the_oracle(oracle, sim, jit_on):
     assert_last_point_on_path(Hs, Hs.track_batch(starts))
 
 
+def test_generated_code_n17_register_lu(oracle, sim, jit_on):
+    """cyclooctane (n = 17) through the specialised unit: the register-blocked LU beyond n = 12 (two-word packed row
+    permutation) and a polyhedral batch, 24 paths each"""
+    from hcb200 import workloads
+    for w in (workloads.cyclooctane_total_degree(24), workloads.cyclooctane_polyhedral().subset(24)):
+        ro, rs = (w.track(api, w.build(api)) for api in (oracle, sim))
+        assert_batches_match(ro, rs)
+
+
 def test_generated_unit_equals_interpreter_classes(sim, monkeypatch):
     """the two device engines run the same tracker: same classes and endpoints on a batch with diverging paths"""
     F = systems.cyclic(5)

@@ -18,6 +18,7 @@ def main():
     mk = {"katsura8": workloads.katsura8, "cyclic7_polyhedral": lambda r: workloads.cyclic_polyhedral(7, r),
           "cyclic7_td": workloads.cyclic7_total_degree, "tritangents": lambda r: workloads.tritangents_total_degree(r if r > 1 else None),
           "cyclooctane_td": lambda r: workloads.cyclooctane_total_degree(r if r > 1 else None),
+          "cyclooctane_polyhedral": lambda r: workloads.cyclooctane_polyhedral(),
           "biochem_sweep": lambda r: workloads.biochem_sweep(api, r * 1024)}[name]
     w = mk(reps)
     h = w.build(api)
@@ -25,7 +26,8 @@ def main():
         r = w.track(api, h)
         tm = lib.timing()
         print(f"{name} x{reps} ({w.N} paths): kernel {tm.kernel_ms:.1f} ms = {w.N / tm.kernel_ms * 1e3:,.0f} paths/s, codes "
-              f"{np.bincount(r.return_code).tolist()}, grid {tm.grid} x {tm.block}", flush=True)
+              f"{np.bincount(r.return_code).tolist()}, grid {tm.grid} x {tm.block}"
+              + (f", second pass {tm.handoff_paths} paths {tm.handoff_ms:.1f} ms" if tm.handoff_paths else ""), flush=True)
 
 
 if __name__ == "__main__":
