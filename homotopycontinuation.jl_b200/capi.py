@@ -183,6 +183,8 @@ class CApi:
         f("polyhedral_track_cells", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(Options), C.c_int64, C.c_int64, C.c_int32,
                                                 c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p,
                                                 C.POINTER(ResultsDesc)], optional=True)
+        f("unique_points_filter", C.c_int32, [C.c_int32, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_double, C.c_double,
+                                              c_int64_p], optional=True)
         f("track_sweep", C.c_int32, [C.c_void_p, C.POINTER(Options), C.c_int64, c_double_p, C.c_int64, c_double_p,
                                      C.POINTER(ResultsDesc)], optional=True)
 

@@ -250,6 +250,27 @@ __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, cons
     if (what == 2) for (int i = 0; i < n * n; ++i) U[i] = L.M.A[i];
 }
 
+// Duplicate filter of the monodromy driver (reference: UniquePoints lookup in add_tracked_result!, src/monodromy.jl:1176-1200,
+// src/unique_points.jl:247-285): candidate i -> index of the first known point within its radius, or -1.  One thread per
+// candidate; the known points are read by all threads of a warp at the same address (broadcast).
+__global__ void hc_unique_filter_kernel(int n, long long M, const cx* known, long long N, const cx* cand, double atol, double rtol, long long* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const cx* c = cand + i * n;
+    double nrm2 = 0;
+    for (int j = 0; j < n; ++j) nrm2 += abs2(c[j]);
+    double rad = rtol * sqrt(nrm2);
+    if (rad < atol) rad = atol;
+    const double rad2 = rad * rad;
+    long long hit = -1;
+    for (long long k = 0; k < M && hit < 0; ++k) {
+        double d = 0;
+        for (int j = 0; j < n; ++j) d += abs2(known[k * n + j] - c[j]);
+        if (d <= rad2) hit = k;
+    }
+    out[i] = hit;
+}
+
 __global__ void hc_dfma_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double b = 1.0000001, c = 1e-9;
@@ -1117,6 +1138,46 @@ int32_t hc_track_sweep(void* H, const hc_options* o, int64_t S, const double* st
     if (S <= 0 || M < 0 || !starts || !target_params) return fail("hc_track_sweep: starts and target parameters are required");
     StartGen sg; sg.start_rows = S; sg.param_div = S;
     return track_impl(h, o, MODE_ENDGAME, S * M, starts, nullptr, nullptr, nullptr, target_params, nullptr, nullptr, nullptr, 0, out, sg);
+}
+
+int32_t hc_unique_points_filter(int32_t n, int64_t M, const double* known, int64_t N, const double* cand, double atol, double rtol,
+                                int64_t* match) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try {
+        if (n <= 0 || M < 0 || N < 0 || (M > 0 && !known) || (N > 0 && (!cand || !match))) throw std::string("hc_unique_points_filter: bad arguments");
+        if (N == 0) return 0;
+#ifndef HC_HOST_SIM
+        if (nodev()) throw std::string("HC_B200_NO_DEVICE is set: no compute calls");
+        ensure_init();
+        use_slot(0);
+        cx* dk = (cx*)dev_alloc((size_t)std::max<int64_t>(M, 1) * n * 16);
+        cx* dc = (cx*)dev_alloc((size_t)N * n * 16);
+        long long* dm = (long long*)dev_alloc((size_t)N * 8);
+        h2d(dk, known, (size_t)M * n * 16); h2d(dc, cand, (size_t)N * n * 16);
+        hc_unique_filter_kernel<<<(unsigned)((N + 127) / 128), 128, 0, cur_stream()>>>(n, M, dk, N, dc, atol, rtol, dm);
+        cudaError_t le = cudaGetLastError();
+        d2h(match, dm, (size_t)N * 8);
+        dev_sync();
+        dev_free(dk); dev_free(dc); dev_free(dm);
+        CK(le);
+#else
+        for (int64_t i = 0; i < N; ++i) {
+            const double* c = cand + 2 * n * i;
+            double nrm2 = 0;
+            for (int j = 0; j < 2 * n; ++j) nrm2 += c[j] * c[j];
+            double rad = rtol * sqrt(nrm2);
+            if (rad < atol) rad = atol;
+            match[i] = -1;
+            for (int64_t k = 0; k < M && match[i] < 0; ++k) {
+                double d = 0;
+                for (int j = 0; j < 2 * n; ++j) { const double e = known[2 * n * k + j] - c[j]; d += e * e; }
+                if (d <= rad * rad) match[i] = k;
+            }
+        }
+#endif
+    } catch (const std::string& e) { return fail(e); }
+    catch (...) { return fail("internal error"); }
+    return 0;
 }
 
 void hc_get_timing(hc_timing* t) { *t = g_timing; }

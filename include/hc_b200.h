@@ -169,6 +169,12 @@ int32_t hc_polyhedral_track_cells(void* Htoric, void* Hcoeff, const hc_options* 
  * column per POINT are copied to the device. */
 int32_t hc_track_sweep(void* H, const hc_options* o, int64_t S, const double* starts, int64_t M,
                        const double* target_params, hc_results* out);
+/* Duplicate filter of a monodromy round (reference: the UniquePoints lookup of add_tracked_result!,
+ * src/monodromy.jl:1176-1200, src/unique_points.jl:247-285): match[i] = index of the first of the M known points
+ * (n complex each, point-major) within max(atol, rtol * ||cand_i||_2) of candidate i, or -1.  The loop driver itself
+ * stays on the host (monodromy.py mirrors it): three hc_track_batch calls per loop, p -> p1 -> p2 -> p. */
+int32_t hc_unique_points_filter(int32_t n, int64_t M, const double* known, int64_t N, const double* cand, double atol, double rtol,
+                                int64_t* match);
 void hc_get_timing(hc_timing* t);
 
 /* Device-resident variant for throughput measurement: inputs are uploaded once, results stay on
