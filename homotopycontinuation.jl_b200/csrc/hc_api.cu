@@ -488,7 +488,8 @@ struct DeviceBatch {  // device-resident inputs and outputs of one batch
     long long handoff_paths = 0; double handoff_ms = 0;
     unsigned char* cold2 = nullptr; size_t cold2_bytes = 0; long long* map2 = nullptr; size_t map2_count = 0;
 #ifndef HC_HOST_SIM
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, f0 = nullptr, f1 = nullptr;
+    bool second_running = false;
 #endif
     ~DeviceBatch() {
         const int keep = g_cur;
@@ -497,6 +498,8 @@ struct DeviceBatch {  // device-resident inputs and outputs of one batch
 #ifndef HC_HOST_SIM
         if (e0) cudaEventDestroy(e0);
         if (e1) cudaEventDestroy(e1);
+        if (f0) cudaEventDestroy(f0);
+        if (f1) cudaEventDestroy(f1);
 #endif
         g_cur = keep;
     }
@@ -726,8 +729,9 @@ void group_programs(SystemH& S, ProgramH*& e, ProgramH*& j) {
 
 // Second pass of a two-pass batch: the paths the thread-per-path kernel gave up (return_code == RC_HANDOFF) are tracked
 // again, from their start solutions, by the lane-group engine -- a group of lanes walks one long path several times
-// faster than a single lane, and nothing waits for it.  Results land at the paths' own indices.  Returns milliseconds.
-double second_pass(DeviceBatch& D) {
+// faster than a single lane, and nothing waits for it.  Results land at the paths' own indices.  The launch is
+// asynchronous (finish_second waits for it), so the second passes of several devices overlap.
+void second_pass(DeviceBatch& D) {
     const long long N = D.N;
     std::vector<int> rc((size_t)N);
     d2h(rc.data(), D.A.R.return_code, (size_t)N * 4);
@@ -735,7 +739,7 @@ double second_pass(DeviceBatch& D) {
     std::vector<long long> idx;
     for (long long k = 0; k < N; ++k) if (rc[(size_t)k] == RC_HANDOFF) idx.push_back(k);
     D.handoff_paths = (long long)idx.size();
-    if (idx.empty()) return 0.0;
+    if (idx.empty()) return;
     HomotopyH& H = *D.H;
     KArgs A2 = D.A;
     ProgramH *Fe, *Fj, *Ge = nullptr, *Gj = nullptr;
@@ -782,22 +786,32 @@ double second_pass(DeviceBatch& D) {
     dev_zero(A2.queue, sizeof(unsigned long long));
     const void* kern = hc_kernel_group(G);
     if (first_use(kern)) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-    cudaEvent_t f0, f1;
-    CK(cudaEventCreate(&f0)); CK(cudaEventCreate(&f1));
-    CK(cudaEventRecord(f0, cur_stream()));
+    if (!D.f0) { CK(cudaEventCreate(&D.f0)); CK(cudaEventCreate(&D.f1)); }
+    CK(cudaEventRecord(D.f0, cur_stream()));
     void* args[] = {(void*)&A2};
-    cudaError_t le = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)block), args, smem, cur_stream());
-    cudaEventRecord(f1, cur_stream());
-    cudaError_t se = cudaEventSynchronize(f1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, f0, f1);
-    cudaEventDestroy(f0); cudaEventDestroy(f1);
-    CK(le); CK(se);
+    CK(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)block), args, smem, cur_stream()));
+    CK(cudaEventRecord(D.f1, cur_stream()));
+    D.second_running = true;
     if (env_int("HC_B200_VERBOSE", 0) >= 1)
-        fprintf(stderr, "[hc_b200] second pass: %lld of %lld paths on the lane-group engine (G = %d, grid %d x %d): %.1f ms\n", N2, N, G, grid, block, (double)ms);
-    return ms;
+        fprintf(stderr, "[hc_b200] second pass: %lld of %lld paths on the lane-group engine (G = %d, grid %d x %d)\n", N2, N, G, grid, block);
 }
 #endif
+// waits for the second pass of the batch, if one was launched; returns its milliseconds
+double finish_second(DeviceBatch& D) {
+#ifndef HC_HOST_SIM
+    if (!D.second_running) return 0.0;
+    use_slot(D.slot);
+    D.second_running = false;
+    CK(cudaEventSynchronize(D.f1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, D.f0, D.f1));
+    D.handoff_ms = ms;
+    return ms;
+#else
+    (void)D;
+    return 0.0;
+#endif
+}
 
 double finish_batch(DeviceBatch& D) {
     use_slot(D.slot);
@@ -806,7 +820,7 @@ double finish_batch(DeviceBatch& D) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, D.e0, D.e1));
     D.handoff_paths = 0; D.handoff_ms = 0;
-    if (D.A.B.handoff_steps > 0) { D.handoff_ms = second_pass(D); ms += (float)D.handoff_ms; }
+    if (D.A.B.handoff_steps > 0) second_pass(D);   // asynchronous: finish_second
     return ms;
 #else
     if (D.plan.engine == 2) {
@@ -824,7 +838,7 @@ double finish_batch(DeviceBatch& D) {
     return 0.0;
 #endif
 }
-double run_batch(DeviceBatch& D) { launch_batch(D); return finish_batch(D); }
+double run_batch(DeviceBatch& D) { launch_batch(D); const double ms = finish_batch(D); return ms + finish_second(D); }
 
 // copies the PathResult arrays of the batch into the caller's arrays at the batch's path offset (stream-ordered:
 // dev_sync() before the host reads them)
@@ -903,7 +917,13 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
         double kms = 0;
         int64_t h2d_bytes = 0;
         long long ho_paths = 0; double ho_ms = 0;
-        for (auto& D : Ds) { kms = std::max(kms, finish_batch(*D)); h2d_bytes += D->h2d_bytes; ho_paths += D->handoff_paths; ho_ms = std::max(ho_ms, D->handoff_ms); }
+        std::vector<double> ms1;
+        for (auto& D : Ds) { ms1.push_back(finish_batch(*D)); h2d_bytes += D->h2d_bytes; }   // first passes done, second passes launched
+        for (size_t i = 0; i < Ds.size(); ++i) {
+            DeviceBatch& D = *Ds[i];
+            kms = std::max(kms, ms1[i] + finish_second(D));
+            ho_paths += D.handoff_paths; ho_ms = std::max(ho_ms, D.handoff_ms);
+        }
         const double tC = now_ms();
         for (auto& D : Ds) fetch_results(*D, out);
         for (auto& D : Ds) { use_slot(D->slot); dev_sync(); }
