@@ -18,9 +18,13 @@
 
 namespace hc {
 
-#define HC_PAR(i, N) for (int i = g.lane; i < (N); i += G)
+// Lane-strided loops.  The trip count is the same for every lane of a group (the loop branch is warp-uniform) and
+// the body is guarded instead: a lane group whose lanes leave `for (i = lane; i < N; i += G)` at different trips
+// pays a divergence + reconvergence (BSSY / BSYNC, a refetch) per loop -- the second-pass capture showed BSYNC at 10 %
+// of the instruction-fetch stalls.  For G == 1 both forms are the plain loop.
+#define HC_PAR(i, N) for (int i##_b = 0, i = g.lane; i##_b < (N); i##_b += G, i += G) if (G == 1 || i < (N))
 // load-only loops (reductions): unrolled so that the loads of four trips are in flight together
-#define HC_PARU(i, N) _Pragma("unroll 4") for (int i = g.lane; i < (N); i += G)
+#define HC_PARU(i, N) _Pragma("unroll 4") for (int i##_b = 0, i = g.lane; i##_b < (N); i##_b += G, i += G) if (G == 1 || i < (N))
 
 // CTA-wide barriers of the lockstep (SYNC) instantiations of the tracker step: every thread of the CTA passes each of
 // them once per round whether or not its lane has work, so that the warps walk the same code together (a 32 KB
@@ -237,7 +241,7 @@ struct Path {
                 y[i] = cfnma(a0, s, y0); y[i + 1] = cfnma(a1, s, y1); y[i + 2] = cfnma(a2, s, y2); y[i + 3] = cfnma(a3, s, y3);
             }
             for (; i < hi; ++i) y[i] = cfnma(a[i], s, y[i]);
-        } else for (int i = lo + g.lane; i < hi; i += G) y[i] = cfnma(a[i], s, y[i]);
+        } else for (int ib = lo, i = lo + g.lane; ib < hi; ib += G, i += G) { if (i < hi) y[i] = cfnma(a[i], s, y[i]); }
     }
     // outputs of a program run: MODE 0 dst = tape, 1 dst = s * tape, 2 dst += s * tape
     template <int MODE>
@@ -631,13 +635,13 @@ struct Path {
         LV A = M.LU;
         for (int k = 0; k < nn; ++k) {
             double amax = -1.0; int kp = k;
-            for (int i = k + g.lane; i < nn; i += G) { double v = abs2(A[k * nn + i]); if (v > amax) { amax = v; kp = i; } }
+            for (int ib = k, i = k + g.lane; ib < nn; ib += G, i += G) { if (i < nn) { double v = abs2(A[k * nn + i]); if (v > amax) { amax = v; kp = i; } } }
             g.argmax(amax, kp);
             if (g.lane == 0) M.ipiv[k] = kp;
             if (amax > 0.0) {
                 if (kp != k) { HC_PAR(j, nn) { cx tmp = A[j * nn + k]; A[j * nn + k] = A[j * nn + kp]; A[j * nn + kp] = tmp; } g.sync(); }
                 cx pinv = cinv(A[k * nn + k]);
-                for (int i = k + 1 + g.lane; i < nn; i += G) A[k * nn + i] = A[k * nn + i] * pinv;
+                for (int ib = k + 1, i = k + 1 + g.lane; ib < nn; ib += G, i += G) { if (i < nn) A[k * nn + i] = A[k * nn + i] * pinv; }
                 g.sync();
             }
             const int m = nn - k - 1;
@@ -647,9 +651,11 @@ struct Path {
                 // trailing update, (column, row) pairs strided over the lanes
                 int jc = g.lane / m, ir = g.lane - jc * m;
                 const int dj = G / m, di = G - dj * m;
-                while (jc < m) {
-                    const int j = k + 1 + jc, i = k + 1 + ir;
-                    A[j * nn + i] = cfnma(A[k * nn + i], A[j * nn + k], A[j * nn + i]);
+                for (int p0 = 0; p0 < m * m; p0 += G) {  // uniform trip count, guarded body (see HC_PAR)
+                    if (jc < m) {
+                        const int j = k + 1 + jc, i = k + 1 + ir;
+                        A[j * nn + i] = cfnma(A[k * nn + i], A[j * nn + k], A[j * nn + i]);
+                    }
                     jc += dj; ir += di;
                     if (ir >= m) { ir -= m; jc += 1; }
                 }
@@ -863,7 +869,7 @@ struct Path {
         }
         for (int j = nn - 1; j >= 0; --j) {  // L^H
             double zr = 0.0, zi = 0.0;
-            for (int i = j + 1 + g.lane; i < nn; i += G) { cx p = conj(A[j * nn + i]) * x[i]; zr += p.re; zi += p.im; }
+            for (int ib = j + 1, i = j + 1 + g.lane; ib < nn; ib += G, i += G) { if (i < nn) { cx p = conj(A[j * nn + i]) * x[i]; zr += p.re; zi += p.im; } }
             zr = g.rsum(zr); zi = g.rsum(zi);
             cx z = x[j] - mk(zr, zi);
             g.sync();

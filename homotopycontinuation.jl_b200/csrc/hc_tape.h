@@ -510,7 +510,7 @@ HC_HDN void run_taylor_tape(const DevProgram& P, TV tape, const Grp<G>& g) {
     int beg = 0;
     for (int L = 0; L < P.n_levels; ++L) {
         const int end = P.level_end[L];
-        for (int i = beg + g.lane; i < end; i += G) exec_mop_taylor<K>(P.ops[i], tape);
+        for (int ib = beg, i = beg + g.lane; ib < end; ib += G, i += G) { if (i < end) exec_mop_taylor<K>(P.ops[i], tape); }  // uniform trips, guarded body
         g.sync();
         beg = end;
     }
