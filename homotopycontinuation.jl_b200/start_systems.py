@@ -10,7 +10,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .modelkit import System, make_system
+from .modelkit import Expr, System, make_system
 
 
 @dataclass
@@ -21,6 +21,7 @@ class TotalDegreeStart:
     scaling: np.ndarray        # parameters of G
     gamma: complex
     target_parameters: np.ndarray | None
+    chart: np.ndarray | None = None   # homogeneous input: F and G carry the row v'x - 1 of this affine chart
 
     def n_paths(self) -> int:
         return int(np.prod(self.degrees))
@@ -37,23 +38,53 @@ class TotalDegreeStart:
             idx = idx // d
             out[:, i] = np.exp(2j * np.pi * k / d)
             # exact values at the axes, as cis() gives in Julia
+        if self.chart is not None:   # homogeneous: [x_1 .. x_{n-1}, 1] put on the chart v'x = 1 (total_degree.jl:262, on_chart!)
+            out = np.concatenate([out, np.ones((N, 1), dtype=np.complex128)], axis=1)
+            out /= (out @ self.chart)[:, None]
         return out
 
 
-def total_degree(F: System, gamma: complex, target_parameters=None) -> TotalDegreeStart:
+def total_degree(F: System, gamma: complex, target_parameters=None, chart_seed: int = 11) -> TotalDegreeStart:
     p = () if target_parameters is None else list(np.asarray(target_parameters, dtype=np.complex128))
     supports, coeffs = F.support_coefficients(p)
-    if F.n_eqs != F.n_vars:
-        raise NotImplementedError("only square affine systems (SURVEY.md section 8: all five configs)")
-    # src/total_degree.jl:48-61: a system whose every polynomial has all its monomials of one degree is homogeneous; the
-    # reference then tracks on an affine chart with G = s .* (x[1:n-1].^D .- x[n].^D).  Charts are outside this path
-    # (SURVEY.md section 8f-3), so say so instead of silently building the affine start system.
+    # src/total_degree.jl:48-61, 94-108: a system whose every polynomial has all its monomials of one degree is homogeneous;
+    # the reference then tracks on a random affine chart v'x = 1 (AffineChartHomotopy, src/homotopies/affine_chart_homotopy.jl
+    # :42-98) with G = s .* (x[1:n-1].^D .- x[n].^D).  The chart is built into the systems here: F and G both get the row
+    # v'x - 1 (in the straight-line homotopy that row is (gamma t + 1 - t)(v'x - 1): the same zero set; the reference keeps
+    # it unscaled) -- a host-side construction, the device tracks an ordinary square system (first half).
     if all(len(set(int(d) for d in A.sum(axis=0))) == 1 for A in supports):
-        raise NotImplementedError("homogeneous system: the reference puts it on an affine chart (src/total_degree.jl:94-108), "
-                                  "which this path does not build")
+        return _total_degree_on_chart(F, gamma, target_parameters, supports, coeffs, chart_seed)
+    if F.n_eqs != F.n_vars:
+        raise NotImplementedError("only square affine systems and homogeneous systems of n - 1 equations (SURVEY.md section 8)")
     D = np.array([int(A.sum(axis=0).max()) for A in supports], dtype=np.int64)
     scaling = np.array([np.abs(c).max() for c in coeffs], dtype=np.float64)
     n = F.n_vars
     G = make_system(lambda x, s: [s[i] * (x[i] ** int(D[i]) - 1) for i in range(n)], n, n)
     tp = None if target_parameters is None else np.asarray(target_parameters, dtype=np.complex128)
     return TotalDegreeStart(F, G, D, scaling, complex(gamma), tp)
+
+
+def _total_degree_on_chart(F: System, gamma, target_parameters, supports, coeffs, chart_seed: int) -> TotalDegreeStart:
+    n = F.n_vars
+    if F.n_eqs != n - 1:
+        raise NotImplementedError("homogeneous system: n - 1 equations in n variables expected (overdetermined systems are squared up by the "
+                                  "reference, src/total_degree.jl:72-88; not built here)")
+    rng = np.random.default_rng(chart_seed)
+    v = (rng.normal(size=n) + 1j * rng.normal(size=n)) / np.sqrt(2)   # randn(ComplexF64, n), affine_chart_homotopy.jl:35
+    D = np.array([int(A.sum(axis=0).max()) for A in supports], dtype=np.int64)
+    scaling = np.array([np.abs(c).max() for c in coeffs], dtype=np.float64)
+    g = F.graph
+    x = [Expr(g, g.var(i)) for i in range(n)]
+    row = x[0] * complex(v[0])
+    for i in range(1, n):
+        row = row + x[i] * complex(v[i])
+    Fc = System(g, list(F.exprs) + [(row - 1.0).i], n, F.n_params)
+
+    def start(xs, s):
+        r = xs[0] * complex(v[0])
+        for i in range(1, n):
+            r = r + xs[i] * complex(v[i])
+        return [s[i] * (xs[i] ** int(D[i]) - xs[n - 1] ** int(D[i])) for i in range(n - 1)] + [r - 1.0]
+    G = make_system(start, n, n - 1)
+    tp = None if target_parameters is None else np.asarray(target_parameters, dtype=np.complex128)
+    return TotalDegreeStart(Fc, G, D, scaling, complex(gamma), tp, chart=v)

@@ -187,6 +187,34 @@ def test_system_sizes(oracle, sim, k):
     assert abs(int(out[0].accepted_steps.sum()) - int(out[1].accepted_steps.sum())) <= 0.02 * out[0].accepted_steps.sum()
 
 
+def test_homogeneous_system_on_an_affine_chart(oracle, sim):
+    """total_degree of a homogeneous system (two quadrics in P^2; reference src/total_degree.jl:46-108): tracked on a random
+    affine chart v'x = 1 with G = s .* (x[1:n-1].^D .- x[n].^D); the chart row is part of F and G (start_systems.py).
+    Four projective solutions, on the chart, zeros of F, and -- dehomogenised -- the solutions of the affine system."""
+    from hcb200 import start_systems
+    quadrics = lambda v: [v[0] ** 2 + 2 * v[1] ** 2 - 3 * v[2] ** 2 + v[0] * v[1], v[0] * v[1] - 2 * v[2] ** 2 + v[1] * v[2] + 0.5 * v[0] ** 2]
+    F = make_system(lambda v, p: quadrics(v), 3)
+    td = start_systems.total_degree(F, 0.4 + 1.3j)
+    assert td.chart is not None and td.n_paths() == 4 and td.F.n_eqs == 3
+    S = td.start_solutions()
+    assert np.abs(S @ td.chart - 1).max() < 1e-14
+    out = []
+    for api in (oracle, sim):
+        H = api.homotopy(capi.H_STRAIGHT_LINE, api.system(td.F), api.system(td.G), gamma=td.gamma, G_params=td.scaling, F_params=[])
+        out.append(H.track_batch(S))
+    assert_batches_match(*out)
+    r = out[1]
+    assert (r.return_code == 1).all() and np.abs(r.solution @ td.chart - 1).max() < 1e-12
+    Fa = make_system(lambda v, p: quadrics([v[0], v[1], 1.0]), 2)
+    ta, Ha = straight_line(sim, Fa, 0.4 + 1.3j)
+    ra = Ha.track_batch(ta.start_solutions())
+    A = r.solution[:, :2] / r.solution[:, 2:3]
+    B = ra.solution[ra.return_code == 1]
+    assert len(B) == 4
+    d = np.abs(A[:, None, :] - B[None, :, :]).max(axis=2)
+    assert (d.min(axis=1) < 1e-8).all() and len(set(d.argmin(axis=1))) == 4
+
+
 @pytest.mark.parametrize("window", [1, 8, 32, 64, 1000])
 def test_segment_scheduler_invariants(sim, window):
     """The lowering the thread-per-path engine runs (hc_lower.h): every op's operands exist before its segment
