@@ -22,6 +22,8 @@ class TotalDegreeStart:
     gamma: complex
     target_parameters: np.ndarray | None
     chart: np.ndarray | None = None   # homogeneous input: F and G carry the row v'x - 1 of this affine chart
+    original: System | None = None    # overdetermined input: the system before squaring up (F = [I A] original)
+    A: np.ndarray | None = None       # ... and the randomisation matrix
 
     def n_paths(self) -> int:
         return int(np.prod(self.degrees))
@@ -54,8 +56,10 @@ def total_degree(F: System, gamma: complex, target_parameters=None, chart_seed: 
     # it unscaled) -- a host-side construction, the device tracks an ordinary square system (first half).
     if all(len(set(int(d) for d in A.sum(axis=0))) == 1 for A in supports):
         return _total_degree_on_chart(F, gamma, target_parameters, supports, coeffs, chart_seed)
+    if F.n_eqs > F.n_vars:
+        return _total_degree_squared_up(F, gamma, target_parameters, supports, coeffs, chart_seed)
     if F.n_eqs != F.n_vars:
-        raise NotImplementedError("only square affine systems and homogeneous systems of n - 1 equations (SURVEY.md section 8)")
+        raise NotImplementedError("underdetermined system")
     D = np.array([int(A.sum(axis=0).max()) for A in supports], dtype=np.int64)
     scaling = np.array([np.abs(c).max() for c in coeffs], dtype=np.float64)
     n = F.n_vars
@@ -88,3 +92,54 @@ def _total_degree_on_chart(F: System, gamma, target_parameters, supports, coeffs
     G = make_system(start, n, n - 1)
     tp = None if target_parameters is None else np.asarray(target_parameters, dtype=np.complex128)
     return TotalDegreeStart(Fc, G, D, scaling, complex(gamma), tp, chart=v)
+
+
+def square_up(F: System, A: np.ndarray) -> System:
+    """RandomizedSystem(F, A) with the identity block: [I A] F, the first n equations plus A times the other m - n
+    (reference src/systems/randomized_system.jl:8-12, 40-47; built symbolically on the host, the device tracks a square system)."""
+    n, m = F.n_vars, F.n_eqs
+    g = F.graph
+    E = [Expr(g, e) for e in F.exprs]
+    rows = []
+    for i in range(n):
+        r = E[i]
+        for j in range(m - n):
+            r = r + E[n + j] * complex(A[i, j])
+        rows.append(r.i)
+    return System(g, rows, n, F.n_params)
+
+
+def _total_degree_squared_up(F: System, gamma, target_parameters, supports, coeffs, seed: int) -> TotalDegreeStart:
+    """Overdetermined affine system (reference src/total_degree.jl:66-92): equations sorted by descending degree, squared up
+    with a random A, D = the n largest degrees, scaling = [I A] scaling.  The excess solutions the randomisation adds are
+    marked afterwards (excess_solution_check)."""
+    n, m = F.n_vars, F.n_eqs
+    D = np.array([int(A.sum(axis=0).max()) for A in supports], dtype=np.int64)
+    scaling = np.array([np.abs(c).max() for c in coeffs], dtype=np.float64)
+    perm = np.argsort(-D, kind="stable")
+    Fs = System(F.graph, [F.exprs[k] for k in perm], n, F.n_params)
+    D, scaling = D[perm], scaling[perm]
+    rng = np.random.default_rng(seed)
+    A = (rng.normal(size=(n, m - n)) + 1j * rng.normal(size=(n, m - n))) / np.sqrt(2)
+    Fr = square_up(Fs, A)
+    sc = scaling[:n].astype(np.complex128) + A @ scaling[n:]
+    Dn = D[:n]
+    G = make_system(lambda x, s: [s[i] * (x[i] ** int(Dn[i]) - 1) for i in range(n)], n, n)
+    tp = None if target_parameters is None else np.asarray(target_parameters, dtype=np.complex128)
+    return TotalDegreeStart(Fr, G, Dn, sc, complex(gamma), tp, original=Fs, A=A)
+
+
+def excess_solution_check(td: TotalDegreeStart, res, tol_factor: float = 100.0, tol_min: float = 1e-8):
+    """Marks the endpoints that solve the squared-up system but not the original one with return code 14
+    (EndgameTrackerCode.excess_solution).  The reference (src/overdetermined.jl:28-64) decides nonsingular endpoints with a
+    Newton iteration on the overdetermined system and singular ones by their residual; this is the residual rule for
+    both: ||F(x)||_inf > max(100 residual(path), 1e-8).  Host side (it runs once per solve on the successes only)."""
+    if td.original is None:
+        return res
+    p = () if td.target_parameters is None else list(td.target_parameters)
+    for k in np.flatnonzero(res.return_code == 1):
+        r = np.abs(np.array(td.original.evaluate(list(res.solution[k]), p), dtype=np.complex128)).max()
+        if r > max(tol_factor * float(res.residual[k]), tol_min):
+            res.return_code[k] = 14
+            res.residual[k] = r
+    return res

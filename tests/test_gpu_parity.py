@@ -300,6 +300,26 @@ def test_two_pass_batches_on_the_heavy_tailed_configs(oracle, gpu, monkeypatch, 
     assert_classes_match(single, rg)
 
 
+def test_homogeneous_and_overdetermined_inputs(oracle, gpu):
+    """The host-side wrappers of SURVEY.md 8f-3 end in ordinary square systems for the device: a homogeneous system on a
+    random affine chart (reference src/total_degree.jl:94-108) and an overdetermined one squared up with [I A]
+    (:66-92, src/overdetermined.jl) -- GPU vs oracle, the excess solutions marked."""
+    from hcb200 import start_systems
+    quad = make_system(lambda v, p: [v[0] ** 2 + 2 * v[1] ** 2 - 3 * v[2] ** 2 + v[0] * v[1], v[0] * v[1] - 2 * v[2] ** 2 + v[1] * v[2] + 0.5 * v[0] ** 2], 3)
+    over = make_system(lambda v, p: [v[0] + v[1] - 3.0, v[0] ** 2 + v[1] ** 2 - 5.0, v[0] * v[1] - 2.0], 2)
+    for F in (quad, over):
+        td = start_systems.total_degree(F, 0.4 + 1.3j)
+        out = []
+        for api in (oracle, gpu):
+            H = api.homotopy(capi.H_STRAIGHT_LINE, api.system(td.F), api.system(td.G), gamma=td.gamma, G_params=td.scaling, F_params=[])
+            out.append(start_systems.excess_solution_check(td, H.track_batch(td.start_solutions())))
+        assert_batches_match(*out)
+        if td.chart is not None:
+            assert (out[1].return_code == 1).all() and np.abs(out[1].solution @ td.chart - 1).max() < 1e-12
+        else:
+            assert sorted(out[1].return_code.tolist()) == [1, 1, 14, 14]
+
+
 def test_set_parameters_between_batches(gpu):
     """start_parameters! / target_parameters! / parameters! (reference test/tracker_test.jl:81-91 "Change parameters"):
     hc_homotopy_set_parameters rewrites the device copies of p and q; the next batch equals a homotopy created with

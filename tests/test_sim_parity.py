@@ -215,6 +215,27 @@ def test_homogeneous_system_on_an_affine_chart(oracle, sim):
     assert (d.min(axis=1) < 1e-8).all() and len(set(d.argmin(axis=1))) == 4
 
 
+def test_overdetermined_system_squared_up(oracle, sim):
+    """total_degree of an overdetermined system (3 equations, 2 variables; reference src/total_degree.jl:66-92,
+    src/systems/randomized_system.jl, src/overdetermined.jl): sorted by degree, squared up with a random [I A], the four
+    paths of the 2 x 2 system end in the two common zeros and two excess solutions, which the check marks (code 14)."""
+    from hcb200 import result, start_systems
+    F = make_system(lambda v, p: [v[0] + v[1] - 3.0, v[0] ** 2 + v[1] ** 2 - 5.0, v[0] * v[1] - 2.0], 2)
+    td = start_systems.total_degree(F, 0.4 + 1.3j)
+    assert td.original is not None and td.F.n_eqs == 2 and list(td.degrees) == [2, 2] and td.A.shape == (2, 1)
+    out = []
+    for api in (oracle, sim):
+        H = api.homotopy(capi.H_STRAIGHT_LINE, api.system(td.F), api.system(td.G), gamma=td.gamma, G_params=td.scaling, F_params=[])
+        out.append(start_systems.excess_solution_check(td, H.track_batch(td.start_solutions())))
+    assert_batches_match(*out)
+    r = out[1]
+    assert sorted(r.return_code.tolist()) == [1, 1, 14, 14]
+    sols = sorted(np.round(r.solution[r.return_code == 1].real, 8).tolist())
+    assert sols == [[1.0, 2.0], [2.0, 1.0]] and np.abs(r.solution[r.return_code == 1].imag).max() < 1e-10
+    st = result.statistics(r)
+    assert st.nonsingular == 2 and st.excess_solution == 2 and st.failed == 0
+
+
 @pytest.mark.parametrize("window", [1, 8, 32, 64, 1000])
 def test_segment_scheduler_invariants(sim, window):
     """The lowering the thread-per-path engine runs (hc_lower.h): every op's operands exist before its segment
