@@ -183,6 +183,7 @@ class CApi:
         f("polyhedral_track_cells", C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(Options), C.c_int64, C.c_int64, C.c_int32,
                                                 c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p,
                                                 C.POINTER(ResultsDesc)], optional=True)
+        f("evaluate_batch", C.c_int32, [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p], optional=True)
         f("unique_points_filter", C.c_int32, [C.c_int32, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_double, C.c_double,
                                               c_int64_p], optional=True)
         f("track_sweep", C.c_int32, [C.c_void_p, C.POINTER(Options), C.c_int64, c_double_p, C.c_int64, c_double_p,
@@ -305,6 +306,24 @@ class HomotopyHandle:
         rc = self.api._evaluate_and_jacobian(self.handle, _dp(xa), _dp(ta), _dp(u.view(np.float64)), _dp(U.view(np.float64)))
         if rc: raise RuntimeError(f"evaluate_and_jacobian failed ({rc})")
         return u, U.reshape(self.n, self.m).T.copy()
+
+    def evaluate_batch(self, X, t, jacobian: bool = False):
+        """H(x_k, t) (and the Jacobians) at all rows of X at once (hc_evaluate_batch); falls back to single-point calls
+        where the library has no batched entry (oracle)."""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.complex128).reshape(-1, self.n))
+        N = X.shape[0]
+        if getattr(self.api, "_evaluate_batch", None) is None:
+            if jacobian:
+                r = [self.evaluate_and_jacobian(x, t) for x in X]
+                return np.array([a for a, _ in r]).reshape(N, self.m), np.array([b for _, b in r]).reshape(N, self.m, self.n)
+            return np.array([self.evaluate(x, t) for x in X]).reshape(N, self.m)
+        ta = _cflat([t])
+        u = np.zeros((N, self.m), np.complex128)
+        U = np.zeros((N, self.n, self.m), np.complex128) if jacobian else None
+        rc = self.api._evaluate_batch(self.handle, N, _dp(X.view(np.float64)), _dp(ta), _dp(u.view(np.float64)),
+                                      _dp(U.view(np.float64)) if U is not None else None)
+        if rc: raise RuntimeError(f"evaluate_batch failed ({rc}): {_last_error(self.api)}")
+        return (u, U.transpose(0, 2, 1).copy()) if jacobian else u
 
     def taylor(self, K, tx, t):
         """tx: (K, n) rows x^0..x^{K-1}; returns the K-th Taylor coefficient of H(x(l), t+l)."""

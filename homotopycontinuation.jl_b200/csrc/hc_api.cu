@@ -230,9 +230,13 @@ __global__ void hc_hook_kernel(const KArgs A, int what, int K, const cx* x, cons
     Lane<1, 0> L;
     L.g.init();
     L.H = &sA.H; L.O = &sA.O; L.n = sA.H.n; L.pidx = L.prow = 0; L.kind = sA.H.kind;
-    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold);
+    const size_t b = blockIdx.x;  // hc_evaluate_batch: one point per block (one thread each), its own slab and scratch
+    carve(L.M, sA.H.n, sA.H.P, sA.H.tape_cx, hc_smem, A.cold + b * (size_t)A.cold_bytes);
     L.n_evaljac = L.n_eval = L.n_evaldd = L.n_tay1 = L.n_tay2 = L.n_tay3 = 0; L.tape_prog = L.tay_prog = nullptr; L.a_in_lu = L.rs_raw = false;
     const int n = sA.H.n;
+    x += b * (size_t)(what == 3 ? K * n : n); u += b * (size_t)n;
+    if (xlo) xlo += b * (size_t)n;
+    if (U) U += b * (size_t)n * n;
     if (tw) for (int i = 0; i < sA.H.P; ++i) L.M.tw[i] = tw[i];
     if (what == 3) { for (int i = 0; i < K * n; ++i) L.M.tx[i] = x[i]; }
     else for (int i = 0; i < n; ++i) L.M.x[i] = x[i];
@@ -1353,6 +1357,59 @@ int32_t hc_evaluate_and_jacobian(void* H, const double* x, const double* t, doub
 int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double* u) {
     if (K < 1 || K > 4) return fail("taylor order must be 1..4");
     return hook(H, 3, K, tx, nullptr, t, u, nullptr);
+}
+// evaluate! / evaluate_and_jacobian! at N points at once (the batched form of the operator API, SURVEY.md section 7 "minimum
+// slice"; what a host uses to check the residuals of many endpoints, e.g. the excess-solution check of an overdetermined
+// solve): x is n x N, u n x N, U (optional) n x n x N, one t for all points.
+int32_t hc_evaluate_batch(void* Hv, int64_t N, const double* x, const double* t, double* u, double* U) {
+    if (N < 0 || !Hv || !x || !t || !u) return fail("hc_evaluate_batch: bad arguments");
+    HomotopyH* H = (HomotopyH*)Hv;
+    const int n = H->dev.n;
+#ifdef HC_HOST_SIM
+    for (int64_t i = 0; i < N; ++i) {
+        const int rc = hook(Hv, U ? 2 : 0, 0, x + 2 * (size_t)n * i, nullptr, t, u + 2 * (size_t)n * i, U ? U + 2 * (size_t)n * n * i : nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+#else
+    std::lock_guard<std::mutex> lock(g_mutex);
+    try {
+        if (nodev()) throw std::string("HC_B200_NO_DEVICE is set: no compute calls");
+        ensure_init();
+        use_slot(0);
+        const int P = H->dev.P;
+        hc_options o; hc_options_default(&o);
+        KArgs A; memset(&A, 0, sizeof(A));
+        A.H = H->dev; A.H.N = 1; A.O = to_dev_options(&o);
+        PathMem<0> dummy;
+        const SlabSizes ss = carve(dummy, n, P, A.H.tape_cx, nullptr, nullptr);
+        if (ss.hot > kSmemMax) throw std::string("system too large for one shared-memory slab");
+        if (first_use((const void*)hc_hook_kernel)) CK(cudaFuncSetAttribute(hc_hook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+        const int64_t chunk = 8192;
+        const int64_t cap = N < chunk ? N : chunk;
+        if (cap == 0) return 0;
+        unsigned char* cold = (unsigned char*)dev_alloc((size_t)cap * ss.cold);
+        cx* dx = (cx*)dev_alloc((size_t)cap * n * 16);
+        cx* du = (cx*)dev_alloc((size_t)cap * n * 16);
+        cx* dU = U ? (cx*)dev_alloc((size_t)cap * n * n * 16) : nullptr;
+        A.cold = cold; A.cold_bytes = (int)ss.cold;
+        const cx tt = mk(t[0], t[1]);
+        cudaError_t le = cudaSuccess;
+        for (int64_t lo = 0; lo < N && le == cudaSuccess; lo += chunk) {
+            const int64_t cnt = N - lo < chunk ? N - lo : chunk;
+            h2d(dx, x + 2 * (size_t)n * lo, (size_t)cnt * n * 16);
+            hc_hook_kernel<<<(unsigned)cnt, 1, ss.hot, cur_stream()>>>(A, U ? 2 : 0, 0, dx, nullptr, tt, nullptr, du, dU);
+            le = cudaGetLastError();
+            d2h(u + 2 * (size_t)n * lo, du, (size_t)cnt * n * 16);
+            if (U) d2h(U + 2 * (size_t)n * n * lo, dU, (size_t)cnt * n * n * 16);
+            dev_sync();
+        }
+        dev_free(cold); dev_free(dx); dev_free(du); if (dU) dev_free(dU);
+        CK(le);
+    } catch (const std::string& e) { return fail(e); }
+    catch (...) { return fail("internal error"); }
+    return 0;
+#endif
 }
 int32_t hc_toric_set_weights(void* Hv, const double* w) {
     HomotopyH* H = (HomotopyH*)Hv;

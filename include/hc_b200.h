@@ -196,6 +196,9 @@ int32_t hc_evaluate_dd(void* H, const double* x_hi, const double* x_lo, const do
 int32_t hc_evaluate_and_jacobian(void* H, const double* x, const double* t, double* u, double* U);
 int32_t hc_taylor(void* H, int32_t K, const double* tx, const double* t, double* u);
 int32_t hc_toric_set_weights(void* H, const double* w);
+/* evaluate! / evaluate_and_jacobian! at N points at once (x: n x N, u: n x N, U: n x n x N or NULL, one t): the batched
+ * form of the operator API, e.g. for residual checks of many endpoints (reference src/overdetermined.jl:3-15) */
+int32_t hc_evaluate_batch(void* H, int64_t N, const double* x, const double* t, double* u, double* U);
 
 /* Specialised kernels (reference: `compile = true`, src/model_kit/compiled_system_homotopy.jl:178-243).  Large batches
  * (HC_B200_JIT_MIN_PATHS, default 8192; HC_B200_JIT = 0 | 1 | auto) are tracked by a kernel that is generated and

@@ -300,6 +300,19 @@ def test_two_pass_batches_on_the_heavy_tailed_configs(oracle, gpu, monkeypatch, 
     assert_classes_match(single, rg)
 
 
+def test_operator_api_batched(oracle, gpu):
+    """hc_evaluate_batch on the device: 20 000 points in one call (several launches of 8192 blocks) == the oracle"""
+    rng = np.random.default_rng(2)
+    _, H = straight_line(gpu, systems.katsura(6), 0.4 + 1.3j)
+    _, Ho = straight_line(oracle, systems.katsura(6), 0.4 + 1.3j)
+    X = rng.normal(size=(20000, 7)) + 1j * rng.normal(size=(20000, 7))
+    u, U = H.evaluate_batch(X, 0.37, jacobian=True)
+    for k in (0, 8191, 8192, 19999):
+        a, A = Ho.evaluate_and_jacobian(X[k], 0.37)
+        assert np.abs(u[k] - a).max() <= 1e-12 * max(1.0, np.abs(a).max()) and np.abs(U[k] - A).max() <= 1e-12 * max(1.0, np.abs(A).max())
+    assert np.abs(H.evaluate_batch(X[:100], 0.37) - u[:100]).max() == 0.0
+
+
 def test_homogeneous_and_overdetermined_inputs(oracle, gpu):
     """The host-side wrappers of SURVEY.md 8f-3 end in ordinary square systems for the device: a homogeneous system on a
     random affine chart (reference src/total_degree.jl:94-108) and an overdetermined one squared up with [I A]

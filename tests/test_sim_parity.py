@@ -27,6 +27,21 @@ def test_operator_api(oracle, sim):
         assert np.abs(a - b).max() <= 1e-13 * max(1.0, np.abs(a).max())
 
 
+def test_operator_api_batched(oracle, sim):
+    """hc_evaluate_batch: evaluate! / evaluate_and_jacobian! at many points in one call == the single-point calls"""
+    rng = np.random.default_rng(2)
+    td, H = straight_line(sim, systems.katsura(4), 0.4 + 1.3j)
+    _, Ho = straight_line(oracle, systems.katsura(4), 0.4 + 1.3j)
+    X = rng.normal(size=(37, 5)) + 1j * rng.normal(size=(37, 5))
+    u, U = H.evaluate_batch(X, 0.37, jacobian=True)
+    u2 = H.evaluate_batch(X, 0.37)
+    for k in (0, 5, 36):
+        a, A = Ho.evaluate_and_jacobian(X[k], 0.37)
+        assert np.abs(u[k] - a).max() <= 1e-13 * max(1.0, np.abs(a).max()) and np.abs(U[k] - A).max() <= 1e-13 * max(1.0, np.abs(A).max())
+        assert np.abs(u2[k] - a).max() <= 1e-13 * max(1.0, np.abs(a).max())
+    assert H.evaluate_batch(X[:0], 0.0).shape == (0, 5)
+
+
 def test_endgame_paths(oracle, sim):
     ro, rs = both(oracle, sim, lambda api: (lambda td_H: td_H[1].track_batch(td_H[0].start_solutions()))(straight_line(api, system_2x2(), 0.4 + 1.3j)))
     assert_batches_match(ro, rs)
