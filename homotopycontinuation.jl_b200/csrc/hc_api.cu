@@ -614,7 +614,12 @@ void setup_batch(DeviceBatch& D, HomotopyH* H, const hc_options* o, int mode, lo
     if (pl.engine == 1) D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8);
     else if (pl.engine == 0) D.A.cold = D.alloc<unsigned char>((size_t)pl.grid * pl.paths_per_block * pl.cold);
     D.A.stage_bytes = (int)pl.stage_bytes;
-    if (pl.engine == 2) { D.A.H.tape_cx = pl.jit_tape_cx; D.A.refill_min = env_int("HC_B200_REFILL_MIN", 8); }
+    if (pl.engine == 2) {
+        D.A.H.tape_cx = pl.jit_tape_cx;
+        D.A.refill_min = env_int("HC_B200_REFILL_MIN", 0);   // 0: adaptive (tpp_loop_sync), > 0: that many parked lanes per warp
+        const char* rk = getenv("HC_B200_REFILL_K");
+        D.A.refill_k = rk ? (float)atof(rk) : 1.0f;
+    }
     D.A.sync_cta = env_int("HC_B200_SYNC_CTA", 0);
 #ifndef HC_HOST_SIM
     // Two-pass batch: the specialised thread-per-path kernel gives up paths beyond HC_B200_HANDOFF_EG_STEPS endgame steps

@@ -24,6 +24,7 @@ struct KArgs {
     int stage_bytes;      // staged programs (0 when !stage)
     const int* cancel;    // optional host-mapped flag: non-zero = stop handing out new paths (src/solve.jl:685-707)
     int sync_cta;         // thread-per-path engines: the warps of a CTA start every round together (instruction-cache sharing)
+    float refill_k;       // lockstep kernels, refill_min <= 0 (adaptive refill threshold, tpp_loop_sync): scale of the cost model
 };
 
 #if defined(__CUDACC__)
@@ -84,7 +85,7 @@ __device__ __forceinline__ void tpp_loop(LaneT& L, const KArgs& A, const KArgs& 
         // barrier until the whole CTA is done
         if (A.sync_cta) { if (!__syncthreads_or((pend | act) != 0u)) break; }
         else if (pend == 0u && act == 0u) break;
-        if (__popc(pend) >= A.refill_min || act == 0u) {
+        if (__popc(pend) >= (A.refill_min > 0 ? A.refill_min : 8) || act == 0u) {
             if (L.ev != EV_NONE) L.event_finish(sA.R);
             const unsigned want = __ballot_sync(0xffffffffu, L.ev == EV_START);
             long long k = -1;
@@ -115,11 +116,26 @@ __device__ __forceinline__ void tpp_loop_sync(LaneT& L, const KArgs& A, const KA
     const unsigned lane = threadIdx.x & 31u;
     const int nwarps = (int)(blockDim.x >> 5);
     bool drained = false;  // warp-uniform
+    // How many parked lanes make an event round worth it.  An event round costs E regular rounds whatever the number of
+    // lanes in it; waiting for T lanes parks T / 2 of the B lanes on average.  With f events per round the overhead
+    // T / (2 B) + E f / T is least at T = sqrt(2 B E f): 50 - 64 lanes for paths of 100 steps (cyclic-7, katsura: E = 1),
+    // 130 - 200 for the 10-step paths of a parameter sweep (E = 4).  Thread 0 measures E (clock64 around the event part
+    // and around the step of a round) and f (parked lanes per round since the last event round) and publishes the next
+    // threshold through shared memory AFTER the step of the round -- every thread has passed a barrier of the step since
+    // it read the old value, and reads the new one behind the barriers at the top of the next round, so the decision
+    // stays CTA-uniform.  A.refill_min > 0 pins the threshold (lanes per warp); A.refill_k scales the model.
+    __shared__ int s_thr;
+    const int nthr0 = A.refill_min > 0 ? A.refill_min * nwarps : 8 * nwarps;
+    if (threadIdx.x == 0) s_thr = nthr0;
+    int since = 0, next_thr = nthr0;
+    float t_reg = 0.f, t_ev = 0.f;
     while (true) {
         const int npend = __syncthreads_count(L.ev != EV_NONE);
         const int nact = __syncthreads_count(L.ev == EV_NONE && L.phase != PH_IDLE);
         if (npend == 0 && nact == 0) break;
-        if (npend >= A.refill_min * nwarps || nact == 0) {
+        const int thr = s_thr;
+        if (npend >= thr || nact == 0) {
+            const long long c0 = clock64();
             if (L.ev != EV_NONE) L.event_finish(sA.R);
             const unsigned want = __ballot_sync(0xffffffffu, L.ev == EV_START);
             long long k = -1;
@@ -135,8 +151,27 @@ __device__ __forceinline__ void tpp_loop_sync(LaneT& L, const KArgs& A, const KA
                 if (L.ev == EV_START) k = base + __popc(want & ((1u << lane) - 1u));
             }
             if (L.ev != EV_NONE) L.event_begin(k, k >= 0 && k < N, sA.B, sA.R);
+            if (threadIdx.x == 0 && A.refill_min <= 0) {
+                const float dt = (float)(clock64() - c0);
+                t_ev = t_ev > 0.f ? 0.75f * t_ev + 0.25f * dt : dt;
+                if (nact != 0 && since > 0 && t_reg > 0.f) {
+                    const float f = (float)npend / (float)since, E = t_ev / t_reg;
+                    int t = (int)sqrtf(2.0f * A.refill_k * (float)blockDim.x * E * f);
+                    const int lo = 4 * nwarps, hi = 24 * nwarps;
+                    t = t < lo ? lo : (t > hi ? hi : t);
+                    next_thr = (thr + t + 1) >> 1;
+                }
+            }
+            since = 0;
         }
+        const long long c2 = clock64();
         L.template iterate_t<true>(L.ev == EV_NONE && L.phase != PH_IDLE);
+        if (threadIdx.x == 0 && A.refill_min <= 0) {
+            const float dt = (float)(clock64() - c2);
+            t_reg = t_reg > 0.f ? 0.9f * t_reg + 0.1f * dt : dt;
+            s_thr = next_thr;
+        }
+        ++since;
     }
 }
 #endif  // __CUDACC__
