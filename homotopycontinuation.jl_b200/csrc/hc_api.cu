@@ -745,7 +745,10 @@ void second_pass(DeviceBatch& D) {
     std::vector<int> rc((size_t)N);
     d2h(rc.data(), D.A.R.return_code, (size_t)N * 4);
     dev_sync();
+    // the paths handed over for their step count first: they are the ones that can run to max_endgame_steps, and the
+    // kernel ends when the last of them ends -- so they must not start behind the (many, short) extended-precision paths
     std::vector<long long> idx;
+    for (long long k = 0; k < N; ++k) if (rc[(size_t)k] == RC_HANDOFF_STEPS) idx.push_back(k);
     for (long long k = 0; k < N; ++k) if (rc[(size_t)k] == RC_HANDOFF) idx.push_back(k);
     D.handoff_paths = (long long)idx.size();
     if (idx.empty()) return;

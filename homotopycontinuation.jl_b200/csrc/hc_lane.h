@@ -43,7 +43,10 @@ enum Phase : int { PH_IDLE = 0, PH_PLAIN, PH_EG, PH_SING, PH_TORIC_A, PH_TORIC_B
 // handles the events of a warp together (event_finish / event_begin below), each kind of work from ONE call
 // site -- otherwise every lane would run its initialisations alone while the other 31 lanes of the warp wait.
 enum Event : int { EV_NONE = 0, EV_START, EV_TORIC_NEXT, EV_FINISH_EG, EV_FINISH_PLAIN, EV_FINISH_POLY_FAILED, EV_HANDOFF };
-enum { RC_HANDOFF = -1 };  // return_code of a path the first pass of a two-pass batch gave up on (never leaves the library)
+// return_code of a path the first pass of a two-pass batch gave up on (never leaves the library): because it switched to
+// extended precision (such paths end within a few hundred steps), or because of its step count (these can run to
+// max_endgame_steps: the second pass starts them first)
+enum { RC_HANDOFF = -1, RC_HANDOFF_STEPS = -2 };
 enum InitKind : int { IK_NONE = 0, IK_TRACKER, IK_EG, IK_POLY_A, IK_POLY_B };
 struct InitReq { int kind; cx t1, t0; double omega, mu, tau, max_init; bool keep_steps, ext; };
 enum Mode : int { MODE_ENDGAME = 0, MODE_TRACKER = 1, MODE_POLYHEDRAL = 2 };
@@ -117,7 +120,7 @@ struct Lane : Path<G, S> {
     // ---- polyhedral
     int toric_acc, toric_rej; double poly_maxw, saved_min_step;
     int cell;  // mixed cell of the path
-    int path_rounds, ho_steps, ho_eg_steps; bool ho_ext;  // tracker steps of the path so far (all stages); hand-off thresholds of the batch
+    int path_rounds, ho_steps, ho_eg_steps; bool ho_ext, ho_by_steps;  // tracker steps of the path so far (all stages); hand-off thresholds of the batch
     // ---- flop accounting totals of finished stages
     int c_fact, c_ldiv;
 
@@ -639,7 +642,7 @@ struct Lane : Path<G, S> {
             ev = EV_START;
         } else if (ev == EV_FINISH_PLAIN) { finish_plain(R); ev = EV_START; }
         else if (ev == EV_FINISH_POLY_FAILED) { finish_poly_failed(R); ev = EV_START; }
-        else if (ev == EV_HANDOFF) { if (g.lane == 0) R.return_code[pidx] = RC_HANDOFF; phase = PH_IDLE; ev = EV_START; }
+        else if (ev == EV_HANDOFF) { if (g.lane == 0) R.return_code[pidx] = ho_by_steps ? RC_HANDOFF_STEPS : RC_HANDOFF; phase = PH_IDLE; ev = EV_START; }
     }
     // Event round, part 2: free lanes take path k (if any is left), toric lanes decide their next stage; all
     // requested tracker initialisations then run from one call site.
@@ -674,7 +677,10 @@ struct Lane : Path<G, S> {
             case PH_EG: if (do_step) eg_post(ok); if (eg_code != EG_tracking) ev = EV_FINISH_EG; break;
             default: break;
         }
-        if (ho_steps > 0 && ev == EV_NONE && (++path_rounds > ho_steps || (ho_ext && extended_prec) || ((phase == PH_EG || phase == PH_SING) && steps_eg > ho_eg_steps))) ev = EV_HANDOFF;
+        if (ho_steps > 0 && ev == EV_NONE) {
+            const bool by_steps = ++path_rounds > ho_steps || ((phase == PH_EG || phase == PH_SING) && steps_eg > ho_eg_steps);
+            if (by_steps || (ho_ext && extended_prec)) { ev = EV_HANDOFF; ho_by_steps = by_steps; }
+        }
     }
     HC_HD void iterate(const BatchIn&, const DevResults&) { iterate_t<false>(true); }
 };
