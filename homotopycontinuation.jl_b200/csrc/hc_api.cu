@@ -33,6 +33,7 @@
 namespace hc {
 const void* hc_kernel_tpl(int slab);    // hc_track_tpl_kernel<slab>, slab = 12288 | 24576 | 49152
 const void* hc_kernel_group(int G);     // hc_track_kernel<G>, G = 8 | 32
+const void* hc_kernel_group_sync(int G);  // hc_track_kernel_sync<G>: its lockstep variant (second pass)
 }
 
 using namespace hc;
@@ -774,9 +775,12 @@ void second_pass(DeviceBatch& D) {
     if (!stage || stage_bytes + ss.hot > kSmemMax) { stage = 0; stage_bytes = 0; }
     if (ss.hot > kSmemMax) throw std::string("system too large for the lane-group engine");
     const long long N2 = (long long)idx.size();
-    // few paths: wide groups (latency of the single path decides); many: narrow groups (throughput)
+    // The lockstep kernel (HC_B200_HANDOFF_SYNC, default) runs a whole warp per path: its warps share what they fetch, which
+    // is what made 32 lanes lose on tritangents without it (12 warps per SM walking different code: 1.95 s; in lockstep
+    // 1.19 s; 8 lanes: 1.35 s).  Unsynchronised: wide groups for few paths (latency), narrow ones for many (throughput).
+    const bool sync2 = env_int("HC_B200_HANDOFF_SYNC", 1) != 0;
     int G = env_int("HC_B200_HANDOFF_GROUP", 0);
-    if (G != 8 && G != 32) G = N2 * 32 <= (long long)sms * 512 ? 32 : 8;
+    if (G != 8 && G != 32) G = (sync2 || N2 * 32 <= (long long)sms * 512) ? 32 : 8;
     int block = 256;
     const long long small = (N2 * G + sms - 1) / sms;
     while (block > 32 && block / 2 >= small) block /= 2;
@@ -796,7 +800,7 @@ void second_pass(DeviceBatch& D) {
     A2.B.N = N2; A2.B.index_map = D.map2; A2.B.handoff_steps = 0; A2.B.handoff_eg_steps = 0; A2.B.handoff_ext = 0;
     A2.stage = stage; A2.stage_bytes = (int)stage_bytes; A2.slab_bytes = (int)ss.hot; A2.cold_bytes = (int)ss.cold; A2.cold = D.cold2;
     dev_zero(A2.queue, sizeof(unsigned long long));
-    const void* kern = hc_kernel_group(G);
+    const void* kern = sync2 ? hc_kernel_group_sync(G) : hc_kernel_group(G);
     if (first_use(kern)) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
     if (!D.f0) { CK(cudaEventCreate(&D.f0)); CK(cudaEventCreate(&D.f1)); }
     CK(cudaEventRecord(D.f0, cur_stream()));
