@@ -775,12 +775,14 @@ void second_pass(DeviceBatch& D) {
     if (!stage || stage_bytes + ss.hot > kSmemMax) { stage = 0; stage_bytes = 0; }
     if (ss.hot > kSmemMax) throw std::string("system too large for the lane-group engine");
     const long long N2 = (long long)idx.size();
-    // The lockstep kernel (HC_B200_HANDOFF_SYNC, default) runs a whole warp per path: its warps share what they fetch, which
-    // is what made 32 lanes lose on tritangents without it (12 warps per SM walking different code: 1.95 s; in lockstep
-    // 1.19 s; 8 lanes: 1.35 s).  Unsynchronised: wide groups for few paths (latency), narrow ones for many (throughput).
-    const bool sync2 = env_int("HC_B200_HANDOFF_SYNC", 1) != 0;
+    // A warp per path (32 lanes).  If the handed-over paths fit the chip at once the kernel is the latency of its longest
+    // path and the warps run free (cyclooctane: 1.0 s; in lockstep 1.1 - 1.3 s); if they come in several waves the warps
+    // of a CTA run in lockstep and share what they fetch (tritangents, 6 735 paths, 12 warps per SM walking different
+    // code: 1.95 s; in lockstep 1.19 s; 8 lanes per path, unsynchronised: 1.35 s).  HC_B200_HANDOFF_SYNC / _GROUP pin either.
+    const int sync_env = env_int("HC_B200_HANDOFF_SYNC", -1);
+    const bool sync2 = sync_env >= 0 ? sync_env != 0 : N2 * 32 > (long long)sms * 512;
     int G = env_int("HC_B200_HANDOFF_GROUP", 0);
-    if (G != 8 && G != 32) G = (sync2 || N2 * 32 <= (long long)sms * 512) ? 32 : 8;
+    if (G != 8 && G != 32) G = 32;
     int block = 256;
     const long long small = (N2 * G + sms - 1) / sms;
     while (block > 32 && block / 2 >= small) block /= 2;
@@ -790,7 +792,7 @@ void second_pass(DeviceBatch& D) {
     const size_t smem = stage_bytes + (size_t)ppb * ss.hot;
     int per_sm = (int)((228 * 1024) / (smem + 2048));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm * block > 512) per_sm = 512 / block;
+    if (per_sm * block > 512) per_sm = 512 / block;                  // register file: 128 registers per thread
     const long long want = (N2 + ppb - 1) / ppb, cap = (long long)sms * per_sm;
     const int grid = (int)std::max(1LL, std::min(want, cap));
     const size_t cold_need = (size_t)grid * ppb * ss.cold;

@@ -50,8 +50,11 @@ __global__ void __launch_bounds__(256, 2) hc_track_kernel(const __grid_constant_
 // handling and one tracker step per round together (CTA-wide barriers inside tracker_step_t<true>), so that they fetch
 // the same code at the same time -- the unsynchronised kernel spends 55 % of its stall samples waiting for instructions
 // (profiles/r02b_ncu_pass2_group32_cyclooctane*.txt).  A group without work keeps the barriers company until the CTA is done.
+#ifndef HC_KERN_SYNC_MIN_CTAS
+#define HC_KERN_SYNC_MIN_CTAS 2   // (1 = 190 registers instead of 128: measured, no gain)
+#endif
 template <int G>
-__global__ void __launch_bounds__(256, 2) hc_track_kernel_sync(const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(256, HC_KERN_SYNC_MIN_CTAS) hc_track_kernel_sync(const __grid_constant__ KArgs A) {
     __shared__ KArgs sA;
     if (threadIdx.x == 0) sA = A;
     __syncthreads();
