@@ -376,6 +376,20 @@ def main():
             scaling_c5 = {"workload": f"bio-chemical network 1 parameter sweep, {args.c5_points} parameter points x {len(starts)} start solutions (whole job)",
                           "scaling": "strong", "n_gpus": world, "paths_per_step": n5, "value": 2 * n5 / dev5, "e2e": 2 * n5 / e2e5, "unit": "paths/s",
                           "entry_point": "hc_track_sweep", "class_counts": reduce_stats(result.statistics(r5).asdict())}
+            try:   # the same sweep with the results reduced on the device: 20 bytes per point come back (hc_track_sweep_counts)
+                from hcb200 import capi as _capi
+                _capi.track_sweep_counts(a5.handles["H"], w5.sweep_starts, w5.sweep_q, opts)
+                barrier()
+                tc0 = time.perf_counter()
+                for _ in range(2):
+                    cnt5 = _capi.track_sweep_counts(a5.handles["H"], w5.sweep_starts, w5.sweep_q, opts)
+                barrier()
+                (dtc,) = reduce_max(time.perf_counter() - tc0)
+                scaling_c5["e2e_counts_only"] = {"value": 2 * n5 / dtc, "unit": "paths/s", "entry_point": "hc_track_sweep_counts",
+                                                 "d2h_bytes_per_step": int(20 * (phi - plo)),
+                                                 "nonsingular_real_this_rank": [int(cnt5[:, 0].sum()), int(cnt5[:, 2].sum())]}
+            except Exception as e:
+                scaling_c5["e2e_counts_only"] = {"error": repr(e)[:200]}
             del a5, w5
         except Exception as e:
             scaling_c5 = {"error": repr(e)[:300]}

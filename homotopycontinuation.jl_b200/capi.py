@@ -184,6 +184,8 @@ class CApi:
                                                 c_int64_p, c_int64_p, c_double_p, c_double_p, c_double_p,
                                                 C.POINTER(ResultsDesc)], optional=True)
         f("evaluate_batch", C.c_int32, [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p], optional=True)
+        f("track_sweep_counts", C.c_int32, [C.c_void_p, C.POINTER(Options), C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_double,
+                                            c_int32_p], optional=True)
         f("unique_points_filter", C.c_int32, [C.c_int32, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_double, C.c_double,
                                               c_int64_p], optional=True)
         f("track_sweep", C.c_int32, [C.c_void_p, C.POINTER(Options), C.c_int64, c_double_p, C.c_int64, c_double_p,
@@ -458,3 +460,20 @@ def polyhedral_track_cells(api: CApi, Htoric: HomotopyHandle, Hcoeff: HomotopyHa
     if rc:
         raise RuntimeError(f"polyhedral_track_cells failed ({rc}): {_last_error(api)}")
     return res
+
+
+def track_sweep_counts(H: "HomotopyHandle", starts, target_params, options: Options | None = None, real_tol: float = 1e-6) -> np.ndarray:
+    """many_solve with the results reduced on the device (hc_track_sweep_counts): (M, 5) int32 array, per parameter point
+    [nonsingular, singular, real, at infinity, failed] over its start solutions."""
+    api = H.api
+    if getattr(api, "_track_sweep_counts", None) is None:
+        raise RuntimeError("device-side result reduction is an entry point of libhc_b200")
+    starts = np.ascontiguousarray(np.asarray(starts, dtype=np.complex128).reshape(-1, H.n))
+    q = np.ascontiguousarray(np.asarray(target_params, dtype=np.complex128).reshape(-1, H.P))
+    opts = options if options is not None else api.default_options()
+    counts = np.zeros((q.shape[0], 5), dtype=np.int32)
+    rc = api._track_sweep_counts(H.handle, C.byref(opts), starts.shape[0], _dp(starts.view(np.float64)), q.shape[0],
+                                 _dp(q.view(np.float64)), float(real_tol), _ip(counts))
+    if rc:
+        raise RuntimeError(f"track_sweep_counts failed ({rc}): {_last_error(api)}")
+    return counts

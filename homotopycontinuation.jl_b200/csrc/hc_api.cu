@@ -276,6 +276,29 @@ __global__ void hc_unique_filter_kernel(int n, long long M, const cx* known, lon
     out[i] = hit;
 }
 
+// Device-side post-processing of a many-parameter solve (reference: many_solve's `transform_result`,
+// src/solve.jl:422-430, 815-881, with a reduction such as nreal / nsolutions): per parameter point the counts
+// [nonsingular, singular, real, at infinity, failed] over its S paths (is_real: max |imag| < tol, src/path_result.jl:280-298;
+// no multiplicity clustering) -- 20 bytes per point leave the device instead of the PathResults of its paths.
+__global__ void hc_sweep_counts_kernel(DevResults R, int n, long long S, long long M, double tol, int* counts) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    int ns = 0, sg = 0, re = 0, inf = 0, fl = 0;
+    for (long long s = 0; s < S; ++s) {
+        const long long k = j * S + s;
+        const int rc = R.return_code[k];
+        if (rc == EG_success) {
+            if (R.singular[k]) ++sg; else ++ns;
+            double m = 0.0;
+            for (int i = 0; i < n; ++i) m = fmax(m, fabs(R.solution[k * n + i].im));
+            if (m < tol) ++re;
+        } else if (rc == EG_at_infinity || rc == EG_at_zero) ++inf;
+        else ++fl;
+    }
+    int* c = counts + 5 * j;
+    c[0] = ns; c[1] = sg; c[2] = re; c[3] = inf; c[4] = fl;
+}
+
 __global__ void hc_dfma_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double b = 1.0000001, c = 1e-9;
@@ -515,6 +538,8 @@ struct DeviceBatch {  // device-resident inputs and outputs of one batch
 };
 
 // How the start solutions (and the rows of the per-path parameters) of a batch are produced.
+struct SweepCounts { int32_t* counts = nullptr; long long S = 0; double real_tol = 1e-6; };  // hc_track_sweep_counts
+
 struct StartGen {
     long long start_rows = 0;           // > 0: `starts` holds this many rows, path k starts from row k % start_rows
     long long param_div = 0;            // > 0: the per-path parameter arrays hold one row per param_div consecutive paths
@@ -895,11 +920,11 @@ void ensure_init();
 
 int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const double* starts, const double* t1, const double* t0,
                const double* path_p, const double* path_q, const double* omega_mu, const int32_t* cell_index,
-               const double* cell_weights, int ncells, hc_results* out, const StartGen& sg = StartGen()) {
+               const double* cell_weights, int ncells, hc_results* out, const StartGen& sg = StartGen(), const SweepCounts* sc = nullptr) {
     std::lock_guard<std::mutex> lock(g_mutex);
     try {
         if (N <= 0) return 0;
-        if (!H || !o || !out) throw std::string("null handle / options / results");
+        if (!H || !o || (!out && !sc)) throw std::string("null handle / options / results");
 #ifndef HC_HOST_SIM
         if (nodev()) throw std::string("HC_B200_NO_DEVICE is set: this process can only build kernels, not track (there is no CPU fallback)");
 #endif
@@ -943,12 +968,26 @@ int track_impl(HomotopyH* H, const hc_options* o, int mode, long long N, const d
             ho_paths += D.handoff_paths; ho_ms = std::max(ho_ms, D.handoff_ms);
         }
         const double tC = now_ms();
+        if (sc) {
+#ifndef HC_HOST_SIM
+            for (auto& D : Ds) {   // per-point counts of the shard, 20 bytes per point back to the host
+                use_slot(D->slot);
+                const long long Mloc = D->N / sc->S, j0 = D->first / sc->S;
+                int* dc = D->alloc<int>((size_t)5 * Mloc);
+                hc_sweep_counts_kernel<<<(unsigned)((Mloc + 127) / 128), 128, 0, cur_stream()>>>(D->A.R, n, sc->S, Mloc, sc->real_tol, dc);
+                CK(cudaGetLastError());
+                d2h(sc->counts + 5 * j0, dc, (size_t)5 * Mloc * sizeof(int));
+            }
+#else
+            throw std::string("hc_track_sweep_counts is an entry point of the CUDA build");
+#endif
+        } else
         for (auto& D : Ds) fetch_results(*D, out);
         for (auto& D : Ds) { use_slot(D->slot); dev_sync(); }
         const double tD = now_ms();
         const DeviceBatch& D0 = *Ds[0];
         g_timing.h2d_ms = tB - tA; g_timing.kernel_ms = kms > 0 ? kms : tC - tB; g_timing.d2h_ms = tD - tC;
-        g_timing.h2d_bytes = h2d_bytes; g_timing.d2h_bytes = result_bytes(N, n, out->counters != nullptr);
+        g_timing.h2d_bytes = h2d_bytes; g_timing.d2h_bytes = sc ? (int64_t)(N / sc->S) * 20 : result_bytes(N, n, out->counters != nullptr);
         g_timing.grid = D0.plan.grid; g_timing.block = D0.plan.block; g_timing.lanes = D0.plan.group;
         g_timing.slab_bytes = D0.plan.engine != 0 ? (int64_t)D0.plan.lanes * (int64_t)(D0.plan.slab + D0.plan.cold) : (int64_t)D0.plan.slab;
         g_timing.devices = (int32_t)Ds.size(); g_timing.engine = D0.plan.engine;
@@ -1176,6 +1215,16 @@ int32_t hc_track_sweep(void* H, const hc_options* o, int64_t S, const double* st
     if (S <= 0 || M < 0 || !starts || !target_params) return fail("hc_track_sweep: starts and target parameters are required");
     StartGen sg; sg.start_rows = S; sg.param_div = S;
     return track_impl(h, o, MODE_ENDGAME, S * M, starts, nullptr, nullptr, nullptr, target_params, nullptr, nullptr, nullptr, 0, out, sg);
+}
+
+int32_t hc_track_sweep_counts(void* H, const hc_options* o, int64_t S, const double* starts, int64_t M, const double* target_params,
+                              double real_tol, int32_t* counts) {
+    HomotopyH* h = (HomotopyH*)H;
+    if (!h || h->dev.kind != H_PARAMETER) return fail("hc_track_sweep_counts needs a parameter homotopy");
+    if (S <= 0 || M < 0 || !starts || !target_params || !counts) return fail("hc_track_sweep_counts: starts, target parameters and counts are required");
+    StartGen sg; sg.start_rows = S; sg.param_div = S;
+    SweepCounts sc; sc.counts = counts; sc.S = S; sc.real_tol = real_tol > 0 ? real_tol : 1e-6;
+    return track_impl(h, o, MODE_ENDGAME, S * M, starts, nullptr, nullptr, nullptr, target_params, nullptr, nullptr, nullptr, 0, nullptr, sg, &sc);
 }
 
 int32_t hc_unique_points_filter(int32_t n, int64_t M, const double* known, int64_t N, const double* cand, double atol, double rtol,

@@ -175,6 +175,12 @@ int32_t hc_track_sweep(void* H, const hc_options* o, int64_t S, const double* st
  * stays on the host (monodromy.py mirrors it): three hc_track_batch calls per loop, p -> p1 -> p2 -> p. */
 int32_t hc_unique_points_filter(int32_t n, int64_t M, const double* known, int64_t N, const double* cand, double atol, double rtol,
                                 int64_t* match);
+/* The same sweep with the results reduced on the device (reference: many_solve with a `transform_result`
+ * that counts, src/solve.jl:422-430): counts is 5 x M int32 -- per parameter point [nonsingular, singular, real (max |imag|
+ * < real_tol, 0 = 1e-6), at infinity, failed] over its S paths, without multiplicity clustering.  20 bytes per point leave
+ * the device instead of the PathResults of its paths. */
+int32_t hc_track_sweep_counts(void* H, const hc_options* o, int64_t S, const double* starts, int64_t M,
+                              const double* target_params, double real_tol, int32_t* counts);
 void hc_get_timing(hc_timing* t);
 
 /* Device-resident variant for throughput measurement: inputs are uploaded once, results stay on

@@ -313,6 +313,26 @@ def test_operator_api_batched(oracle, gpu):
     assert np.abs(H.evaluate_batch(X[:100], 0.37) - u[:100]).max() == 0.0
 
 
+def test_sweep_with_device_side_counts(gpu):
+    """hc_track_sweep_counts (result post-processing on the device; reference many_solve with a counting
+    `transform_result`, src/solve.jl:422-430): per parameter point [nonsingular, singular, real, at infinity, failed] ==
+    the same counts taken on the host from the full PathResults of hc_track_sweep; only 20 bytes per point come back."""
+    from hcb200 import workloads
+    w = workloads.biochem_sweep(gpu, 4096)
+    h = w.build(gpu)
+    full = capi.track_sweep(h["H"], w.sweep_starts, w.sweep_q)
+    counts = capi.track_sweep_counts(h["H"], w.sweep_starts, w.sweep_q)
+    assert lib.timing().d2h_bytes == 20 * 4096
+    S = len(w.sweep_starts)
+    rc = full.return_code.reshape(4096, S)
+    ok = rc == 1
+    sing = full.singular.reshape(4096, S) != 0
+    real = (np.abs(full.solution.imag).max(axis=1) < 1e-6).reshape(4096, S)
+    want = np.stack([(ok & ~sing).sum(1), (ok & sing).sum(1), (ok & real).sum(1), np.isin(rc, (2, 3)).sum(1),
+                     (~ok & ~np.isin(rc, (2, 3))).sum(1)], axis=1)
+    assert np.array_equal(counts, want) and counts[:, 0].sum() > 0 and (counts.sum(axis=1) - counts[:, 2] == S).all()
+
+
 def test_homogeneous_and_overdetermined_inputs(oracle, gpu):
     """The host-side wrappers of SURVEY.md 8f-3 end in ordinary square systems for the device: a homogeneous system on a
     random affine chart (reference src/total_degree.jl:94-108) and an overdetermined one squared up with [I A]
